@@ -1,0 +1,180 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY (see oracle/mpgcn_oracle.py header).
+
+Run in the build container, where /root/reference is mounted:
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+The script imports the reference modules `MPGCN` and `GCN` from /root/reference by bare
+name (exactly how `Model_Trainer.py:5` imports them), instantiates the reference classes
+on CPU in fp32 at fixed seeds, runs forward + autograd backward, and stores inputs,
+parameters, outputs and gradients.  /root/reference does not exist on the GPU box, so
+the fixtures -- not the reference -- travel.  Nothing here is copied from the reference;
+it is only *called*.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("MPGCN_REFERENCE_DIR", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _load_ref(name):
+    """Import a reference module under a private name so a repo-local `MPGCN.py` shim can
+    never shadow it."""
+    spec = importlib.util.spec_from_file_location(f"_ref_{name}", os.path.join(REF, f"{name}.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _np(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def make_supports(ref_gcn, kind, K, N, batch, rng):
+    """Support stacks.  kind: 'dense' -> N(0,1)/sqrt(N) (no identity shortcut);
+    'rw' -> reference Adj_Processor('random_walk_diffusion', K-1) on a U[0,1) adjacency
+    (K supports, T_0 = I; GCN.py:80-82,128-138); 'cheb' -> chebyshev (lambda_max=2 fallback,
+    GCN.py:117-126); 'localpool' (K must be 1)."""
+    shape = (batch, N, N) if batch else (1, N, N)
+    if kind == "dense":
+        g = (rng.standard_normal((shape[0], K, N, N)) / np.sqrt(N)).astype(np.float32)
+    else:
+        adj = torch.from_numpy(rng.random(shape).astype(np.float32))
+        if kind == "rw":
+            proc = ref_gcn.Adj_Processor("random_walk_diffusion", K - 1)
+        elif kind == "cheb":
+            proc = ref_gcn.Adj_Processor("chebyshev", K - 1)
+        elif kind == "localpool":
+            assert K == 1
+            proc = ref_gcn.Adj_Processor("localpool", 1)
+        else:
+            raise ValueError(kind)
+        g = _np(proc.process(adj))
+        assert g.shape[1] == K, (g.shape, K)
+    return g if batch else g[0]
+
+
+BDGCN_CASES = [
+    # name, dynamic, K, N, B, C, H, act, bias, support kind
+    ("bdgcn_s_k1_n7", False, 1, 7, 2, 4, 5, "relu", True, "localpool"),
+    ("bdgcn_s_k3_n12", False, 3, 12, 2, 8, 8, "relu", True, "rw"),
+    ("bdgcn_s_k3_n12_linear_nobias", False, 3, 12, 2, 8, 8, None, False, "dense"),
+    ("bdgcn_d_k3_n10", True, 3, 10, 3, 8, 8, "relu", True, "rw"),
+    ("bdgcn_s_k6_n9", False, 6, 9, 1, 4, 6, "relu", True, "dense"),
+    ("bdgcn_s_k2_n16_cheb", False, 2, 16, 2, 6, 3, "relu", True, "cheb"),
+    ("bdgcn_s_k3_n47_c32", False, 3, 47, 1, 32, 32, "relu", True, "rw"),
+    ("bdgcn_d_k3_n33_c32", True, 3, 33, 2, 32, 32, "relu", True, "dense"),
+    ("bdgcn_s_k1_n50_c32", False, 1, 50, 2, 32, 32, "relu", True, "localpool"),
+]
+
+
+def gen_bdgcn(ref_mpgcn, ref_gcn):
+    for idx, (name, dyn, K, N, B, C, H, act, bias, gk) in enumerate(BDGCN_CASES):
+        rng = np.random.default_rng(1000 + idx)
+        torch.manual_seed(1000 + idx)
+        layer = ref_mpgcn.BDGCN(K=K, input_dim=C, hidden_dim=H, use_bias=bias,
+                                activation=torch.nn.ReLU if act == "relu" else None)
+        if bias:   # reference inits b to 0; use a non-trivial bias so the add is exercised
+            with torch.no_grad():
+                layer.b.copy_(torch.from_numpy(rng.standard_normal(H).astype(np.float32) * 0.1))
+        X = np.tanh(rng.standard_normal((B, N, N, C))).astype(np.float32)
+        d_out = rng.standard_normal((B, N, N, H)).astype(np.float32)
+        Xt = torch.from_numpy(X).requires_grad_(True)
+        if dyn:
+            go = make_supports(ref_gcn, gk, K, N, B, rng)
+            gd = make_supports(ref_gcn, gk, K, N, B, rng)
+            G = (torch.from_numpy(go), torch.from_numpy(gd))
+        else:
+            g = make_supports(ref_gcn, gk, K, N, 0, rng)
+            G = torch.from_numpy(g)
+        out = layer(Xt, G)
+        out.backward(torch.from_numpy(d_out))
+        rec = dict(X=X, W=_np(layer.W), d_out=d_out, out=_np(out), dX=_np(Xt.grad), dW=_np(layer.W.grad),
+                   K=K, act=act or "none", dynamic=int(dyn))
+        if bias:
+            rec.update(b=_np(layer.b), db=_np(layer.b.grad))
+        if dyn:
+            rec.update(G_o=go, G_d=gd)
+        else:
+            rec.update(G=g)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print("wrote", name, "out", out.shape)
+
+
+LSTM_CASES = [("lstm_s50_t5_c8", 50, 5, 8), ("lstm_s96_t4_c32", 96, 4, 32), ("lstm_s33_t12_c32", 33, 12, 32)]
+
+
+def gen_lstm():
+    for idx, (name, S, T, C) in enumerate(LSTM_CASES):
+        rng = np.random.default_rng(2000 + idx)
+        torch.manual_seed(2000 + idx)
+        lstm = torch.nn.LSTM(input_size=1, hidden_size=C, num_layers=1, batch_first=True)   # MPGCN.py:69
+        x = (rng.random((S, T, 1)) * 8).astype(np.float32)       # log1p(flow)-like range
+        d_h = rng.standard_normal((S, C)).astype(np.float32)
+        xt = torch.from_numpy(x).requires_grad_(True)
+        h0 = torch.zeros(1, S, C)
+        out, _ = lstm(xt, (h0, h0.clone()))                      # MPGCN.py:80-87,103
+        hT = out[:, -1, :]                                       # MPGCN.py:104
+        hT.backward(torch.from_numpy(d_h))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x, d_hT=d_h, hT=_np(hT), dx=_np(xt.grad),
+                            w_ih=_np(lstm.weight_ih_l0), w_hh=_np(lstm.weight_hh_l0),
+                            b_ih=_np(lstm.bias_ih_l0), b_hh=_np(lstm.bias_hh_l0),
+                            dw_ih=_np(lstm.weight_ih_l0.grad), dw_hh=_np(lstm.weight_hh_l0.grad),
+                            db_ih=_np(lstm.bias_ih_l0.grad), db_hh=_np(lstm.bias_hh_l0.grad))
+        print("wrote", name)
+
+
+MODEL_CASES = [
+    # name, N, K_supports, kernel, T, B, hidden        (M=2: static + dynamic, as Model_Trainer.py:47,107)
+    ("mpgcn_cfg1_n50_k1", 50, 1, "localpool", 4, 2, 32),        # BASELINE.json configs[0]
+    ("mpgcn_n6_k3", 6, 3, "rw", 3, 2, 8),
+    ("mpgcn_n20_k3_h32", 20, 3, "rw", 5, 2, 32),
+]
+
+
+def gen_model(ref_mpgcn, ref_gcn):
+    for idx, (name, N, K, gk, T, B, hid) in enumerate(MODEL_CASES):
+        rng = np.random.default_rng(3000 + idx)
+        torch.manual_seed(3000 + idx)
+        model = ref_mpgcn.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=hid, lstm_num_layers=1,
+                                gcn_hidden_dim=hid, gcn_num_layers=3, num_nodes=N, user_bias=True,
+                                activation=torch.nn.ReLU)        # Model_Trainer.py:47-56
+        x_seq = (rng.random((B, T, N, N, 1)) * 8).astype(np.float32)
+        g_static = make_supports(ref_gcn, gk, K, N, 0, rng)
+        g_o = make_supports(ref_gcn, gk, K, N, B, rng)
+        g_d = make_supports(ref_gcn, gk, K, N, B, rng)
+        d_y = rng.standard_normal((B, 1, N, N, 1)).astype(np.float32)
+        y = model(x_seq=torch.from_numpy(x_seq), G_list=[torch.from_numpy(g_static), (torch.from_numpy(g_o), torch.from_numpy(g_d))])
+        y.backward(torch.from_numpy(d_y))
+        rec = dict(x_seq=x_seq, G_static=g_static, G_o=g_o, G_d=g_d, d_y=d_y, y=_np(y), K=K, hidden=hid)
+        for k, v in model.state_dict().items():
+            rec["param:" + k] = _np(v)
+        for k, p in model.named_parameters():
+            rec["grad:" + k] = _np(p.grad)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print("wrote", name, "y", y.shape)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if not os.path.isdir(REF):
+        sys.exit(f"reference not found at {REF}; fixtures can only be regenerated in the build container")
+    ref_mpgcn = _load_ref("MPGCN")
+    ref_gcn = _load_ref("GCN")
+    gen_bdgcn(ref_mpgcn, ref_gcn)
+    gen_lstm()
+    gen_model(ref_mpgcn, ref_gcn)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,84 @@
+"""Pin the CPU oracle (oracle/mpgcn_oracle.py) against golden vectors produced by the
+unmodified reference classes (oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from oracle import mpgcn_oracle as orc
+
+TOL = 2e-5      # fp32 summation-order noise between torch (bmm) and numpy (einsum)
+
+
+def _check(a, ref, tol=TOL, what=""):
+    linf, l2 = orc.rel_errors(a, ref)
+    assert linf <= tol and l2 <= tol, f"{what}: rel_Linf={linf:.3e} rel_L2={l2:.3e} > {tol}"
+
+
+def _graph(g):
+    return (g["G_o"], g["G_d"]) if int(g["dynamic"]) else g["G"]
+
+
+@pytest.mark.parametrize("name", golden_names("bdgcn_"))
+def test_bdgcn_forward_backward_matches_reference(name):
+    g = load_golden(name)
+    act = None if str(g["act"]) == "none" else "relu"
+    b = g.get("b")
+    out = orc.bdgcn_forward(g["X"], _graph(g), g["W"], b, act)
+    _check(out, g["out"], what="out")
+    dX, dW, db = orc.bdgcn_backward(g["X"], _graph(g), g["W"], b, act, g["d_out"])
+    _check(dX, g["dX"], what="dX")
+    _check(dW, g["dW"], what="dW")
+    if b is not None:
+        _check(db, g["db"], what="db")
+
+
+@pytest.mark.parametrize("name", golden_names("bdgcn_"))
+def test_factored_order_equals_unfactored(name):
+    g = load_golden(name)
+    act = None if str(g["act"]) == "none" else "relu"
+    X64 = g["X"].astype(np.float64)
+    G = _graph(g)
+    G64 = tuple(a.astype(np.float64) for a in G) if isinstance(G, tuple) else G.astype(np.float64)
+    b = g.get("b")
+    ref = orc.bdgcn_forward(X64, G64, g["W"].astype(np.float64), None if b is None else b.astype(np.float64), act)
+    fac = orc.bdgcn_forward_factored(X64, G64, g["W"].astype(np.float64), None if b is None else b.astype(np.float64), act)
+    _check(fac, ref, tol=1e-12, what="factored")
+    _check(ref, g["out"], what="fp64 vs reference fp32")
+
+
+@pytest.mark.parametrize("name", golden_names("lstm_"))
+def test_lstm_matches_reference(name):
+    g = load_golden(name)
+    w = (g["w_ih"], g["w_hh"], g["b_ih"], g["b_hh"])
+    _check(orc.lstm_last_forward(g["x"], *w), g["hT"], what="hT")
+    dx, dwi, dwh, dbi, dbh = orc.lstm_last_backward(g["x"], *w, g["d_hT"])
+    for a, k in ((dx, "dx"), (dwi, "dw_ih"), (dwh, "dw_hh"), (dbi, "db_ih"), (dbh, "db_hh")):
+        _check(a, g[k], tol=5e-5, what=k)
+
+
+@pytest.mark.parametrize("name", golden_names("mpgcn_"))
+def test_model_matches_reference(name):
+    g = load_golden(name)
+    params = {k[6:]: v for k, v in g.items() if k.startswith("param:")}
+    G_list = [g["G_static"], (g["G_o"], g["G_d"])]
+    y, grads = orc.mpgcn_forward_backward(params, g["x_seq"], G_list, M=2, gcn_num_layers=3, d_y=g["d_y"])
+    _check(y, g["y"], tol=5e-5, what="y")
+    assert set(grads) == {k[5:] for k in g if k.startswith("grad:")}
+    for k, v in grads.items():
+        _check(v, g["grad:" + k], tol=2e-4, what=k)
+
+
+def test_properties_linearity_and_identity():
+    rng = np.random.default_rng(7)
+    B, N, C, H, K = 2, 6, 3, 4, 2
+    X1, X2 = rng.standard_normal((2, B, N, N, C))
+    G = rng.standard_normal((K, N, N))
+    W = rng.standard_normal((K * K * C, H))
+    f = lambda X: orc.bdgcn_forward(X, G, W, None, None)
+    np.testing.assert_allclose(f(2.0 * X1 - 3.0 * X2), 2.0 * f(X1) - 3.0 * f(X2), rtol=1e-10, atol=1e-10)
+    eye = np.stack([np.eye(N)] * K)
+    W4 = W.reshape(K, K, C, H)
+    np.testing.assert_allclose(orc.bdgcn_forward(X1, eye, W, None, None), X1 @ W4.sum(axis=(0, 1)), rtol=1e-10, atol=1e-10)
+    # static == dynamic with the static stack broadcast over the batch
+    Gb = np.broadcast_to(G, (B, K, N, N)).copy()
+    np.testing.assert_allclose(orc.bdgcn_forward(X1, (Gb, Gb), W, None, "relu"), orc.bdgcn_forward(X1, G, W, None, "relu"), rtol=1e-12, atol=1e-12)
