@@ -1,0 +1,92 @@
+/* mpgcn_b200 -- C ABI of the B200-native MPGCN hot path.
+ *
+ * The reference (underdoc-wang/MPGCN) has no FFI: its "plugin boundary" for this path is the
+ * Python module surface `MPGCN.BDGCN` / `MPGCN.MPGCN` (reference MPGCN.py:6-50, 54-112), whose
+ * arithmetic it delegates to torch.einsum / nn.LSTM.  These entry points are what a binding
+ * for that surface calls instead; `mpgcn_b200/MPGCN.py` is that binding (ctypes), and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
+ *     tensors are dense, row-major (last index fastest), fp32 (`float`), in the reference's own
+ *     layouts; nothing is mutated except the documented outputs;
+ *   - `stream` is a cudaStream_t (0 = default stream); all work is enqueued on it and the
+ *     calls return without synchronising;
+ *   - return value 0 = success; non-zero = failure, message from mpgcn_last_error()
+ *     (thread-local).  Nothing ever aborts the process;
+ *   - `precision`: 0 = exact fp32 CUDA-core kernels; 1 = fp16-operand / fp32-accumulate
+ *     tcgen05 tensor-core engine (requires C == H == 32, K <= 8);
+ *   - `workspace` is caller-owned scratch of at least the size the matching *_workspace_bytes
+ *     query returns (256-byte aligned); `saved` is the activation stash forward fills for
+ *     backward (size from mpgcn_bdgcn_saved_bytes, 64-byte aligned); pass NULL for inference.
+ */
+#ifndef MPGCN_B200_H_
+#define MPGCN_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPGCN_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MPGCN_API __attribute__((visibility("default")))
+#else
+#define MPGCN_API
+#endif
+
+MPGCN_API int mpgcn_abi_version(void);
+MPGCN_API const char* mpgcn_last_error(void);
+
+/* 1 if `precision` can serve this layer shape, else 0 (replaces nothing in the reference; the
+ * Python binding uses it to pick the kernel family). */
+MPGCN_API int mpgcn_bdgcn_precision_supported(int B, int N, int K, int C, int H, int precision);
+
+MPGCN_API size_t mpgcn_bdgcn_saved_bytes(int B, int N, int K, int C, int H, int precision);
+MPGCN_API size_t mpgcn_bdgcn_fwd_workspace_bytes(int B, int N, int K, int C, int H, int dynamic, int precision);
+MPGCN_API size_t mpgcn_bdgcn_bwd_workspace_bytes(int B, int N, int K, int C, int H, int dynamic, int precision);
+
+/* BDGCN.forward  (reference MPGCN.py:24-50):
+ *     out[b,m,e,h] = act( sum_{o,d,l} ( sum_{n,c} G_o[n,m] X[b,n,c,l] G_d[c,e] ) W[(o*K+d)*C+l, h] + bias[h] )
+ *   X   [B,N,N,C]
+ *   G_o, G_d : static graph  (dynamic == 0): both point to the same [K,N,N] support stack
+ *                                             (MPGCN.py:26-32);
+ *              dynamic graph (dynamic == 1): [B,K,N,N] origin / destination stacks, the two
+ *                                             members of the reference's tuple (MPGCN.py:34-40)
+ *   W   [K*K*C, H]   bias [H] or NULL (use_bias=False)   act: 0 = None, 1 = ReLU (MPGCN.py:13,49)
+ *   out [B,N,N,H] */
+MPGCN_API int mpgcn_bdgcn_forward(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, const float* bias, int act,
+                        float* out, void* saved, void* workspace, size_t workspace_bytes, int B, int N, int K, int C, int H,
+                        int precision, void* stream);
+
+/* Gradients autograd derives through MPGCN.py:24-50 (loss.backward(), Model_Trainer.py:114).
+ *   d_out [B,N,N,H], out = forward output (for the ReLU mask), saved = forward stash
+ *   dX [B,N,N,C] or NULL (input needs no grad), dW [K*K*C,H], db [H] or NULL */
+MPGCN_API int mpgcn_bdgcn_backward(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
+                         const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
+                         int K, int C, int H, int precision, void* stream);
+
+/* nn.LSTM(input_size=1, hidden=C, layers=1, batch_first) over the B*NN OD cells with zero initial
+ * state, returning only the last hidden state (reference MPGCN.py:69,80-87,100-104).
+ *   x_seq [B,T,NN] (= the model input [B,T,N,N,1] unchanged, NN = N*N)
+ *   w_ih [4C,1], w_hh [4C,C], b_ih [4C], b_hh [4C]   (gate order i,f,g,o)
+ *   hT   [B*NN, C] */
+MPGCN_API int mpgcn_lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
+                            int B, int T, long long NN, int C, void* stream);
+/* BPTT for the above. d_hT [B*NN,C]; outputs d_w_ih [4C], d_w_hh [4C,C], d_b_ih [4C], d_b_hh [4C];
+ * d_x [B,T,NN] or NULL. */
+MPGCN_API int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                             const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
+                             long long NN, int C, void* stream);
+
+/* Test / diagnostics only: byte offset of an intermediate inside the precision-1 workspace
+ * (which: 0 X16, 1 Gd16, 2 Go16, 3 W16, 4 U16 forward; 10 dP16, 11 Gd16, 12 Go16, 13 V16, 14 Y16, 15 Wq16,
+ * 16 dW partials backward; 17 = number of dW split-K slices). */
+MPGCN_API long long mpgcn_debug_tc_workspace_offset(int which, int B, int N, int K, int dynamic);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPGCN_B200_H_ */

@@ -1,0 +1,74 @@
+"""ctypes binding of libmpgcn_b200.so (C ABI: include/mpgcn_b200.h).
+
+The shared library is built in-tree by `mpgcn_b200/csrc/Makefile` (`__graft_entry__.build()`),
+for sm_100a only.  There is deliberately no fallback: if the library is missing or a call
+fails, a RuntimeError is raised -- the product never silently computes on another path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpgcn_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+PREC_FP32 = 0      # exact fp32 CUDA-core kernels
+PREC_FP16_TC = 1   # fp16 operands / fp32 accumulate on tcgen05 tensor cores
+
+_lib = None
+
+_c_f = ctypes.c_void_p   # device pointers travel as void*
+_SIGS = {
+    "mpgcn_abi_version": (ctypes.c_int, []),
+    "mpgcn_last_error": (ctypes.c_char_p, []),
+    "mpgcn_bdgcn_precision_supported": (ctypes.c_int, [ctypes.c_int] * 6),
+    "mpgcn_bdgcn_saved_bytes": (ctypes.c_size_t, [ctypes.c_int] * 6),
+    "mpgcn_bdgcn_fwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 7),
+    "mpgcn_bdgcn_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 7),
+    "mpgcn_bdgcn_forward": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int, _c_f, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, ctypes.c_size_t]
+                            + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    "mpgcn_bdgcn_backward": (ctypes.c_int, [_c_f, _c_f, _c_f, _c_f, ctypes.c_int, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, _c_f,
+                                            ctypes.c_size_t] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    "mpgcn_debug_tc_workspace_offset": (ctypes.c_longlong, [ctypes.c_int] * 5),
+    "mpgcn_lstm_last_forward": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
+    "mpgcn_lstm_last_backward": (ctypes.c_int, [_c_f] * 11 + [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j", str(max(1, (os.cpu_count() or 2)))], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building libmpgcn_b200.so failed (see output above)")
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"mpgcn_b200: CUDA library {LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"or `make -C {CSRC}`. There is no CPU / PyTorch fallback for the hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mpgcn_abi_version() != 1:
+        raise RuntimeError("mpgcn_b200: ABI version mismatch between the Python binding and libmpgcn_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().mpgcn_last_error()
+        raise RuntimeError(f"mpgcn_b200.{what} failed: {msg.decode() if msg else 'unknown error'}")

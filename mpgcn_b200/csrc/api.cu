@@ -1,0 +1,99 @@
+// extern "C" entry points of libmpgcn_b200 (declared in include/mpgcn_b200.h).
+#include "../../include/mpgcn_b200.h"
+
+#include "kernels.h"
+
+namespace mpgcn {
+size_t simt_saved_bytes(const BdgcnShape& s);
+size_t simt_fwd_ws_bytes(const BdgcnShape& s);
+size_t simt_bwd_ws_bytes(const BdgcnShape& s);
+size_t tc_saved_bytes(const BdgcnShape& s);
+size_t tc_fwd_ws_bytes(const BdgcnShape& s);
+size_t tc_bwd_ws_bytes(const BdgcnShape& s);
+long long tc_debug_offset(const BdgcnShape& s, int which);
+}  // namespace mpgcn
+
+using namespace mpgcn;
+
+static BdgcnShape mk(int B, int N, int K, int C, int H, int dynamic, int act) {
+  BdgcnShape s;
+  s.B = B; s.N = N; s.K = K; s.C = C; s.H = H; s.dynamic = dynamic; s.act = act;
+  return s;
+}
+
+static int check_shape(const BdgcnShape& s, int precision) {
+  MPGCN_CHECK(s.B >= 1 && s.N >= 1 && s.K >= 1 && s.C >= 1 && s.H >= 1, "bad BDGCN shape B=%d N=%d K=%d C=%d H=%d", s.B, s.N, s.K, s.C, s.H);
+  MPGCN_CHECK(precision == PREC_FP32_SIMT || precision == PREC_FP16_TC, "unknown precision %d", precision);
+  MPGCN_CHECK(s.act == 0 || s.act == 1, "unknown activation code %d", s.act);
+  if (precision == PREC_FP16_TC)
+    MPGCN_CHECK(tc_supported(s), "precision 1 (tcgen05) needs C == H == 32 and K <= 8 (got C=%d H=%d K=%d)", s.C, s.H, s.K);
+  return 0;
+}
+
+extern "C" {
+
+int mpgcn_abi_version(void) { return MPGCN_B200_ABI_VERSION; }
+const char* mpgcn_last_error(void) { return last_error(); }
+
+int mpgcn_bdgcn_precision_supported(int B, int N, int K, int C, int H, int precision) {
+  const BdgcnShape s = mk(B, N, K, C, H, 0, 0);
+  if (precision == PREC_FP32_SIMT) return B >= 1 && N >= 1 && K >= 1 && C >= 1 && H >= 1;
+  if (precision == PREC_FP16_TC) return tc_supported(s) ? 1 : 0;
+  return 0;
+}
+
+size_t mpgcn_bdgcn_saved_bytes(int B, int N, int K, int C, int H, int precision) {
+  const BdgcnShape s = mk(B, N, K, C, H, 0, 0);
+  return precision == PREC_FP16_TC ? tc_saved_bytes(s) : simt_saved_bytes(s);
+}
+size_t mpgcn_bdgcn_fwd_workspace_bytes(int B, int N, int K, int C, int H, int dynamic, int precision) {
+  const BdgcnShape s = mk(B, N, K, C, H, dynamic, 0);
+  return precision == PREC_FP16_TC ? tc_fwd_ws_bytes(s) : simt_fwd_ws_bytes(s);
+}
+size_t mpgcn_bdgcn_bwd_workspace_bytes(int B, int N, int K, int C, int H, int dynamic, int precision) {
+  const BdgcnShape s = mk(B, N, K, C, H, dynamic, 0);
+  return precision == PREC_FP16_TC ? tc_bwd_ws_bytes(s) : simt_bwd_ws_bytes(s);
+}
+
+int mpgcn_bdgcn_forward(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, const float* bias, int act,
+                        float* out, void* saved, void* workspace, size_t workspace_bytes, int B, int N, int K, int C, int H,
+                        int precision, void* stream) {
+  const BdgcnShape s = mk(B, N, K, C, H, dynamic ? 1 : 0, act);
+  if (int e = check_shape(s, precision)) return e;
+  MPGCN_CHECK(X && G_o && G_d && W && out && workspace, "mpgcn_bdgcn_forward: null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == PREC_FP16_TC) return bdgcn_forward_tc(s, X, G_o, G_d, W, bias, out, saved, workspace, workspace_bytes, st);
+  return bdgcn_forward_simt(s, X, G_o, G_d, W, bias, out, saved, workspace, workspace_bytes, st);
+}
+
+int mpgcn_bdgcn_backward(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
+                         const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
+                         int K, int C, int H, int precision, void* stream) {
+  const BdgcnShape s = mk(B, N, K, C, H, dynamic ? 1 : 0, act);
+  if (int e = check_shape(s, precision)) return e;
+  MPGCN_CHECK(d_out && out && G_o && G_d && W && saved && dW && workspace, "mpgcn_bdgcn_backward: null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == PREC_FP16_TC) return bdgcn_backward_tc(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, st);
+  return bdgcn_backward_simt(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, st);
+}
+
+long long mpgcn_debug_tc_workspace_offset(int which, int B, int N, int K, int dynamic) {
+  return tc_debug_offset(mk(B, N, K, 32, 32, dynamic, 0), which);
+}
+
+int mpgcn_lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
+                            int B, int T, long long NN, int C, void* stream) {
+  MPGCN_CHECK(x_seq && w_ih && w_hh && b_ih && b_hh && hT, "mpgcn_lstm_last_forward: null pointer argument");
+  return lstm_last_forward(x_seq, w_ih, w_hh, b_ih, b_hh, hT, B, T, NN, C, static_cast<cudaStream_t>(stream));
+}
+
+int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                             const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
+                             long long NN, int C, void* stream) {
+  MPGCN_CHECK(x_seq && w_ih && w_hh && b_ih && b_hh && d_hT && d_w_ih && d_w_hh && d_b_ih && d_b_hh,
+              "mpgcn_lstm_last_backward: null pointer argument");
+  return lstm_last_backward(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, B, T, NN, C,
+                            static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

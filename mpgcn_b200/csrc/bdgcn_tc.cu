@@ -1,0 +1,356 @@
+// BDGCN layer on the tcgen05 contraction engine (precision 1: fp16 operands, fp32 accumulate).
+//
+// Same factored algebra as bdgcn_simt.cu (reference: /root/reference/MPGCN.py:24-50; factoring:
+// SURVEY.md section 7.1); each contraction is one launch of tc::contract_kernel with operands
+// described by TMA tensor maps over fp16 copies living in the caller's workspace:
+//
+//   forward   X16 [B][n][c][l]      G16 [zg][K][N][Np]  (Np = N rounded up to 8, rows padded)
+//             Z16 [B][d][n][e][l]   (saved for backward)   U16 [B][o][n][e][h]
+//     FWD_A   Z = X x2 G_d          A_MN128 (G_d [c][e])     B = X16  (ch, c, n, b)
+//     FWD_MIX U = sum_d Z_d W[o,d]  A_K64   (Z plane)        B = W16  (h, (d,l), o)
+//     FWD_B   out = act(sum_o G_o^T x1 U_o + b)   A_MN128 (G flat [(o,n)][m])  B = U16 flat
+//   backward  dP16 [B][m][e][h]   V16 [B][o][n][e][h]   Y16 [B][d][n][e][l]   Wq16 [d][o][h][l]
+//     BWD_V   V = G_o x1 dPre       A_K128  (G_o [n][m])     B = dP16 flat
+//     BWD_DW  dW = Z^T V            A_MN64  (Z)              B = V16  (h, row, o, b)   split-K
+//     BWD_MIX Y = sum_o V_o W[o,d]^T  A_K64 (V plane)        B = Wq16 (l, (o,h), d)
+//     BWD_DX  dX = sum_d Y_d x2 G_d^T A_K128 (G_d [c][e])    B = Y16  (l, e, n, (b,d))
+#include "kernels.h"
+#include "tc_engine.cuh"
+
+#include <string.h>
+
+namespace mpgcn {
+
+using tc::GemmParams;
+
+namespace {
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline int pad8(int n) { return (n + 7) / 8 * 8; }
+const int kBig = 1 << 30;
+
+tc::OperandMap omap(int z_div, int z_mod, int z_mul, int seg_mul, int k_seg) {
+  tc::OperandMap m;
+  m.z_div = z_div; m.z_mod = z_mod; m.z_mul = z_mul; m.seg_mul = seg_mul; m.k_seg = k_seg;
+  return m;
+}
+
+void init_params(GemmParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.am = omap(1, 1, 0, 0, 0);
+  p.bm = omap(1, 1, 0, 0, 0);
+  p.kb_per_slice = 1;
+  p.ep.alpha = 1.f;
+}
+
+// support stack G16 [zg*K][N rows][Np]: as A_MN128 (dims m, k-rows, z) or A_K128 (dims k, m-rows, z)
+int map_support_mn(CUtensorMap* m, const __half* g16, int N, int Np, long long rows_per_z, long long nz) {
+  const uint64_t dims[4] = {(uint64_t)N, (uint64_t)rows_per_z, (uint64_t)nz, 1};
+  const uint64_t str[3] = {(uint64_t)Np * 2, (uint64_t)rows_per_z * Np * 2, (uint64_t)rows_per_z * Np * 2 * (uint64_t)nz};
+  const uint32_t box[4] = {64, 64, 1, 1};
+  return make_tmap_f16(m, g16, 4, dims, str, box, TMAP_SW128);
+}
+int map_support_k(CUtensorMap* m, const __half* g16, int N, int Np, long long nz) {
+  const uint64_t dims[4] = {(uint64_t)N, (uint64_t)N, (uint64_t)nz, 1};
+  const uint64_t str[3] = {(uint64_t)Np * 2, (uint64_t)N * Np * 2, (uint64_t)N * Np * 2 * (uint64_t)nz};
+  const uint32_t box[4] = {64, 128, 1, 1};
+  return make_tmap_f16(m, g16, 4, dims, str, box, TMAP_SW128);
+}
+// channel-chunk tensor T[z][r][k][32]: dims (ch, k, r, z)
+int map_chunks(CUtensorMap* m, const __half* t, long long k_rows, long long k_stride_el, long long r_count, long long r_stride_el,
+               long long z_count, long long z_stride_el, int box_k, int box_r) {
+  const uint64_t dims[4] = {32, (uint64_t)k_rows, (uint64_t)r_count, (uint64_t)z_count};
+  const uint64_t str[3] = {(uint64_t)k_stride_el * 2, (uint64_t)r_stride_el * 2, (uint64_t)z_stride_el * 2};
+  const uint32_t box[4] = {32, (uint32_t)box_k, (uint32_t)box_r, 1};
+  return make_tmap_f16(m, t, 4, dims, str, box, TMAP_SW64);
+}
+// flat tensor T[z][k][cols]: dims (col, k, z, 1), box (32, box_k)
+int map_flat(CUtensorMap* m, const __half* t, long long cols, long long k_rows, long long z_count, int box_k) {
+  const uint64_t dims[4] = {(uint64_t)cols, (uint64_t)k_rows, (uint64_t)z_count, 1};
+  const uint64_t str[3] = {(uint64_t)cols * 2, (uint64_t)cols * k_rows * 2, (uint64_t)cols * k_rows * 2 * (uint64_t)z_count};
+  const uint32_t box[4] = {32, (uint32_t)box_k, 1, 1};
+  return make_tmap_f16(m, t, 4, dims, str, box, TMAP_SW64);
+}
+// K-major plane tensor T[plane][rows][32]: dims (k=32, row, plane, 1), box (32, 128)
+int map_planes(CUtensorMap* m, const __half* t, long long rows, long long planes) {
+  const uint64_t dims[4] = {32, (uint64_t)rows, (uint64_t)planes, 1};
+  const uint64_t str[3] = {64, (uint64_t)rows * 64, (uint64_t)rows * 64 * (uint64_t)planes};
+  const uint32_t box[4] = {32, 128, 1, 1};
+  return make_tmap_f16(m, t, 4, dims, str, box, TMAP_SW64);
+}
+}  // namespace
+
+bool tc_supported(const BdgcnShape& s) { return s.C == 32 && s.H == 32 && s.K >= 1 && s.K <= 8 && s.N >= 1 && s.B >= 1; }
+
+static size_t n2(const BdgcnShape& s) { return (size_t)s.N * s.N; }
+static size_t g16_elems(const BdgcnShape& s) { return (size_t)(s.dynamic ? s.B : 1) * s.K * s.N * pad8(s.N); }
+
+size_t tc_saved_bytes(const BdgcnShape& s) { return (size_t)s.B * s.K * n2(s) * s.C * sizeof(__half); }
+
+// workspace layouts (byte offsets); also served to tests by mpgcn_debug_tc_workspace_offset()
+struct FwdLayout { size_t x16, gd16, go16, w16, u16, z16, total; };
+struct BwdLayout { size_t dp16, gd16, go16, v16, y16, wq16, partials, total; };
+static size_t take(size_t& off, size_t bytes) {
+  off = align_up(off, 1024);
+  const size_t r = off;
+  off += bytes;
+  return r;
+}
+static FwdLayout fwd_layout(const BdgcnShape& s) {
+  FwdLayout L;
+  size_t off = 0;
+  L.x16 = take(off, (size_t)s.B * n2(s) * 32 * 2);
+  L.gd16 = take(off, g16_elems(s) * 2);
+  L.go16 = take(off, g16_elems(s) * 2);
+  L.w16 = take(off, (size_t)s.K * s.K * 32 * 32 * 2);
+  L.u16 = take(off, (size_t)s.B * s.K * n2(s) * 32 * 2);
+  L.z16 = take(off, tc_saved_bytes(s));            // used only when the caller passes no `saved` buffer
+  L.total = align_up(off, 1024);
+  return L;
+}
+size_t tc_fwd_ws_bytes(const BdgcnShape& s) { return fwd_layout(s).total; }
+static int dw_slices(const BdgcnShape& s, int* kb_per_slice, int* kb_total) {
+  const int kbps = ceil_div((long long)n2(s), 64);
+  const int total = s.B * kbps;
+  const int MT = ceil_div(s.K, 4);
+  int want = device_sm_count() / MT;
+  if (want < 1) want = 1;
+  int per = ceil_div(total, want);
+  if (per < 1) per = 1;
+  *kb_per_slice = per;
+  *kb_total = total;
+  return ceil_div(total, per);
+}
+static BwdLayout bwd_layout(const BdgcnShape& s) {
+  BwdLayout L;
+  size_t off = 0;
+  L.dp16 = take(off, (size_t)s.B * n2(s) * 32 * 2);
+  L.gd16 = take(off, g16_elems(s) * 2);
+  L.go16 = take(off, g16_elems(s) * 2);
+  L.v16 = take(off, (size_t)s.B * s.K * n2(s) * 32 * 2);
+  L.y16 = take(off, (size_t)s.B * s.K * n2(s) * 32 * 2);
+  L.wq16 = take(off, (size_t)s.K * s.K * 32 * 32 * 2);
+  int per = 1, total = 1;
+  const int slices = dw_slices(s, &per, &total);
+  L.partials = take(off, (size_t)slices * ceil_div(s.K, 4) * 128 * s.K * 32 * 4);
+  L.total = align_up(off, 1024);
+  return L;
+}
+size_t tc_bwd_ws_bytes(const BdgcnShape& s) { return bwd_layout(s).total; }
+
+// which: 0 x16, 1 gd16, 2 go16, 3 w16, 4 u16 (forward); 10 dp16, 11 gd16, 12 go16, 13 v16, 14 y16, 15 wq16, 16 partials,
+// 17 number of dW slices (not an offset)
+long long tc_debug_offset(const BdgcnShape& s, int which) {
+  const FwdLayout F = fwd_layout(s);
+  const BwdLayout Bw = bwd_layout(s);
+  int per = 1, total = 1;
+  switch (which) {
+    case 0: return (long long)F.x16;
+    case 1: return (long long)F.gd16;
+    case 2: return (long long)F.go16;
+    case 3: return (long long)F.w16;
+    case 4: return (long long)F.u16;
+    case 10: return (long long)Bw.dp16;
+    case 11: return (long long)Bw.gd16;
+    case 12: return (long long)Bw.go16;
+    case 13: return (long long)Bw.v16;
+    case 14: return (long long)Bw.y16;
+    case 15: return (long long)Bw.wq16;
+    case 16: return (long long)Bw.partials;
+    case 17: return dw_slices(s, &per, &total);
+    default: return -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// individual contractions
+// ---------------------------------------------------------------------------------------
+// FWD_A:  Z16[b][d][n][e][l] = sum_c G_d[c][e] X16[b][n][c][l]
+static int run_fwd_a(const BdgcnShape& s, const __half* gd16, const __half* x16, __half* z16, cudaStream_t st) {
+  const int N = s.N, K = s.K, Np = pad8(N);
+  GemmParams p;
+  init_params(p);
+  if (int e = map_support_mn(&p.a_map, gd16, N, Np, N, (long long)(s.dynamic ? s.B : 1) * K)) return e;
+  if (int e = map_chunks(&p.b_map, x16, N, 32, N, (long long)N * 32, s.B, (long long)N * N * 32, 64, 8)) return e;
+  p.am = omap(1, s.dynamic ? kBig : K, 1, 0, 0);        // z = b*K + d -> support index
+  p.bm = omap(K, kBig, 1, 0, 0);                        // -> b
+  p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B * K; p.R = 8;
+  p.kb_total = p.kb_per_seg = ceil_div(N, 64);
+  p.ep.out = z16; p.ep.out_f16 = 1;
+  p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
+  p.ep.m_valid = N; p.ep.r_valid = N;
+  return tc::launch_contract(tc::A_MN128, 64, p, st);
+}
+
+// MIX: D16[b][r][row][32] = sum_{seg} A16[b][seg][row][32] * Wm16[r][(seg,32)][32]   (both channel mixes)
+static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, __half* d16, cudaStream_t st) {
+  const int K = s.K;
+  const long long NN = (long long)s.N * s.N;
+  GemmParams p;
+  init_params(p);
+  if (int e = map_planes(&p.a_map, a16, NN, (long long)s.B * K)) return e;
+  if (int e = map_chunks(&p.b_map, w16, (long long)K * 32, 32, K, (long long)K * 32 * 32, 1, (long long)K * K * 32 * 32, 32, K)) return e;
+  p.am = omap(1, kBig, K, 1, 0);        // plane = b*K + seg
+  p.bm = omap(1, 1, 0, 0, 32);          // k rows = seg*32
+  p.MT = ceil_div(NN, 128); p.NT = 1; p.Z = s.B; p.R = K;
+  p.kb_total = K; p.kb_per_seg = 1;
+  p.ep.out = d16; p.ep.out_f16 = 1;
+  p.ep.sZ = (long long)K * NN * 32; p.ep.sI = 32; p.ep.sR = NN * 32;
+  p.ep.m_valid = (int)NN; p.ep.r_valid = K;
+  return tc::launch_contract(tc::A_K64, 32, p, st);
+}
+
+// FWD_B: out[b][m][e][h] = act( sum_{(o,n)} Gflat[(o,n)][m] U16[b][(o,n)][e][h] + bias[h] )
+static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16, const float* bias, float* out, cudaStream_t st) {
+  const int N = s.N, K = s.K, Np = pad8(N);
+  GemmParams p;
+  init_params(p);
+  if (int e = map_support_mn(&p.a_map, go16, N, Np, (long long)K * N, s.dynamic ? s.B : 1)) return e;
+  if (int e = map_flat(&p.b_map, u16, (long long)N * 32, (long long)K * N, s.B, 64)) return e;
+  p.am = omap(1, s.dynamic ? kBig : 1, 1, 0, 0);
+  p.bm = omap(1, kBig, 1, 0, 0);
+  p.b_flat = 1;
+  p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;
+  p.kb_total = p.kb_per_seg = ceil_div((long long)K * N, 64);
+  p.ep.out = out; p.ep.out_f16 = 0;
+  p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
+  p.ep.m_valid = N; p.ep.r_valid = N;
+  p.ep.bias = bias; p.ep.relu = s.act;
+  return tc::launch_contract(tc::A_MN128, 64, p, st);
+}
+
+// BWD_V: V16[b][o][n][e][h] = sum_m G_o[n][m] dP16[b][m][e][h]
+static int run_bwd_v(const BdgcnShape& s, const __half* go16, const __half* dp16, __half* v16, cudaStream_t st) {
+  const int N = s.N, K = s.K, Np = pad8(N);
+  GemmParams p;
+  init_params(p);
+  if (int e = map_support_k(&p.a_map, go16, N, Np, (long long)(s.dynamic ? s.B : 1) * K)) return e;
+  if (int e = map_flat(&p.b_map, dp16, (long long)N * 32, N, s.B, 64)) return e;
+  p.am = omap(1, s.dynamic ? kBig : K, 1, 0, 0);        // z = b*K + o
+  p.bm = omap(K, kBig, 1, 0, 0);
+  p.b_flat = 1;
+  p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B * K; p.R = 8;
+  p.kb_total = p.kb_per_seg = ceil_div(N, 64);
+  p.ep.out = v16; p.ep.out_f16 = 1;
+  p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
+  p.ep.m_valid = N; p.ep.r_valid = N;
+  return tc::launch_contract(tc::A_K128, 64, p, st);
+}
+
+// BWD_DW: P[slice][mt][(d%4)*32+l][o][h] = sum over the slice's (b,row) range of Z16[b][d][row][l] V16[b][o][row][h]
+static int run_bwd_dw(const BdgcnShape& s, const __half* z16, const __half* v16, float* partials, int* slices_out, int* mt_out,
+                      cudaStream_t st) {
+  const int K = s.K;
+  const long long NN = (long long)s.N * s.N;
+  GemmParams p;
+  init_params(p);
+  if (int e = map_chunks(&p.a_map, z16, NN, 32, K, NN * 32, s.B, (long long)K * NN * 32, 64, 4)) return e;
+  if (int e = map_chunks(&p.b_map, v16, NN, 32, K, NN * 32, s.B, (long long)K * NN * 32, 64, K)) return e;
+  p.am = omap(1, 1, 0, 1, 0);           // z (slice) ignored; batch element = segment
+  p.bm = omap(1, 1, 0, 1, 0);
+  int per = 1, total = 1;
+  const int slices = dw_slices(s, &per, &total);
+  p.MT = ceil_div(K, 4); p.NT = 1; p.Z = slices; p.R = K;
+  p.kb_total = total; p.kb_per_seg = ceil_div(NN, 64);
+  p.split_k = 1; p.kb_per_slice = per;
+  p.ep.out = partials; p.ep.out_f16 = 0;
+  p.ep.sZ = (long long)p.MT * 128 * K * 32; p.ep.sI = (long long)K * 32; p.ep.sR = 32;
+  p.ep.m_valid = p.MT * 128; p.ep.r_valid = K;
+  *slices_out = slices;
+  *mt_out = p.MT;
+  return tc::launch_contract(tc::A_MN64, 64, p, st);
+}
+
+// BWD_DX: dX[b][n][c][l] = sum_{d,e} G_d[c][e] Y16[b][d][n][e][l]
+static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16, float* dX, cudaStream_t st) {
+  const int N = s.N, K = s.K, Np = pad8(N);
+  GemmParams p;
+  init_params(p);
+  if (int e = map_support_k(&p.a_map, gd16, N, Np, (long long)(s.dynamic ? s.B : 1) * K)) return e;
+  if (int e = map_chunks(&p.b_map, y16, N, 32, N, (long long)N * 32, (long long)s.B * K, (long long)N * N * 32, 64, 8)) return e;
+  p.am = omap(1, s.dynamic ? kBig : 1, s.dynamic ? K : 0, 1, 0);   // support index = (b*K) + d
+  p.bm = omap(1, kBig, K, 1, 0);                                    // plane = b*K + d
+  p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;
+  p.kb_per_seg = ceil_div(N, 64); p.kb_total = K * p.kb_per_seg;
+  p.ep.out = dX; p.ep.out_f16 = 0;
+  p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
+  p.ep.m_valid = N; p.ep.r_valid = N;
+  return tc::launch_contract(tc::A_K128, 64, p, st);
+}
+
+static int convert_supports(const BdgcnShape& s, const float* Go, const float* Gd, __half* go16, __half* gd16, const __half** go_used,
+                            cudaStream_t st) {
+  const size_t rows = (size_t)(s.dynamic ? s.B : 1) * s.K * s.N;
+  if (int e = cvt_f32_to_f16_padded(Gd, gd16, rows, s.N, pad8(s.N), st)) return e;
+  if (Go == Gd) {
+    *go_used = gd16;
+  } else {
+    if (int e = cvt_f32_to_f16_padded(Go, go16, rows, s.N, pad8(s.N), st)) return e;
+    *go_used = go16;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// layer forward / backward
+// ---------------------------------------------------------------------------------------
+int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const float* Gd, const float* W, const float* bias,
+                     float* out, void* saved, void* ws, size_t ws_bytes, cudaStream_t st) {
+  MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d K=%d)", s.C, s.H, s.K);
+  const size_t NN = n2(s);
+  const FwdLayout L = fwd_layout(s);
+  MPGCN_CHECK(ws_bytes >= L.total, "bdgcn_forward: workspace too small (%zu < %zu bytes)", ws_bytes, L.total);
+  MPGCN_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  uint8_t* wb = static_cast<uint8_t*>(ws);
+  __half* x16 = reinterpret_cast<__half*>(wb + L.x16);
+  __half* gd16 = reinterpret_cast<__half*>(wb + L.gd16);
+  __half* go16 = reinterpret_cast<__half*>(wb + L.go16);
+  __half* w16 = reinterpret_cast<__half*>(wb + L.w16);
+  __half* u16 = reinterpret_cast<__half*>(wb + L.u16);
+  __half* z16 = saved ? static_cast<__half*>(saved) : reinterpret_cast<__half*>(wb + L.z16);
+  MPGCN_CHECK((reinterpret_cast<uintptr_t>(z16) & 63) == 0, "`saved` buffer must be 64-byte aligned");
+
+  const __half* go_used = nullptr;
+  if (int e = cvt_f32_to_f16(X, x16, (size_t)s.B * NN * 32, st)) return e;
+  if (int e = convert_supports(s, Go, Gd, go16, gd16, &go_used, st)) return e;
+  if (int e = cvt_f32_to_f16(W, w16, (size_t)s.K * s.K * 32 * 32, st)) return e;
+  if (int e = run_fwd_a(s, gd16, x16, z16, st)) return e;
+  if (int e = run_mix(s, z16, w16, u16, st)) return e;
+  if (int e = run_fwd_b(s, go_used, u16, bias, out, st)) return e;
+  return 0;
+}
+
+int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out, const float* Go, const float* Gd, const float* W,
+                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, cudaStream_t st) {
+  MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d K=%d)", s.C, s.H, s.K);
+  MPGCN_CHECK(saved != nullptr, "bdgcn_backward: forward was run without a `saved` buffer");
+  const size_t NN = n2(s);
+  const __half* z16 = static_cast<const __half*>(saved);
+  const BwdLayout L = bwd_layout(s);
+  MPGCN_CHECK(ws_bytes >= L.total, "bdgcn_backward: workspace too small (%zu < %zu bytes)", ws_bytes, L.total);
+  MPGCN_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  uint8_t* wb = static_cast<uint8_t*>(ws);
+  __half* dp16 = reinterpret_cast<__half*>(wb + L.dp16);
+  __half* gd16 = reinterpret_cast<__half*>(wb + L.gd16);
+  __half* go16 = reinterpret_cast<__half*>(wb + L.go16);
+  __half* v16 = reinterpret_cast<__half*>(wb + L.v16);
+  __half* y16 = reinterpret_cast<__half*>(wb + L.y16);
+  __half* wq16 = reinterpret_cast<__half*>(wb + L.wq16);
+  float* partials = reinterpret_cast<float*>(wb + L.partials);
+
+  const __half* go_used = nullptr;
+  if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 32, st));
+  if (int e = relu_bwd_prep(d_out, out, s.act, dp16, nullptr, db, (size_t)s.B * NN * 32, 32, st)) return e;
+  if (int e = convert_supports(s, Go, Gd, go16, gd16, &go_used, st)) return e;
+  if (int e = run_bwd_v(s, go_used, dp16, v16, st)) return e;
+  int slices = 0, mt = 0;
+  if (int e = run_bwd_dw(s, z16, v16, partials, &slices, &mt, st)) return e;
+  if (int e = reduce_dw_partials(partials, dW, slices, mt, s.K, st)) return e;
+  if (dX) {
+    if (int e = permute_w_bwd(W, wq16, nullptr, s.K, 32, 32, st)) return e;
+    if (int e = run_mix(s, v16, wq16, y16, st)) return e;
+    if (int e = run_bwd_dx(s, gd16, y16, dX, st)) return e;
+  }
+  return 0;
+}
+
+}  // namespace mpgcn

@@ -1,0 +1,73 @@
+// Internal host-side declarations shared by the translation units of libmpgcn_b200.
+#pragma once
+
+#include "common.cuh"
+
+namespace mpgcn {
+
+const char* last_error();
+
+// ---- generic fp32 SIMT strided/batched contraction (simt_kernels.cu) ---------------------
+//   D[z](i,j) (+)= alpha * sum_seg sum_k A[z](i,k;seg) * B[z](k,j;seg)  (+ bias[j % bias_mod], ReLU)
+struct SgemmParams {
+  const float* A;
+  const float* B;
+  float* D;
+  int M, N, K;                 // K per segment
+  long long a_si, a_sk;        // element strides of A(i,k)
+  long long b_sk, b_sj;        // element strides of B(k,j)
+  long long d_si;              // D(i,j): j stride 1
+  int nseg;
+  long long a_sseg, b_sseg;
+  int Z0, Z1, Z2;              // batch z = (z0*Z1 + z1)*Z2 + z2
+  long long a_sz[3], b_sz[3], d_sz[3];
+  int ksplit;                  // > 1: split each segment's K into slices, atomically add into D (D pre-zeroed)
+  float alpha;
+  const float* bias;
+  int bias_mod;
+  int relu;
+};
+int simt_sgemm(const SgemmParams& p, cudaStream_t stream);
+
+// ---- elementwise / layout helpers (prep_kernels.cu) ---------------------------------------
+int cvt_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t s);
+// [rows][cols] fp32 -> [rows][ld] fp16 (ld >= cols, padding zeroed)
+int cvt_f32_to_f16_padded(const float* src, __half* dst, size_t rows, int cols, int ld, cudaStream_t s);
+// d_pre = d_out * (out > 0) (relu) or d_out; fp16 and/or fp32 output; db[h] += sum (db may be null; pre-zeroed)
+int relu_bwd_prep(const float* d_out, const float* out, int relu, __half* d_pre16, float* d_pre32, float* db, size_t n, int H,
+                  cudaStream_t s);
+// W[o][d][l][h] fp32 -> Wq[d][o][h][l] (fp16 and/or fp32)
+int permute_w_bwd(const float* W, __half* wq16, float* wq32, int K, int C, int H, cudaStream_t s);
+// dW[o][d][l][h] = sum_slices P[slice][mt][(d%4)*32 + l][o][h]   (C = H = 32)
+int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int K, cudaStream_t s);
+
+// ---- per-cell LSTM, last hidden state (lstm_kernels.cu) ------------------------------------
+int lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
+                      int B, int T, long long NN, int C, cudaStream_t s);
+int lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                       const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
+                       long long NN, int C, cudaStream_t s);
+
+// ---- BDGCN layer orchestration ---------------------------------------------------------------
+struct BdgcnShape {
+  int B, N, K, C, H;
+  int dynamic;      // supports are per-sample [B,K,N,N] pairs
+  int act;          // 0 none, 1 relu
+};
+enum Precision { PREC_FP32_SIMT = 0, PREC_FP16_TC = 1 };
+
+bool tc_supported(const BdgcnShape& s);
+size_t bdgcn_saved_bytes(const BdgcnShape& s, int precision);
+size_t bdgcn_fwd_workspace_bytes(const BdgcnShape& s, int precision);
+size_t bdgcn_bwd_workspace_bytes(const BdgcnShape& s, int precision);
+
+int bdgcn_forward_simt(const BdgcnShape& s, const float* X, const float* Go, const float* Gd, const float* W, const float* bias,
+                       float* out, void* saved, void* ws, size_t ws_bytes, cudaStream_t st);
+int bdgcn_backward_simt(const BdgcnShape& s, const float* d_out, const float* out, const float* Go, const float* Gd, const float* W,
+                        const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
+int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const float* Gd, const float* W, const float* bias,
+                     float* out, void* saved, void* ws, size_t ws_bytes, cudaStream_t st);
+int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out, const float* Go, const float* Gd, const float* W,
+                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace mpgcn

@@ -1,0 +1,260 @@
+// fp32 CUDA-core path: a strided / batched / segmented SGEMM that evaluates every
+// contraction of the BDGCN layer exactly in fp32 (precision mode 0), plus the elementwise
+// and layout kernels shared with the tensor-core path.
+//
+// This is the exact-arithmetic mode of the product (used for shapes the tcgen05 engine
+// does not cover -- channel counts other than 32 -- and as the on-device cross-check of
+// the fp16 tensor path).  It is NOT a CPU fallback: everything here runs on the GPU.
+#include "kernels.h"
+
+namespace mpgcn {
+
+// ---------------------------------------------------------------------------------------
+// SGEMM: 64 x BN output tile, 16-deep k slab, 256 threads, 4 x (BN/16) micro-tile
+// ---------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p, int tiles_m, int tiles_n) {
+  constexpr int BM = 64, BKS = 16, TN = BN / 16;
+  __shared__ float As[BKS][BM + 4];
+  __shared__ float Bs[BKS][BN + 4];
+
+  long long bid = blockIdx.x;
+  const int tn = (int)(bid % tiles_n); bid /= tiles_n;
+  const int tm = (int)(bid % tiles_m); bid /= tiles_m;
+  const int slice = (int)(bid % p.ksplit); bid /= p.ksplit;
+  const int z2 = (int)(bid % p.Z2); bid /= p.Z2;
+  const int z1 = (int)(bid % p.Z1); bid /= p.Z1;
+  const int z0 = (int)bid;
+
+  const float* A = p.A + z0 * p.a_sz[0] + z1 * p.a_sz[1] + z2 * p.a_sz[2];
+  const float* B = p.B + z0 * p.b_sz[0] + z1 * p.b_sz[1] + z2 * p.b_sz[2];
+  float* D = p.D + z0 * p.d_sz[0] + z1 * p.d_sz[1] + z2 * p.d_sz[2];
+
+  const int tid = threadIdx.x;
+  const int ty = tid / 16, tx = tid % 16;
+  const int i0 = tm * BM, j0 = tn * BN;
+
+  float acc[4][TN];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+
+  const int k_per_slice = (p.K + p.ksplit - 1) / p.ksplit;
+  const int k_lo = slice * k_per_slice;
+  const int k_hi = min(p.K, k_lo + k_per_slice);
+  const bool a_i_fast = (p.a_si == 1);
+  const bool b_j_fast = (p.b_sj == 1);
+
+  for (int seg = 0; seg < p.nseg; ++seg) {
+    const float* As_g = A + seg * p.a_sseg;
+    const float* Bs_g = B + seg * p.b_sseg;
+    for (int k0 = k_lo; k0 < k_hi; k0 += BKS) {
+#pragma unroll
+      for (int q = 0; q < (BM * BKS) / 256; ++q) {
+        const int idx = tid + q * 256;
+        const int ii = a_i_fast ? idx % BM : idx / BKS;
+        const int kk = a_i_fast ? idx / BM : idx % BKS;
+        const int gi = i0 + ii, gk = k0 + kk;
+        As[kk][ii] = (gi < p.M && gk < k_hi) ? As_g[gi * p.a_si + gk * p.a_sk] : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < (BN * BKS) / 256; ++q) {
+        const int idx = tid + q * 256;
+        const int jj = b_j_fast ? idx % BN : idx / BKS;
+        const int kk = b_j_fast ? idx / BN : idx % BKS;
+        const int gj = j0 + jj, gk = k0 + kk;
+        Bs[kk][jj] = (gj < p.N && gk < k_hi) ? Bs_g[gk * p.b_sk + gj * p.b_sj] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BKS; ++kk) {
+        float a[4], b[TN];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) a[x] = As[kk][ty * 4 + x];
+#pragma unroll
+        for (int y = 0; y < TN; ++y) b[y] = Bs[kk][tx * TN + y];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < TN; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+      }
+      __syncthreads();
+    }
+  }
+
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int gi = i0 + ty * 4 + x;
+    if (gi >= p.M) continue;
+#pragma unroll
+    for (int y = 0; y < TN; ++y) {
+      const int gj = j0 + tx * TN + y;
+      if (gj >= p.N) continue;
+      float v = acc[x][y] * p.alpha;
+      float* dst = D + gi * p.d_si + gj;
+      if (p.ksplit > 1) {
+        atomicAdd(dst, v);
+      } else {
+        if (p.bias) v += p.bias[gj % p.bias_mod];
+        if (p.relu) v = fmaxf(v, 0.f);
+        *dst = v;
+      }
+    }
+  }
+}
+
+int simt_sgemm(const SgemmParams& p, cudaStream_t stream) {
+  MPGCN_CHECK(p.M > 0 && p.N > 0 && p.K > 0 && p.nseg > 0 && p.ksplit > 0, "simt_sgemm: empty problem");
+  const int bn = (p.N <= 32) ? 32 : 64;
+  const int tiles_m = (p.M + 63) / 64;
+  const int tiles_n = (p.N + bn - 1) / bn;
+  const long long blocks = (long long)tiles_m * tiles_n * p.ksplit * p.Z0 * p.Z1 * p.Z2;
+  MPGCN_CHECK(blocks > 0 && blocks < (1ll << 31), "simt_sgemm: grid too large (%lld blocks)", blocks);
+  if (bn == 32)
+    sgemm_kernel<32><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_m, tiles_n);
+  else
+    sgemm_kernel<64><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_m, tiles_n);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// elementwise / layout kernels
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ __half f2h_sat(float x) {
+  // round-to-nearest-even, saturating to +-65504 instead of producing inf
+  return __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+}
+
+__global__ void cvt_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    __half2 a = __halves2half2(f2h_sat(v.x), f2h_sat(v.y));
+    __half2 b = __halves2half2(f2h_sat(v.z), f2h_sat(v.w));
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = pk;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = f2h_sat(src[i]);
+}
+
+static inline unsigned grid_for(size_t work_items, int threads) {
+  size_t b = (work_items + threads - 1) / threads;
+  const size_t cap = (size_t)device_sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+int cvt_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  MPGCN_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "cvt: misaligned pointers");
+  cvt_f16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(src, dst, n);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void cvt_f16_padded_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t rows, int cols, int ld) {
+  const size_t total = rows * (size_t)ld;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / ld;
+    const int c = (int)(i - r * ld);
+    dst[i] = (c < cols) ? f2h_sat(src[r * cols + c]) : __float2half_rn(0.f);
+  }
+}
+
+int cvt_f32_to_f16_padded(const float* src, __half* dst, size_t rows, int cols, int ld, cudaStream_t s) {
+  if (rows == 0) return 0;
+  cvt_f16_padded_kernel<<<grid_for(rows * ld, 256), 256, 0, s>>>(src, dst, rows, cols, ld);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// d_pre = d_out * [out > 0];  db[h] += sum over cells.  Thread's channel is fixed because the
+// grid stride is a multiple of H.
+__global__ void relu_bwd_prep_kernel(const float* __restrict__ d_out, const float* __restrict__ out, int relu,
+                                     __half* __restrict__ d16, float* __restrict__ d32, float* __restrict__ db, size_t n, int H) {
+  extern __shared__ float s_db[];   // [blockDim.x]
+  const size_t stride = (size_t)gridDim.x * blockDim.x;   // multiple of H by construction
+  float local = 0.f;
+  const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = first; i < n; i += stride) {
+    float g = d_out[i];
+    if (relu && !(out[i] > 0.f)) g = 0.f;
+    if (d16) d16[i] = f2h_sat(g);
+    if (d32) d32[i] = g;
+    local += g;
+  }
+  if (db) {
+    s_db[threadIdx.x] = local;
+    __syncthreads();
+    if ((int)threadIdx.x < H) {
+      // threads t, t+H, t+2H, ... of this block share channel (first % H)
+      float sum = 0.f;
+      for (int t = threadIdx.x; t < (int)blockDim.x; t += H) sum += s_db[t];
+      const int ch = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) % H);
+      atomicAdd(&db[ch], sum);
+    }
+  }
+}
+
+int relu_bwd_prep(const float* d_out, const float* out, int relu, __half* d16, float* d32, float* db, size_t n, int H,
+                  cudaStream_t s) {
+  if (n == 0) return 0;
+  MPGCN_CHECK(H >= 1 && H <= 1024, "relu_bwd_prep: H=%d unsupported", H);
+  int threads = (256 / H) * H;          // multiple of H so each thread keeps one channel
+  if (threads == 0) threads = H;
+  unsigned blocks = grid_for(n, threads);
+  relu_bwd_prep_kernel<<<blocks, threads, threads * sizeof(float), s>>>(d_out, out, relu, d16, d32, db, n, H);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void permute_w_bwd_kernel(const float* __restrict__ W, __half* __restrict__ q16, float* __restrict__ q32, int K, int C, int H) {
+  const int total = K * K * C * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // destination index i = ((d*K + o)*H + h)*C + l
+    const int l = i % C;
+    const int h = (i / C) % H;
+    const int o = (i / (C * H)) % K;
+    const int d = i / (C * H * K);
+    const float v = W[((size_t)(o * K + d) * C + l) * H + h];
+    if (q16) q16[i] = f2h_sat(v);
+    if (q32) q32[i] = v;
+  }
+}
+
+int permute_w_bwd(const float* W, __half* wq16, float* wq32, int K, int C, int H, cudaStream_t s) {
+  permute_w_bwd_kernel<<<grid_for((size_t)K * K * C * H, 256), 256, 0, s>>>(W, wq16, wq32, K, C, H);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void reduce_dw_kernel(const float* __restrict__ P, float* __restrict__ dW, int slices, int MT, int K) {
+  // dW index i = ((o*K + d)*32 + l)*32 + h ; partial row = (d%4)*32 + l of m-tile d/4
+  const int total = K * K * 32 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int h = i % 32;
+    const int l = (i / 32) % 32;
+    const int d = (i / 1024) % K;
+    const int o = i / (1024 * K);
+    const int mt = d / 4;
+    const size_t row = (size_t)mt * 128 + (d % 4) * 32 + l;
+    float sum = 0.f;
+    for (int s = 0; s < slices; ++s) sum += P[(((size_t)s * MT * 128 + row) * K + o) * 32 + h];
+    dW[i] = sum;
+  }
+}
+
+int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int K, cudaStream_t s) {
+  reduce_dw_kernel<<<grid_for((size_t)K * K * 1024, 256), 256, 0, s>>>(P, dW, slices, MT, K);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mpgcn

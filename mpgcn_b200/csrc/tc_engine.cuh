@@ -1,0 +1,304 @@
+// tcgen05 / TMA contraction engine: one persistent, warp-specialised kernel template that
+// evaluates every tensor-core contraction of the BDGCN layer (forward and backward).
+//
+//   D[z][i][(r,ch)] = alpha * sum_k A_z[k or i major] * B_z[k][(r,ch)]   (+ bias[ch], ReLU)
+//
+// * fp16 operands (kind::f16), fp32 accumulation in TMEM, M = 128 rows per tile,
+//   N = 32*R columns per tile (R <= 8 "channel chunks" of 32 = one 64-byte swizzle row).
+// * operands are staged by TMA into a multi-stage shared-memory ring in exactly the
+//   canonical UMMA layouts, so no thread ever touches operand bytes:
+//     A_MN128 : A is [k][m], m contiguous      (G_d for  Z = X x2 G_d ; G_o flat for  pre = sum G_o^T U)
+//     A_K128  : A is [m][k], k contiguous      (G_o for  V = G_o x1 dPre ; G_d for dX)
+//     A_K64   : A is [m][32], one 32-wide k block per plane (channel mixes Z->U, V->Y)
+//     A_MN64  : A is [k][chunk][32]            (Z for the weight gradient dW = Z^T V)
+//     B       : always [k][chunk r][32 ch], 64-byte rows, SWIZZLE_64B, MN-major
+// * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+//   warps 2..5 = epilogue (TMEM -> registers -> global).  Two TMEM accumulators
+//   (2 x 256 columns) let the epilogue of tile t overlap the MMAs of tile t+1.
+//
+// Reference math being evaluated: BDGCN.forward, /root/reference/MPGCN.py:24-50, in the
+// factored order of SURVEY.md section 7.1.
+#pragma once
+
+#include "common.cuh"
+
+namespace mpgcn {
+namespace tc {
+
+enum AKind : int { A_MN128 = 0, A_K128 = 1, A_K64 = 2, A_MN64 = 3 };
+
+// tile/k-block -> TMA coordinate map of one operand
+struct OperandMap {
+  int z_div, z_mod, z_mul;   // z' = ((z / z_div) % z_mod) * z_mul + seg * seg_mul
+  int seg_mul;
+  int k_seg;                 // k coordinate (elements) += seg * k_seg
+};
+
+struct Epilogue {
+  void* out;                 // float* or __half*
+  __half* out16;             // optional fp16 shadow of a float output (same strides), may be null
+  long long sZ, sI, sR;      // element strides of z, row i, chunk r (channel stride is 1)
+  int m_valid, r_valid;      // bounds on i and r
+  int out_f16;               // 1: out is __half
+  int relu;
+  const float* bias;         // [32] or null
+  float alpha;
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap a_map;
+  CUtensorMap b_map;
+  OperandMap am, bm;
+  int b_flat;                // 1: B tile = R separate (32 x BK) boxes of a flat [rows][cols] tensor
+  int MT, NT, Z;             // tile grid: tile id = (z * NT + nt) * MT + mt
+  int R;                     // 32-column chunks per tile
+  int kb_total, kb_per_seg;  // k-blocks over all segments / per segment
+  int split_k, kb_per_slice; // split-K: z is a k-slice [z*kb_per_slice, ...)
+  int stages;
+  Epilogue ep;
+};
+
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 256;
+
+template <int AK, int BK>
+struct Cfg {
+  static constexpr int A_STAGE = (AK == A_MN128) ? BK * 256 : (AK == A_K128) ? 128 * 128 : (AK == A_K64) ? 128 * 64 : 4 * BK * 64;
+  static constexpr bool A_MN = (AK == A_MN128) || (AK == A_MN64);
+  // byte advance of the A descriptor start address per UMMA (K = 16)
+  static constexpr uint32_t A_KSTEP = (AK == A_MN128) ? 16 * 128 : (AK == A_MN64) ? 16 * 64 : 32;
+  static constexpr uint32_t A_LBO = (AK == A_MN128) ? BK * 128 : (AK == A_MN64) ? BK * 64 : 16;
+  static constexpr uint32_t A_SBO = (AK == A_MN128 || AK == A_K128) ? 1024 : 512;
+  static constexpr uint32_t A_LAYOUT = (AK == A_MN128 || AK == A_K128) ? 2u : 4u;   // SW128 : SW64
+  static constexpr uint32_t B_KSTEP = 16 * 64;
+  static constexpr uint32_t B_LBO = BK * 64;
+  static constexpr uint32_t B_SBO = 512;
+  static_assert(AK != A_K128 || BK == 64, "K-major SW128 rows hold exactly 64 halves");
+  static_assert(AK != A_K64 || BK == 32, "K-major SW64 rows hold exactly 32 halves");
+  static_assert(BK % 16 == 0, "UMMA K is 16 for fp16");
+};
+
+__host__ __device__ inline size_t smem_bytes(int a_stage, int R, int BK, int stages) {
+  return 1024 /*align slack*/ + (size_t)stages * (a_stage + (size_t)R * BK * 64) + 512 /*barriers, tmem slot, bias*/;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* sbias, long long off, uint32_t (&acc)[32]) {
+  float v[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    float x = __uint_as_float(acc[c]) * ep.alpha;
+    if (ep.bias) x += sbias[c];
+    if (ep.relu) x = fmaxf(x, 0.f);
+    v[c] = x;
+  }
+  if (ep.out_f16) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out) + off);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __half2 h0 = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
+      __half2 h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
+      __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
+      __half2 h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2);
+      pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      dst[q] = pk;
+    }
+  } else {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    if (ep.out16) {
+      uint4* d16 = reinterpret_cast<uint4*>(ep.out16 + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __half2 h0 = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
+        __half2 h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
+        __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
+        __half2 h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        d16[q] = pk;
+      }
+    }
+  }
+}
+
+template <int AK, int BK>
+__global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<AK, BK>;
+  constexpr int A_STAGE = C::A_STAGE;
+  const int R = p.R;
+  const int B_STAGE = R * BK * 64;
+  const int S = p.stages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)S * A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)S * B_STAGE);
+  uint64_t* empty = full + S;
+  uint64_t* tfull = empty + S;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map);
+    tma_prefetch_desc(&p.b_map);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp == 2) sbias[lane] = p.ep.bias ? p.ep.bias[lane] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.MT * p.NT * p.Z;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mt = t % p.MT;
+        const int rest = t / p.MT;
+        const int nt = rest % p.NT;
+        const int z = rest / p.NT;
+        const int kb0 = p.split_k ? z * p.kb_per_slice : 0;
+        const int kb1 = p.split_k ? min(kb0 + p.kb_per_slice, p.kb_total) : p.kb_total;
+        const int zA0 = ((z / p.am.z_div) % p.am.z_mod) * p.am.z_mul;
+        const int zB0 = ((z / p.bm.z_div) % p.bm.z_mod) * p.bm.z_mul;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(A_STAGE + B_STAGE));
+          const int seg = kb / p.kb_per_seg;
+          const int kk = kb - seg * p.kb_per_seg;
+          const int zA = zA0 + seg * p.am.seg_mul;
+          const int zB = zB0 + seg * p.bm.seg_mul;
+          const int kA = kk * BK + seg * p.am.k_seg;
+          const int kB = kk * BK + seg * p.bm.k_seg;
+          uint8_t* a_dst = sA + (size_t)stage * A_STAGE;
+          uint8_t* b_dst = sB + (size_t)stage * B_STAGE;
+          if (AK == A_MN128) {          // dims (m, k, z, 1), two 64-wide m boxes
+            tma_load_4d(a_dst, &p.a_map, &full[stage], mt * 128, kA, zA, 0);
+            tma_load_4d(a_dst + BK * 128, &p.a_map, &full[stage], mt * 128 + 64, kA, zA, 0);
+          } else if (AK == A_K128 || AK == A_K64) {   // dims (k, m, z, 1)
+            tma_load_4d(a_dst, &p.a_map, &full[stage], kA, mt * 128, zA, 0);
+          } else {                      // A_MN64: dims (ch, k, chunk, z), 4 chunks per tile
+            tma_load_4d(a_dst, &p.a_map, &full[stage], 0, kA, mt * 4, zA);
+          }
+          if (!p.b_flat) {              // dims (ch, k, r, z)
+            tma_load_4d(b_dst, &p.b_map, &full[stage], 0, kB, nt * R, zB);
+          } else {                      // dims (col, k, z, 1): one 32-column box per chunk
+            for (int j = 0; j < R; ++j)
+              tma_load_4d(b_dst + (size_t)j * BK * 64, &p.b_map, &full[stage], (nt * R + j) * 32, kB, zB, 0);
+          }
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t idesc = umma_idesc_f16(128, 32 * R, C::A_MN ? 1 : 0, 1);
+    const uint64_t a_hi = umma_desc_hi(C::A_SBO, C::A_LAYOUT);
+    const uint64_t b_hi = umma_desc_hi(C::B_SBO, 4u);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int z = (t / p.MT) / p.NT;
+      const int kb0 = p.split_k ? z * p.kb_per_slice : 0;
+      const int kb1 = p.split_k ? min(kb0 + p.kb_per_slice, p.kb_total) : p.kb_total;
+      mbar_wait(&tempty[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = umma_desc(a_hi, a_addr + k * C::A_KSTEP, C::A_LBO);
+            const uint64_t bd = umma_desc(b_hi, b_addr + k * C::B_KSTEP, C::B_LBO);
+            umma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                 // frees this smem stage when the MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int quarter = warp & 3;     // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mt = t % p.MT;
+      const int rest = t / p.MT;
+      const int nt = rest % p.NT;
+      const int z = rest / p.NT;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int i = mt * 128 + quarter * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAccCols;
+      const long long base = (long long)z * p.ep.sZ + (long long)i * p.ep.sI;
+      for (int j = 0; j < R; ++j) {
+        uint32_t regs[32];
+        tmem_ld_32x32(t_row + (uint32_t)j * 32, regs);
+        tmem_ld_wait();
+        const int r = nt * R + j;
+        if (i < p.ep.m_valid && r < p.ep.r_valid) store_chunk(p.ep, sbias, base + (long long)r * p.ep.sR, regs);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+#endif  // __CUDACC__
+
+// Launch one contraction (implemented in tc_engine.cu).  ak/bk select the instantiation.
+int launch_contract(int ak, int bk, GemmParams& p, cudaStream_t stream);
+
+}  // namespace tc
+}  // namespace mpgcn

@@ -1,0 +1,156 @@
+"""Autograd-aware operators of the hot path, each a thin call into the C ABI.
+
+    bdgcn(X, G, W, b, activation)  <->  reference BDGCN.forward           (MPGCN.py:24-50)
+    lstm_last(x_seq, w_ih, w_hh, b_ih, b_hh)  <->  nn.LSTM(...)[:, -1, :]  (MPGCN.py:69,100-104)
+
+PyTorch supplies device memory, the current stream and the autograd tape; all arithmetic is in
+libmpgcn_b200.so.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+
+_PREC_NAMES = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16_TC, "auto": -1}
+
+
+def default_precision() -> str:
+    """'auto' (tensor cores whenever the shape allows), 'fp16' or 'fp32'.  Env: MPGCN_B200_PRECISION."""
+    return os.environ.get("MPGCN_B200_PRECISION", "auto")
+
+
+def resolve_precision(name, B, N, K, C, H) -> int:
+    name = default_precision() if name is None else name
+    if name not in _PREC_NAMES:
+        raise ValueError(f"unknown precision {name!r}; expected one of {sorted(_PREC_NAMES)}")
+    lib = _lib.load()
+    if name == "auto":
+        return _lib.PREC_FP16_TC if lib.mpgcn_bdgcn_precision_supported(B, N, K, C, H, _lib.PREC_FP16_TC) else _lib.PREC_FP32
+    code = _PREC_NAMES[name]
+    if not lib.mpgcn_bdgcn_precision_supported(B, N, K, C, H, code):
+        raise RuntimeError(f"precision {name!r} does not support B={B} N={N} K={K} C={C} H={H} (tensor path needs C == H == 32, K <= 8)")
+    return code
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"mpgcn_b200: {what} must be a CUDA tensor (got device {t.device}); the engine has no CPU path")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _scratch(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class _BDGCNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, G_o, G_d, W, b, dynamic: bool, act: int, precision):
+        lib = _lib.load()
+        B, N, N2, C = X.shape
+        K = G_o.shape[-3]
+        H = W.shape[1]
+        prec = resolve_precision(precision, B, N, K, C, H)
+        Xc, Goc, Wc = _f32c(X), _f32c(G_o), _f32c(W)
+        Gdc = Goc if G_d is G_o else _f32c(G_d)
+        bc = None if b is None else _f32c(b)
+        out = torch.empty((B, N, N, H), dtype=torch.float32, device=X.device)
+        need_grad = any(ctx.needs_input_grad)
+        saved = _scratch(lib.mpgcn_bdgcn_saved_bytes(B, N, K, C, H, prec), X.device) if need_grad else None
+        ws_bytes = lib.mpgcn_bdgcn_fwd_workspace_bytes(B, N, K, C, H, int(dynamic), prec)
+        ws = _scratch(ws_bytes, X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(lib.mpgcn_bdgcn_forward(_ptr(Xc), _ptr(Goc), _ptr(Gdc), int(dynamic), _ptr(Wc), _ptr(bc), act, _ptr(out),
+                                               _ptr(saved), _ptr(ws), ws.numel(), B, N, K, C, H, prec, _stream()), "bdgcn_forward")
+        ctx.shape = (B, N, K, C, H)
+        ctx.meta = (bool(dynamic), act, prec, b is not None)
+        ctx.save_for_backward(out, Goc, Gdc, Wc, saved if saved is not None else torch.empty(0, device=X.device))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        out, Goc, Gdc, Wc, saved = ctx.saved_tensors
+        B, N, K, C, H = ctx.shape
+        dynamic, act, prec, has_bias = ctx.meta
+        if saved.numel() == 0:
+            raise RuntimeError("mpgcn_b200.bdgcn: backward called but forward ran without requires_grad inputs")
+        d_out = _f32c(d_out)
+        need_dx = ctx.needs_input_grad[0]
+        dX = torch.empty((B, N, N, C), dtype=torch.float32, device=out.device) if need_dx else None
+        dW = torch.empty_like(Wc)
+        db = torch.empty(H, dtype=torch.float32, device=out.device) if has_bias else None
+        ws = _scratch(lib.mpgcn_bdgcn_bwd_workspace_bytes(B, N, K, C, H, int(dynamic), prec), out.device)
+        with torch.cuda.device(out.device):
+            _lib.check(lib.mpgcn_bdgcn_backward(_ptr(d_out), _ptr(out), _ptr(Goc), _ptr(Gdc), int(dynamic), _ptr(Wc), act, _ptr(saved),
+                                                _ptr(dX), _ptr(dW), _ptr(db), _ptr(ws), ws.numel(), B, N, K, C, H, prec, _stream()),
+                       "bdgcn_backward")
+        return dX, None, None, dW, db, None, None, None
+
+
+def bdgcn(X: torch.Tensor, G, W: torch.Tensor, b, relu: bool, precision=None) -> torch.Tensor:
+    """out = act(cat_{o,d}(G_o^T X G_d) W + b); G is a [K,N,N] tensor or a pair of [B,K,N,N] tensors."""
+    _require_cuda(X, "X")
+    if isinstance(G, torch.Tensor):
+        G_o = G_d = G
+        dynamic = False
+    else:
+        G_o, G_d = G
+        dynamic = True
+    for g in (G_o, G_d):
+        _require_cuda(g, "G")
+        if g.device != X.device:
+            raise RuntimeError("mpgcn_b200: X and G must be on the same device")
+    return _BDGCNFn.apply(X, G_o, G_d, W, b, dynamic, 1 if relu else 0, precision)
+
+
+class _LSTMLastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_seq, w_ih, w_hh, b_ih, b_hh):
+        lib = _lib.load()
+        B, T = x_seq.shape[0], x_seq.shape[1]
+        NN = x_seq[0, 0].numel()
+        C = w_hh.shape[1]
+        xc = _f32c(x_seq)
+        ws = [_f32c(t) for t in (w_ih, w_hh, b_ih, b_hh)]
+        hT = torch.empty((B * NN, C), dtype=torch.float32, device=x_seq.device)
+        with torch.cuda.device(x_seq.device):
+            _lib.check(lib.mpgcn_lstm_last_forward(_ptr(xc), *[_ptr(t) for t in ws], _ptr(hT), B, T, NN, C, _stream()), "lstm_last_forward")
+        ctx.dims = (B, T, NN, C)
+        ctx.save_for_backward(xc, *ws)
+        return hT
+
+    @staticmethod
+    def backward(ctx, d_hT):
+        lib = _lib.load()
+        xc, w_ih, w_hh, b_ih, b_hh = ctx.saved_tensors
+        B, T, NN, C = ctx.dims
+        d_hT = _f32c(d_hT)
+        dev = xc.device
+        g_wih, g_whh = torch.empty_like(w_ih), torch.empty_like(w_hh)
+        g_bih, g_bhh = torch.empty_like(b_ih), torch.empty_like(b_hh)
+        d_x = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.mpgcn_lstm_last_backward(_ptr(xc), _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(d_hT), _ptr(g_wih),
+                                                    _ptr(g_whh), _ptr(g_bih), _ptr(g_bhh), _ptr(d_x), B, T, NN, C, _stream()),
+                       "lstm_last_backward")
+        return d_x, g_wih, g_whh, g_bih, g_bhh
+
+
+def lstm_last(x_seq: torch.Tensor, w_ih, w_hh, b_ih, b_hh) -> torch.Tensor:
+    """h_T of a 1-layer, input-size-1 LSTM run over every OD cell of x_seq [B,T,N,N,1] -> [B*N*N, C]."""
+    _require_cuda(x_seq, "x_seq")
+    return _LSTMLastFn.apply(x_seq, w_ih, w_hh, b_ih, b_hh)

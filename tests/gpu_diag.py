@@ -1,0 +1,185 @@
+"""Stage-by-stage diagnostics of the tcgen05 path on a real GPU (not a pytest file).
+
+    python tests/gpu_diag.py [--out gpurun_out/diag.json] [--cases small|all]
+
+Each tensor-core contraction is checked in isolation: its inputs are read back from the
+workspace exactly as the kernel saw them (fp16), the expected result is computed with
+torch in fp32 from those inputs, and the kernel's output is compared.  Every case runs in
+a subprocess so a device-side trap cannot poison the following cases.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rel(a, ref):
+    import torch
+    a, ref = a.double(), ref.double()
+    d = (a - ref).abs()
+    return dict(linf=float(d.max() / ref.abs().max().clamp_min(1e-30)), l2=float(d.norm() / ref.norm().clamp_min(1e-30)),
+                nan=int(torch.isnan(a).sum()), absmax_ref=float(ref.abs().max()))
+
+
+def pattern(a, ref, dims):
+    """Which index classes are wrong: per-dim count of slices whose max error exceeds 1e-2 of the ref scale."""
+    import torch
+    d = (a.double() - ref.double()).abs() / ref.abs().max().clamp_min(1e-30)
+    out = {}
+    for i, name in enumerate(dims):
+        other = [j for j in range(d.dim()) if j != i]
+        bad = (d.amax(dim=other) > 1e-2)
+        idx = torch.nonzero(bad).flatten().tolist()
+        out[name] = dict(bad=len(idx), of=d.shape[i], first=idx[:12])
+    return out
+
+
+def run_case(B, N, K, dynamic, seed=0):
+    import torch
+    from mpgcn_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    C = H = 32
+    X = torch.tanh(torch.randn(B, N, N, C, generator=g)).to(dev)
+    if dynamic:
+        Go = (torch.randn(B, K, N, N, generator=g) / N ** 0.5).to(dev)
+        Gd = (torch.randn(B, K, N, N, generator=g) / N ** 0.5).to(dev)
+    else:
+        Go = Gd = (torch.randn(K, N, N, generator=g) / N ** 0.5).to(dev)
+    W = (torch.randn(K * K * C, H, generator=g) * (2.0 / (K * K * C + H)) ** 0.5).to(dev)
+    bias = (torch.randn(H, generator=g) * 0.1).to(dev)
+    d_out = torch.randn(B, N, N, H, generator=g).to(dev)
+    res = {}
+    Np = (N + 7) // 8 * 8
+    off = lambda w: lib.mpgcn_debug_tc_workspace_offset(w, B, N, K, int(dynamic))
+
+    def view16(buf, o, shape):
+        n = 1
+        for s_ in shape:
+            n *= s_
+        return buf[o:o + 2 * n].view(torch.float16).view(*shape)
+
+    # ---------------- forward ----------------
+    out = torch.empty(B, N, N, H, device=dev)
+    saved = torch.zeros(lib.mpgcn_bdgcn_saved_bytes(B, N, K, C, H, 1), dtype=torch.uint8, device=dev)
+    ws = torch.zeros(lib.mpgcn_bdgcn_fwd_workspace_bytes(B, N, K, C, H, int(dynamic), 1), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.mpgcn_bdgcn_forward(X.data_ptr(), Go.data_ptr(), Gd.data_ptr(), int(dynamic), W.data_ptr(), bias.data_ptr(), 1,
+                                       out.data_ptr(), saved.data_ptr(), ws.data_ptr(), ws.numel(), B, N, K, C, H, 1, st), "fwd")
+    torch.cuda.synchronize()
+    nz = B if dynamic else 1
+    x16 = view16(ws, off(0), (B, N, N, 32)).float()
+    gd16 = view16(ws, off(1), (nz, K, N, Np))[..., :N].float()
+    go16 = gd16 if (not dynamic) else view16(ws, off(2), (nz, K, N, Np))[..., :N].float()
+    w16 = view16(ws, off(3), (K, K, 32, 32)).float()
+    u16 = view16(ws, off(4), (B, K, N, N, 32)).float()
+    z16 = saved.view(torch.float16).view(B, K, N, N, 32).float()
+    res["cvt_x"] = rel(x16, X)
+    res["cvt_g"] = rel(gd16, Gd.view(nz, K, N, N))
+    gdb = gd16.expand(B, K, N, N)
+    gob = go16.expand(B, K, N, N)
+    z_ref = torch.einsum("bncl,bdce->bdnel", x16, gdb)
+    res["FWD_A"] = rel(z16, z_ref)
+    res["FWD_A_pattern"] = pattern(z16, z_ref, ["b", "d", "n", "e", "l"])
+    u_ref = torch.einsum("bdnel,odlh->boneh", z16, w16)
+    res["FWD_MIX"] = rel(u16, u_ref)
+    res["FWD_MIX_pattern"] = pattern(u16, u_ref, ["b", "o", "n", "e", "h"])
+    o_ref = torch.relu(torch.einsum("bonm,boneh->bmeh", gob, u16) + bias)
+    res["FWD_B"] = rel(out, o_ref)
+    res["FWD_B_pattern"] = pattern(out, o_ref, ["b", "m", "e", "h"])
+    # end-to-end vs fp32 factored reference
+    W4 = W.view(K, K, C, H)
+    Gdb = Gd.view(nz, K, N, N).expand(B, K, N, N)
+    Gob = Go.view(nz, K, N, N).expand(B, K, N, N)
+    z32 = torch.einsum("bncl,bdce->bdnel", X, Gdb)
+    u32 = torch.einsum("bdnel,odlh->boneh", z32, W4)
+    o32 = torch.relu(torch.einsum("bonm,boneh->bmeh", Gob, u32) + bias)
+    res["forward_vs_fp32"] = rel(out, o32)
+
+    # ---------------- backward ----------------
+    dX = torch.empty(B, N, N, C, device=dev)
+    dW = torch.empty(K * K * C, H, device=dev)
+    db = torch.empty(H, device=dev)
+    wsb = torch.zeros(lib.mpgcn_bdgcn_bwd_workspace_bytes(B, N, K, C, H, int(dynamic), 1), dtype=torch.uint8, device=dev)
+    _lib.check(lib.mpgcn_bdgcn_backward(d_out.data_ptr(), out.data_ptr(), Go.data_ptr(), Gd.data_ptr(), int(dynamic), W.data_ptr(), 1,
+                                        saved.data_ptr(), dX.data_ptr(), dW.data_ptr(), db.data_ptr(), wsb.data_ptr(), wsb.numel(),
+                                        B, N, K, C, H, 1, st), "bwd")
+    torch.cuda.synchronize()
+    dp16 = view16(wsb, off(10), (B, N, N, 32)).float()
+    v16 = view16(wsb, off(13), (B, K, N, N, 32)).float()
+    y16 = view16(wsb, off(14), (B, K, N, N, 32)).float()
+    wq16 = view16(wsb, off(15), (K, K, 32, 32)).float()       # [d][o][h][l]
+    dp_ref = d_out * (out > 0)
+    res["prep_dpre"] = rel(dp16, dp_ref)
+    res["db"] = rel(db, dp_ref.sum(dim=(0, 1, 2)))
+    v_ref = torch.einsum("bonm,bmeh->boneh", gob, dp16)
+    res["BWD_V"] = rel(v16, v_ref)
+    res["BWD_V_pattern"] = pattern(v16, v_ref, ["b", "o", "n", "e", "h"])
+    dw_ref = torch.einsum("bdnel,boneh->odlh", z16, v16).reshape(K * K * C, H)
+    res["BWD_DW"] = rel(dW, dw_ref)
+    res["BWD_DW_pattern"] = pattern(dW.view(K, K, C, H), dw_ref.view(K, K, C, H), ["o", "d", "l", "h"])
+    res["permute_wq"] = rel(wq16, W4.permute(1, 0, 3, 2).half().float())
+    y_ref = torch.einsum("boneh,dohl->bdnel", v16, wq16)
+    res["BWD_MIX"] = rel(y16, y_ref)
+    res["BWD_MIX_pattern"] = pattern(y16, y_ref, ["b", "d", "n", "e", "l"])
+    dx_ref = torch.einsum("bdnel,bdce->bncl", y16, gdb)
+    res["BWD_DX"] = rel(dX, dx_ref)
+    res["BWD_DX_pattern"] = pattern(dX, dx_ref, ["b", "n", "c", "l"])
+    # end-to-end gradients vs fp32 autograd of the factored form
+    Xr = X.clone().requires_grad_(True)
+    Wr = W.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    z = torch.einsum("bncl,bdce->bdnel", Xr, Gdb)
+    u = torch.einsum("bdnel,odlh->boneh", z, Wr.view(K, K, C, H))
+    o = torch.relu(torch.einsum("bonm,boneh->bmeh", Gob, u) + br)
+    o.backward(d_out)
+    res["dX_vs_fp32"] = rel(dX, Xr.grad)
+    res["dW_vs_fp32"] = rel(dW, Wr.grad)
+    res["db_vs_fp32"] = rel(db, br.grad)
+    return res
+
+
+CASES = {
+    "small": [(1, 32, 1, 0), (2, 33, 3, 1), (1, 47, 3, 0), (2, 200, 3, 0), (1, 128, 6, 1)],
+    "all": [(1, 32, 1, 0), (2, 33, 3, 1), (1, 47, 3, 0), (2, 200, 3, 0), (1, 128, 6, 1), (2, 500, 3, 0), (1, 1000, 3, 0), (2, 130, 8, 0)],
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "diag.json"))
+    ap.add_argument("--cases", default="small")
+    ap.add_argument("--one", default=None, help="internal: B,N,K,dyn")
+    a = ap.parse_args()
+    if a.one:
+        B, N, K, dyn = map(int, a.one.split(","))
+        print("RESULT " + json.dumps(run_case(B, N, K, dyn)))
+        return
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    allres = {}
+    for (B, N, K, dyn) in CASES[a.cases]:
+        key = f"B{B}_N{N}_K{K}_dyn{dyn}"
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", f"{B},{N},{K},{dyn}"], capture_output=True, text=True,
+                               timeout=600)
+            line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            if line:
+                allres[key] = json.loads(line[-1][7:])
+            else:
+                allres[key] = dict(error=(r.stdout[-1500:] + "\n" + r.stderr[-2500:]))
+        except subprocess.TimeoutExpired:
+            allres[key] = dict(error="timeout")
+        summ = {k: (v if not isinstance(v, dict) else (f"{v['linf']:.2e}" if "linf" in v else "...")) for k, v in allres[key].items()
+                if not k.endswith("_pattern")}
+        print(key, json.dumps(summ), flush=True)
+        with open(a.out, "w") as f:
+            json.dump(allres, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""CPU-only checks of the drop-in boundary: module surface, state_dict contract, error conventions,
+and that libmpgcn_b200.so loads and exports every symbol include/mpgcn_b200.h declares."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from conftest import ROOT, load_golden
+
+import MPGCN as shim
+from mpgcn_b200 import _lib
+
+
+def _model(N=6, K=3, hid=8, M=2):
+    return shim.MPGCN(M=M, K=K, input_dim=1, lstm_hidden_dim=hid, lstm_num_layers=1, gcn_hidden_dim=hid, gcn_num_layers=3,
+                      num_nodes=N, user_bias=True, activation=nn.ReLU)
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "mpgcn_b200.h")).read()
+    declared = set(re.findall(r"MPGCN_API\s+[\w\s\*]+?\b(mpgcn_\w+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mpgcn_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert lib.mpgcn_abi_version() == 1
+
+
+def test_workspace_queries_are_pure_host_functions():
+    lib = _lib.load()
+    assert lib.mpgcn_bdgcn_precision_supported(2, 50, 3, 32, 32, 1) == 1
+    assert lib.mpgcn_bdgcn_precision_supported(2, 50, 3, 16, 32, 1) == 0
+    assert lib.mpgcn_bdgcn_precision_supported(2, 50, 3, 16, 7, 0) == 1
+    assert lib.mpgcn_bdgcn_saved_bytes(2, 50, 3, 32, 32, 1) == 2 * 3 * 2500 * 32 * 2
+    assert lib.mpgcn_bdgcn_saved_bytes(2, 50, 3, 32, 32, 0) == 2 * 3 * 2500 * 32 * 4
+    assert lib.mpgcn_bdgcn_fwd_workspace_bytes(2, 50, 3, 32, 32, 0, 1) > 0
+
+
+def test_null_pointer_is_an_error_not_a_crash():
+    lib = _lib.load()
+    rc = lib.mpgcn_bdgcn_forward(None, None, None, 0, None, None, 1, None, None, None, 0, 1, 4, 1, 32, 32, 0, None)
+    assert rc != 0 and b"null" in lib.mpgcn_last_error()
+    rc = lib.mpgcn_bdgcn_forward(None, None, None, 0, None, None, 1, None, None, None, 0, 1, 4, 1, 16, 32, 1, None)
+    assert rc != 0 and b"C == H == 32" in lib.mpgcn_last_error()
+
+
+def test_state_dict_contract_matches_reference_checkpoint():
+    g = load_golden("mpgcn_n6_k3")
+    ref_params = {k[6:]: v for k, v in g.items() if k.startswith("param:")}
+    m = _model()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref_params.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == ref_params[k].shape, k
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ref_params.items()})     # reference checkpoint loads
+    np.testing.assert_array_equal(m.branch_models[1]['spatial'][2].W.detach().numpy(), ref_params["branch_models.1.spatial.2.W"])
+
+
+def test_constructor_attributes_and_init():
+    torch.manual_seed(0)
+    layer = shim.BDGCN(K=3, input_dim=4, hidden_dim=5, use_bias=True, activation=nn.ReLU)
+    assert (layer.K, layer.input_dim, layer.hidden_dim, layer.use_bias) == (3, 4, 5, True)
+    assert isinstance(layer.activation, nn.ReLU)
+    assert tuple(layer.W.shape) == (36, 5) and tuple(layer.b.shape) == (5,)
+    assert float(layer.b.abs().sum()) == 0.0
+    std = float(layer.W.std())
+    assert abs(std - (2.0 / (36 + 5)) ** 0.5) < 0.05       # xavier_normal_
+    assert not hasattr(shim.BDGCN(K=1, input_dim=2, hidden_dim=2, use_bias=False), "b")
+    m = _model()
+    assert (m.M, m.K, m.num_nodes, m.lstm_hidden_dim, m.lstm_num_layers, m.gcn_num_layers) == (2, 3, 6, 8, 1, 3)
+    h = m.init_hidden_list(2)
+    assert len(h) == 2 and tuple(h[0][0].shape) == (1, 2 * 36, 8) and float(h[1][1].abs().sum()) == 0.0
+
+
+def test_error_conventions():
+    layer = shim.BDGCN(K=3, input_dim=4, hidden_dim=5)
+    X = torch.zeros(2, 6, 6, 4)
+    with pytest.raises(AssertionError):
+        layer(X, torch.zeros(2, 6, 6))                       # K mismatch (reference MPGCN.py:27)
+    with pytest.raises(AssertionError):
+        layer(X, (torch.zeros(2, 2, 6, 6), torch.zeros(2, 3, 6, 6)))   # reference MPGCN.py:35
+    with pytest.raises(NotImplementedError):
+        layer(X, [torch.zeros(3, 6, 6)])                     # neither Tensor nor tuple (reference MPGCN.py:41-42)
+    m = _model()
+    with pytest.raises(AssertionError):
+        m(torch.zeros(2, 3, 6, 6), [torch.zeros(3, 6, 6)] * 2)          # not 5-D (reference MPGCN.py:95)
+    with pytest.raises(AssertionError):
+        m(torch.zeros(2, 3, 5, 5, 1), [torch.zeros(3, 5, 5)] * 2)       # N mismatch
+    with pytest.raises(AssertionError):
+        m(torch.zeros(2, 3, 6, 6, 1), [torch.zeros(3, 6, 6)])           # len(G_list) != M (reference MPGCN.py:96)
+
+
+def test_cpu_tensors_fail_loudly_no_fallback():
+    layer = shim.BDGCN(K=1, input_dim=32, hidden_dim=32)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        layer(torch.zeros(1, 4, 4, 32), torch.zeros(1, 4, 4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mpgcn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("test oracle", ""), f"{f} references the oracle"
