@@ -105,7 +105,9 @@ static int launch_impl(GemmParams& p, cudaStream_t stream) {
   if (stages > 8) stages = 8;
   MPGCN_CHECK(stages >= 2, "tile does not fit in shared memory");
   p.stages = stages;
-  const size_t smem = smem_bytes(C::A_STAGE, p.R, BK, stages);
+  // always request the full opt-in budget: exactly one CTA per SM, so the 512-column TMEM allocation never contends
+  const size_t smem = kMaxSmem;
+  MPGCN_CHECK(smem_bytes(C::A_STAGE, p.R, BK, stages) <= smem, "internal: smem budget");
   const long long tiles = (long long)p.MT * p.NT * p.Z;
   MPGCN_CHECK(tiles > 0 && tiles < (1ll << 31), "bad tile count %lld", tiles);
   MPGCN_CHECK(p.kb_total > 0 && p.kb_per_seg > 0, "empty contraction");
