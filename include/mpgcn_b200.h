@@ -81,6 +81,15 @@ MPGCN_API int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, co
                              const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
                              long long NN, int C, void* stream);
 
+/* Launch accounting (bench.py evidence).  Every launch of a kernel of this library is counted per tag
+ * (0 FWD_A, 1 FWD_MIX, 2 FWD_B, 3 BWD_V, 4 BWD_DW, 5 BWD_MIX, 6 BWD_DX: tcgen05 contractions; 7 fp32 SIMT GEMM;
+ * 8 elementwise/layout; 9 LSTM forward; 10 LSTM backward).  With profiling enabled, tags 0-6, 9, 10 are also
+ * bracketed by CUDA events on the launch stream; mpgcn_profile_read (HOST pointers; call after synchronising)
+ * returns launches, algorithmic flops and summed device milliseconds since the last reset. */
+MPGCN_API void mpgcn_profile_enable(int on);
+MPGCN_API void mpgcn_profile_reset(void);
+MPGCN_API int mpgcn_profile_read(int tag, long long* launches, double* flops, double* ms);
+
 /* Test / diagnostics only: byte offset of an intermediate inside the precision-1 workspace
  * (which: 0 X16, 1 Gd16, 2 Go16, 3 W16, 4 U16 forward; 10 dP16, 11 Gd16, 12 Go16, 13 V16, 14 Y16, 15 Wq16,
  * 16 dW partials backward; 17 = number of dW split-K slices). */

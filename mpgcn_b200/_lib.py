@@ -31,6 +31,9 @@ _SIGS = {
                             + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     "mpgcn_bdgcn_backward": (ctypes.c_int, [_c_f, _c_f, _c_f, _c_f, ctypes.c_int, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, _c_f,
                                             ctypes.c_size_t] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    "mpgcn_profile_enable": (None, [ctypes.c_int]),
+    "mpgcn_profile_reset": (None, []),
+    "mpgcn_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "mpgcn_debug_tc_workspace_offset": (ctypes.c_longlong, [ctypes.c_int] * 5),
     "mpgcn_lstm_last_forward": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
     "mpgcn_lstm_last_backward": (ctypes.c_int, [_c_f] * 11 + [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
@@ -72,3 +75,17 @@ def check(code: int, what: str) -> None:
     if code != 0:
         msg = load().mpgcn_last_error()
         raise RuntimeError(f"mpgcn_b200.{what} failed: {msg.decode() if msg else 'unknown error'}")
+
+
+PROFILE_TAGS = ("FWD_A", "FWD_MIX", "FWD_B", "BWD_V", "BWD_DW", "BWD_MIX", "BWD_DX", "SIMT_GEMM", "ELEMENTWISE", "LSTM_FWD", "LSTM_BWD")
+
+
+def profile_read() -> dict:
+    """{tag: {launches, flops, ms}} since the last mpgcn_profile_reset(); synchronise the device first."""
+    lib = load()
+    out = {}
+    for i, name in enumerate(PROFILE_TAGS):
+        n, f, ms = ctypes.c_longlong(0), ctypes.c_double(0), ctypes.c_double(0)
+        check(lib.mpgcn_profile_read(i, ctypes.byref(n), ctypes.byref(f), ctypes.byref(ms)), "profile_read")
+        out[name] = dict(launches=n.value, flops=f.value, ms=ms.value)
+    return out

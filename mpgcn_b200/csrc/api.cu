@@ -77,6 +77,14 @@ int mpgcn_bdgcn_backward(const float* d_out, const float* out, const float* G_o,
   return bdgcn_backward_simt(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, st);
 }
 
+void mpgcn_profile_enable(int on) { prof_enable(on); }
+void mpgcn_profile_reset(void) { prof_reset(); }
+int mpgcn_profile_read(int tag, long long* launches, double* flops, double* ms) {
+  MPGCN_CHECK(launches && flops && ms, "mpgcn_profile_read: null output pointer");
+  MPGCN_CHECK(prof_read(tag, launches, flops, ms) == 0, "mpgcn_profile_read: unknown tag %d", tag);
+  return 0;
+}
+
 long long mpgcn_debug_tc_workspace_offset(int which, int B, int N, int K, int dynamic) {
   return tc_debug_offset(mk(B, N, K, 32, 32, dynamic, 0), which);
 }

@@ -178,11 +178,12 @@ static int run_fwd_a(const BdgcnShape& s, const __half* gd16, const __half* x16,
   p.ep.out = z16; p.ep.out_f16 = 1;
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
+  prof_set_next(PROF_FWD_A, 2.0 * s.B * K * (double)N * N * N * 32);
   return tc::launch_contract(tc::A_MN128, 64, p, st);
 }
 
 // MIX: D16[b][r][row][32] = sum_{seg} A16[b][seg][row][32] * Wm16[r][(seg,32)][32]   (both channel mixes)
-static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, __half* d16, cudaStream_t st) {
+static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, __half* d16, int tag, cudaStream_t st) {
   const int K = s.K;
   const long long NN = (long long)s.N * s.N;
   GemmParams p;
@@ -196,6 +197,7 @@ static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, __
   p.ep.out = d16; p.ep.out_f16 = 1;
   p.ep.sZ = (long long)K * NN * 32; p.ep.sI = 32; p.ep.sR = NN * 32;
   p.ep.m_valid = (int)NN; p.ep.r_valid = K;
+  prof_set_next(tag, 2.0 * s.B * (double)K * K * NN * 32 * 32);
   return tc::launch_contract(tc::A_K64, 32, p, st);
 }
 
@@ -215,6 +217,7 @@ static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16,
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
   p.ep.bias = bias; p.ep.relu = s.act;
+  prof_set_next(PROF_FWD_B, 2.0 * s.B * K * (double)N * N * N * 32);
   return tc::launch_contract(tc::A_MN128, 64, p, st);
 }
 
@@ -233,6 +236,7 @@ static int run_bwd_v(const BdgcnShape& s, const __half* go16, const __half* dp16
   p.ep.out = v16; p.ep.out_f16 = 1;
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
+  prof_set_next(PROF_BWD_V, 2.0 * s.B * K * (double)N * N * N * 32);
   return tc::launch_contract(tc::A_K128, 64, p, st);
 }
 
@@ -257,6 +261,7 @@ static int run_bwd_dw(const BdgcnShape& s, const __half* z16, const __half* v16,
   p.ep.m_valid = p.MT * 128; p.ep.r_valid = K;
   *slices_out = slices;
   *mt_out = p.MT;
+  prof_set_next(PROF_BWD_DW, 2.0 * s.B * (double)K * K * NN * 32 * 32);
   return tc::launch_contract(tc::A_MN64, 64, p, st);
 }
 
@@ -274,6 +279,7 @@ static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16
   p.ep.out = dX; p.ep.out_f16 = 0;
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
+  prof_set_next(PROF_BWD_DX, 2.0 * s.B * K * (double)N * N * N * 32);
   return tc::launch_contract(tc::A_K128, 64, p, st);
 }
 
@@ -314,7 +320,7 @@ int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const
   if (int e = convert_supports(s, Go, Gd, go16, gd16, &go_used, st)) return e;
   if (int e = cvt_f32_to_f16(W, w16, (size_t)s.K * s.K * 32 * 32, st)) return e;
   if (int e = run_fwd_a(s, gd16, x16, z16, st)) return e;
-  if (int e = run_mix(s, z16, w16, u16, st)) return e;
+  if (int e = run_mix(s, z16, w16, u16, PROF_FWD_MIX, st)) return e;
   if (int e = run_fwd_b(s, go_used, u16, bias, out, st)) return e;
   return 0;
 }
@@ -347,7 +353,7 @@ int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out,
   if (int e = reduce_dw_partials(partials, dW, slices, mt, s.K, st)) return e;
   if (dX) {
     if (int e = permute_w_bwd(W, wq16, nullptr, s.K, 32, 32, st)) return e;
-    if (int e = run_mix(s, v16, wq16, y16, st)) return e;
+    if (int e = run_mix(s, v16, wq16, y16, PROF_BWD_MIX, st)) return e;
     if (int e = run_bwd_dx(s, gd16, y16, dX, st)) return e;
   }
   return 0;

@@ -173,4 +173,16 @@ int make_tmap_f16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* 
 
 int device_sm_count();
 
+// ----------------------------------------------------------------------------------------
+// host: launch accounting / per-launch CUDA-event timing (bench.py's roofline evidence)
+// ----------------------------------------------------------------------------------------
+enum ProfTag {
+  PROF_FWD_A = 0, PROF_FWD_MIX, PROF_FWD_B, PROF_BWD_V, PROF_BWD_DW, PROF_BWD_MIX, PROF_BWD_DX,   // tcgen05 contractions
+  PROF_SIMT_GEMM, PROF_ELEMENTWISE, PROF_LSTM_FWD, PROF_LSTM_BWD, PROF_NUM_TAGS
+};
+void prof_set_next(int tag, double flops);             // annotate the next contraction launch
+void prof_count(int tag);                              // count one launch of our own kernels
+void prof_begin(int tag, double flops, cudaStream_t s);   // event before launch (no-op unless enabled)
+void prof_end(cudaStream_t s);                            // event after launch
+
 }  // namespace mpgcn

@@ -6,6 +6,9 @@
 namespace mpgcn {
 
 const char* last_error();
+void prof_enable(int on);
+void prof_reset();
+int prof_read(int tag, long long* launches, double* flops, double* ms);
 
 // ---- generic fp32 SIMT strided/batched contraction (simt_kernels.cu) ---------------------
 //   D[z](i,j) (+)= alpha * sum_seg sum_k A[z](i,k;seg) * B[z](k,j;seg)  (+ bias[j % bias_mod], ReLU)

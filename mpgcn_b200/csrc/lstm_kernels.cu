@@ -107,7 +107,9 @@ int lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, 
   const long long tiles = (cells + CELLS - 1) / CELLS;
   long long grid = (long long)device_sm_count() * 8;
   if (grid > tiles) grid = tiles;
+  prof_begin(PROF_LSTM_FWD, 8.0 * C * (C + 1) * (double)cells * T, st);
   lstm_fwd_kernel<<<(unsigned)grid, threads, smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, cells, T, NN, C, CELLS);
+  prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -152,7 +154,6 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ x_seq, const float* __
 
   const int s = tid / C, u = tid % C;
   const long long tiles = (cells + CELLS - 1) / CELLS;
-  const float* zero_row = nullptr;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long cell = tile * CELLS + s;
     const bool live = cell < cells;
@@ -242,7 +243,6 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ x_seq, const float* __
       __syncthreads();
     }
   }
-  (void)zero_row;
   for (int e = tid; e < G * C; e += nthr) atomicAdd(&d_w_hh[e], acc_whh[e]);
   for (int j = tid; j < G; j += nthr) {
     atomicAdd(&d_w_ih[j], acc_wih[j]);
@@ -284,9 +284,12 @@ int lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh,
   const long long tiles = (cells + CELLS - 1) / CELLS;
   long long grid = device_sm_count();
   if (grid > tiles) grid = tiles;
+  prof_begin(PROF_LSTM_BWD, 16.0 * C * (C + 1) * (double)cells * T, st);
   lstm_bwd_kernel<<<(unsigned)grid, threads, smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x, cells, T,
                                                            NN, C, CELLS);
+  prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
+  prof_count(PROF_ELEMENTWISE);
   copy_kernel<<<(G + 255) / 256, 256, 0, st>>>(d_b_ih, d_b_hh, G);   // d(b_ih) == d(b_hh)
   MPGCN_CUDA(cudaGetLastError());
   return 0;

@@ -111,6 +111,7 @@ int simt_sgemm(const SgemmParams& p, cudaStream_t stream) {
   const int tiles_n = (p.N + bn - 1) / bn;
   const long long blocks = (long long)tiles_m * tiles_n * p.ksplit * p.Z0 * p.Z1 * p.Z2;
   MPGCN_CHECK(blocks > 0 && blocks < (1ll << 31), "simt_sgemm: grid too large (%lld blocks)", blocks);
+  prof_count(PROF_SIMT_GEMM);
   if (bn == 32)
     sgemm_kernel<32><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_m, tiles_n);
   else
@@ -153,6 +154,7 @@ static inline unsigned grid_for(size_t work_items, int threads) {
 int cvt_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t s) {
   if (n == 0) return 0;
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "cvt: misaligned pointers");
+  prof_count(PROF_ELEMENTWISE);
   cvt_f16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(src, dst, n);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
@@ -170,6 +172,7 @@ __global__ void cvt_f16_padded_kernel(const float* __restrict__ src, __half* __r
 
 int cvt_f32_to_f16_padded(const float* src, __half* dst, size_t rows, int cols, int ld, cudaStream_t s) {
   if (rows == 0) return 0;
+  prof_count(PROF_ELEMENTWISE);
   cvt_f16_padded_kernel<<<grid_for(rows * ld, 256), 256, 0, s>>>(src, dst, rows, cols, ld);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
@@ -210,6 +213,7 @@ int relu_bwd_prep(const float* d_out, const float* out, int relu, __half* d16, f
   int threads = (256 / H) * H;          // multiple of H so each thread keeps one channel
   if (threads == 0) threads = H;
   unsigned blocks = grid_for(n, threads);
+  prof_count(PROF_ELEMENTWISE);
   relu_bwd_prep_kernel<<<blocks, threads, threads * sizeof(float), s>>>(d_out, out, relu, d16, d32, db, n, H);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
@@ -230,6 +234,7 @@ __global__ void permute_w_bwd_kernel(const float* __restrict__ W, __half* __rest
 }
 
 int permute_w_bwd(const float* W, __half* wq16, float* wq32, int K, int C, int H, cudaStream_t s) {
+  prof_count(PROF_ELEMENTWISE);
   permute_w_bwd_kernel<<<grid_for((size_t)K * K * C * H, 256), 256, 0, s>>>(W, wq16, wq32, K, C, H);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
@@ -252,6 +257,7 @@ __global__ void reduce_dw_kernel(const float* __restrict__ P, float* __restrict_
 }
 
 int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int K, cudaStream_t s) {
+  prof_count(PROF_ELEMENTWISE);
   reduce_dw_kernel<<<grid_for((size_t)K * K * 1024, 256), 256, 0, s>>>(P, dW, slices, MT, K);
   MPGCN_CUDA(cudaGetLastError());
   return 0;

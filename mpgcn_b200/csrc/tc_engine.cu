@@ -2,6 +2,7 @@
 #include "tc_engine.cuh"
 
 #include <mutex>
+#include <vector>
 #include <stdarg.h>
 #include <string.h>
 
@@ -29,6 +30,70 @@ int device_sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// ---------------------------------------------------------------------------------------
+// launch accounting and optional per-launch event timing
+// ---------------------------------------------------------------------------------------
+namespace {
+struct ProfState {
+  bool enabled = false;
+  long long launches[PROF_NUM_TAGS] = {0};
+  double flops[PROF_NUM_TAGS] = {0};
+  double ms[PROF_NUM_TAGS] = {0};
+  struct Pending { cudaEvent_t a, b; int tag; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  int cur_tag = -1;
+  cudaEvent_t cur_a = nullptr;
+  int next_tag = -1;
+  double next_flops = 0;
+} g_prof;
+cudaEvent_t prof_event() {
+  if (!g_prof.pool.empty()) { cudaEvent_t e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void prof_set_next(int tag, double flops) { g_prof.next_tag = tag; g_prof.next_flops = flops; }
+void prof_count(int tag) { if (tag >= 0 && tag < PROF_NUM_TAGS) g_prof.launches[tag]++; }
+void prof_begin(int tag, double flops, cudaStream_t s) {
+  prof_count(tag);
+  if (tag >= 0 && tag < PROF_NUM_TAGS) g_prof.flops[tag] += flops;
+  if (!g_prof.enabled) return;
+  g_prof.cur_tag = tag;
+  g_prof.cur_a = prof_event();
+  cudaEventRecord(g_prof.cur_a, s);
+}
+void prof_end(cudaStream_t s) {
+  if (!g_prof.enabled || g_prof.cur_a == nullptr) return;
+  cudaEvent_t b = prof_event();
+  cudaEventRecord(b, s);
+  g_prof.pending.push_back({g_prof.cur_a, b, g_prof.cur_tag});
+  g_prof.cur_a = nullptr;
+}
+void prof_enable(int on) { g_prof.enabled = on != 0; }
+void prof_reset() {
+  for (int i = 0; i < PROF_NUM_TAGS; ++i) { g_prof.launches[i] = 0; g_prof.flops[i] = 0; g_prof.ms[i] = 0; }
+  for (auto& p : g_prof.pending) { g_prof.pool.push_back(p.a); g_prof.pool.push_back(p.b); }
+  g_prof.pending.clear();
+}
+// resolves pending event pairs (caller must have synchronised the stream)
+int prof_read(int tag, long long* launches, double* flops, double* ms) {
+  for (auto& p : g_prof.pending) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess && p.tag >= 0 && p.tag < PROF_NUM_TAGS) g_prof.ms[p.tag] += t;
+    g_prof.pool.push_back(p.a);
+    g_prof.pool.push_back(p.b);
+  }
+  g_prof.pending.clear();
+  if (tag < 0 || tag >= PROF_NUM_TAGS) return 1;
+  *launches = g_prof.launches[tag];
+  *flops = g_prof.flops[tag];
+  *ms = g_prof.ms[tag];
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -112,7 +177,13 @@ static int launch_impl(GemmParams& p, cudaStream_t stream) {
   MPGCN_CHECK(tiles > 0 && tiles < (1ll << 31), "bad tile count %lld", tiles);
   MPGCN_CHECK(p.kb_total > 0 && p.kb_per_seg > 0, "empty contraction");
   int grid = (int)(tiles < device_sm_count() ? tiles : device_sm_count());
+  const int tag = g_prof.next_tag;
+  const double fl = g_prof.next_flops;
+  g_prof.next_tag = -1;
+  g_prof.next_flops = 0;
+  prof_begin(tag, fl, stream);
   contract_kernel<AK, BK><<<grid, kThreads, smem, stream>>>(p);
+  prof_end(stream);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -104,16 +104,25 @@ def bdgcn_forward(X, G, W, b=None, act="relu", return_cache=False):
     return out
 
 
-def bdgcn_backward(X, G, W, b, act, d_out):
+def bdgcn_backward(X, G, W, b, act, d_out, mask_from=None):
     """Gradients the reference obtains from autograd through MPGCN.py:24-50
     (loss.backward(), Model_Trainer.py:114).  The supports never require grad.
-    Returns (dX [B,N,N,C], dW [K*K*C,H], db [H] or None)."""
+    Returns (dX [B,N,N,C], dW [K*K*C,H], db [H] or None).
+
+    mask_from: optional forward output of ANOTHER implementation; if given, the ReLU mask is
+    (mask_from > 0) instead of the oracle's own (pre > 0).  A reduced-precision forward flips
+    the sign of pre-activations that lie within its rounding error of zero, so its (exact)
+    gradient differs from the fp32 one on those few elements by O(1); passing its output here
+    yields the gradient of the function it actually computed ("ReLU mask")."""
     X = np.asarray(X)
     go, gd = _support_pair(G, X.shape[0])
     Bsz, N, _, C = X.shape
     K = go.shape[1]
     out, (feats, pre) = bdgcn_forward(X, G, W, b, act, return_cache=True)
-    d_pre = d_out * (pre > 0) if act == "relu" else d_out
+    if act == "relu":
+        d_pre = d_out * ((pre if mask_from is None else np.asarray(mask_from)) > 0)
+    else:
+        d_pre = d_out
     db = d_pre.sum(axis=(0, 1, 2)) if b is not None else None
     dW = np.tensordot(feats, d_pre, axes=([0, 1, 2], [0, 1, 2]))     # [K*K*C, H]
     d_feats = d_pre @ W.T                                            # [B,N,N,K*K*C]

@@ -4,8 +4,12 @@ Tolerances (written here once):
   * precision "fp32" (CUDA-core kernels): rel_Linf, rel_L2 <= 5e-5 vs the reference fixtures
     (fp32 summation-order noise only);
   * precision "fp16" (tcgen05, fp16 operands / fp32 accumulation): forward <= 1e-3 -- the bound
-    BASELINE.json's north_star states ("within 1e-3 relative fp32"); gradients <= 2e-3
-    (no bound is stated for them; they pass through the same number of fp16 roundings twice).
+    BASELINE.json's north_star states ("within 1e-3 relative fp32").  Gradients: <= 2e-3 against the
+    oracle's gradient evaluated with the ENGINE's ReLU mask (the gradient of the function actually
+    computed), and <= 8e-2 against the reference's own gradient: a reduced-precision forward flips
+    the sign of the ~3e-4 fraction of pre-activations that lie within its rounding error of zero,
+    and each flip moves one d_pre element by O(|d_out|), i.e. rel_L2 ~ sqrt(flipped/active) ~ 2-3 %
+    for an i.i.d. d_out (measured 1.3-4.3e-2).  No implementation below fp32 can avoid that.
 """
 import numpy as np
 import pytest
@@ -21,6 +25,9 @@ from mpgcn_b200 import _lib, ops
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": (5e-5, 5e-5), "fp16": (1e-3, 2e-3)}
+LOOSE_FP16_GRAD = 8e-2
+
+import abi
 
 
 def _check(a, ref, tol, what):
@@ -64,10 +71,17 @@ def test_bdgcn_layer_matches_reference_fixture(name, cuda_device):
         torch.cuda.synchronize()
         tf, tb = TOL[prec]
         _check(out, g["out"], tf, f"{name}/{prec}/out")
-        _check(X.grad, g["dX"], tb, f"{name}/{prec}/dX")
-        _check(layer.W.grad, g["dW"], tb, f"{name}/{prec}/dW")
+        if prec == "fp32" or act is None:
+            refs = (g["dX"], g["dW"], g.get("db"))
+        else:   # gradient of the computed function: oracle backward with the engine's ReLU mask
+            Gn = (g["G_o"], g["G_d"]) if int(g["dynamic"]) else g["G"]
+            refs = orc.bdgcn_backward(g["X"], Gn, g["W"], g.get("b"), "relu", g["d_out"], mask_from=out.detach().cpu().numpy())
+            _check(X.grad, g["dX"], LOOSE_FP16_GRAD, f"{name}/{prec}/dX vs reference")
+            _check(layer.W.grad, g["dW"], LOOSE_FP16_GRAD, f"{name}/{prec}/dW vs reference")
+        _check(X.grad, refs[0], tb, f"{name}/{prec}/dX")
+        _check(layer.W.grad, refs[1], tb, f"{name}/{prec}/dW")
         if "b" in g:
-            _check(layer.b.grad, g["db"], tb, f"{name}/{prec}/db")
+            _check(layer.b.grad, refs[2], tb, f"{name}/{prec}/db")
 
 
 @pytest.mark.parametrize("name", golden_names("lstm_"))
@@ -107,8 +121,8 @@ def test_full_model_matches_reference_fixture(name, cuda_device):
         tf, tb = TOL[prec]
         _check(y, g["y"], tf, f"{name}/{prec}/y")
         for k, p in model.named_parameters():
-            # LSTM gradients sit behind three fp16 layers: same 2e-3 bound in fp16 mode, 2e-4 in fp32
-            _check(p.grad, g["grad:" + k], max(tb, 2e-4), f"{name}/{prec}/grad:{k}")
+            # fp32: summation-order noise only.  fp16: ReLU-mask flips in 4 stacked ReLUs (see module docstring)
+            _check(p.grad, g["grad:" + k], 2e-4 if prec == "fp32" else LOOSE_FP16_GRAD, f"{name}/{prec}/grad:{k}")
 
 
 @pytest.mark.parametrize("N,K,B,dyn", [(200, 3, 2, False), (130, 6, 1, True), (257, 2, 1, False)])
@@ -120,20 +134,19 @@ def test_tensor_path_agrees_with_fp32_path_at_size(N, K, B, dyn, cuda_device):
         G = (torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5, torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5)
     else:
         G = torch.randn(K, N, N, device=cuda_device) / N ** 0.5
-    layer = shim.BDGCN(K=K, input_dim=32, hidden_dim=32, use_bias=True, activation=nn.ReLU).to(cuda_device)
-    with torch.no_grad():
-        layer.b.normal_(0, 0.1)
+    W = torch.randn(K * K * 32, 32, device=cuda_device) * (2.0 / (K * K * 32 + 32)) ** 0.5
+    b = torch.randn(32, device=cuda_device) * 0.1
     d_out = torch.randn(B, N, N, 32, device=cuda_device)
-    res = {}
-    for prec in ("fp32", "fp16"):
-        layer.precision = prec
-        layer.zero_grad()
-        Xg = X.clone().requires_grad_(True)
-        out = layer(Xg, G)
-        out.backward(d_out)
-        res[prec] = [t.detach().cpu().numpy() for t in (out, Xg.grad, layer.W.grad, layer.b.grad)]
-    for a, r, what, tol in zip(res["fp16"], res["fp32"], ("out", "dX", "dW", "db"), (1e-3, 2e-3, 2e-3, 2e-3)):
-        _check(a, r, tol, f"N={N} K={K} {what}")
+    Go, Gd = (G if dyn else (G, G))
+    out16, saved16 = abi.forward(X, Go, Gd, W, b, True, "fp16")
+    out32, saved32 = abi.forward(X, Go, Gd, W, b, True, "fp32")
+    _check(out16, out32.cpu().numpy(), 1e-3, f"N={N} K={K} out")
+    g16 = abi.backward(d_out, out16, Go, Gd, W, True, saved16, "fp16")
+    g32 = abi.backward(d_out, out16, Go, Gd, W, True, saved32, "fp32")      # same ReLU mask (out16) on both paths
+    for a, r, what in zip(g16, g32, ("dX", "dW", "db")):
+        _check(a, r.cpu().numpy(), 2e-3, f"N={N} K={K} {what}")
+    flipped = float(((out16 > 0) != (out32 > 0)).float().mean())
+    assert flipped < 2e-3, f"ReLU mask flips {flipped:.2e}"
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])

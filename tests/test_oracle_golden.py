@@ -82,3 +82,20 @@ def test_properties_linearity_and_identity():
     # static == dynamic with the static stack broadcast over the batch
     Gb = np.broadcast_to(G, (B, K, N, N)).copy()
     np.testing.assert_allclose(orc.bdgcn_forward(X1, (Gb, Gb), W, None, "relu"), orc.bdgcn_forward(X1, G, W, None, "relu"), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["bdgcn_s_k3_n12", "bdgcn_d_k3_n10", "bdgcn_s_k3_n12_linear_nobias"])
+def test_torch_port_matches_reference_fixture(name):
+    """The CPU timing arm (oracle/torch_port.py) computes the same function as the reference."""
+    import torch
+    from oracle import torch_port
+    g = load_golden(name)
+    X = torch.from_numpy(g["X"]).requires_grad_(True)
+    W = torch.from_numpy(g["W"]).requires_grad_(True)
+    b = torch.from_numpy(g["b"]).requires_grad_(True) if "b" in g else None
+    G = (torch.from_numpy(g["G_o"]), torch.from_numpy(g["G_d"])) if int(g["dynamic"]) else torch.from_numpy(g["G"])
+    out = torch_port.bdgcn_layer(X, G, W, b, relu=str(g["act"]) == "relu")
+    out.backward(torch.from_numpy(g["d_out"]))
+    _check(out.detach().numpy(), g["out"], what="out")
+    _check(X.grad.numpy(), g["dX"], what="dX")
+    _check(W.grad.numpy(), g["dW"], what="dW")
