@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "auto"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="under ncu: honour --warmup < 3, skip the e2e and CPU arms (numbers are not bench values)")
     return ap.parse_args()
 
 
@@ -115,7 +116,7 @@ def cpu_sample(a, seed=0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     N, K, T, C = a.nodes, a.supports, a.obs, a.hidden
-    # keep one sample at ~<= 10 s: if the full-size layer is too slow on this host, time a smaller N and scale by N^3
+    # keep one sample to a few seconds: if the full-size layer is too slow on this host, time a smaller N and scale by N^3
     x = torch.randn(1536, 1536)
     t0 = time.perf_counter()
     for _ in range(3):
@@ -123,13 +124,13 @@ def cpu_sample(a, seed=0):
     rate = 3 * 2 * 1536 ** 3 / (time.perf_counter() - t0)          # flop/s of a large sgemm
     est = 3.0 * (4 * K * K * N ** 3 * C) / rate * 1.6
     Ns = N
-    while est > 10.0 and Ns > 100:
+    while est > 4.0 and Ns > 100:
         Ns = int(Ns * 0.85)
         est = 3.0 * (4 * K * K * Ns ** 3 * C) / rate * 1.6
     t_layer_s = torch_port.time_bdgcn_layer_fwd_bwd(Ns, K, B=1, C=C, H=C, seed=seed)
     t_layer = t_layer_s * (N / Ns) ** 3
     cells = N * N
-    sample_cells = min(cells, 100_000)
+    sample_cells = min(cells, 20_000)
     t_lstm = torch_port.time_lstm_fwd_bwd(sample_cells, T, C=C, seed=seed) * cells / sample_cells
     total = 2 * (3 * t_layer + t_lstm)
     detail = dict(cores=cores, bdgcn_layer_N_timed=Ns, t_bdgcn_layer_s=round(t_layer_s, 4), t_bdgcn_layer_scaled_s=round(t_layer, 4),
@@ -233,7 +234,8 @@ def run_ours(a):
 
     # ---- resident-input arm -------------------------------------------------------------------
     x, y, go, gd = (t.to(dev) for t in (x_host, y_host, go_host, gd_host))
-    for _ in range(max(3, a.warmup)):
+    n_warm = a.warmup if a.profile else max(3, a.warmup)
+    for _ in range(n_warm):
         step(x, y, go, gd)
     sync_all()
     lib.mpgcn_profile_reset()
@@ -258,7 +260,7 @@ def run_ours(a):
 
     # ---- end-to-end arm: host buffers in, loss out, every step -----------------------------------
     e2e = None
-    if not a.no_e2e:
+    if not (a.no_e2e or a.profile):
         del x, go, gd
         h2d = sum(t.numel() * t.element_size() for t in (x_host, y_host, go_host, gd_host))
 
@@ -313,13 +315,13 @@ def run_ours(a):
     gpu_launches = sum(v["launches"] for v in prof.values())
 
     cpu_baseline = None
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not (a.no_cpu_baseline or a.profile):
         t_cpu, detail = cpu_sample(a)
         cpu_baseline = {"value": (T * N * N) / t_cpu, "unit": UNIT, "cores": detail["cores"], "kind": "port", "sample": sample_text(detail, a),
                         "detail": detail}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": n_warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16" if a.precision != "fp32" else "f32", "data": "synthetic", "config": workload_config(a, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
