@@ -107,7 +107,7 @@ int bdgcn_backward_simt(const BdgcnShape& s, const float* d_out, const float* ou
   const long long g_sb = s.dynamic ? K * NN : 0;
 
   if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * H, st));
-  if (int e = relu_bwd_prep(d_out, out, s.act, nullptr, dPre, db, (size_t)s.B * NN * H, (int)H, st)) return e;
+  if (int e = relu_bwd_prep(d_out, out, s.act, nullptr, dPre, db, (size_t)s.B * NN * H, (int)H, nullptr, st)) return e;
 
   {  // V[b,o] (n x (e,h)) = G_o (n x m) * dPre[b] (m x (e,h))
     SgemmParams p{};

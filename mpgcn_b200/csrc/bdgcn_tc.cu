@@ -88,7 +88,7 @@ size_t tc_saved_bytes(const BdgcnShape& s) { return (size_t)s.B * s.K * n2(s) * 
 
 // workspace layouts (byte offsets); also served to tests by mpgcn_debug_tc_workspace_offset()
 struct FwdLayout { size_t x16, gd16, go16, w16, u16, z16, total; };
-struct BwdLayout { size_t dp16, gd16, go16, v16, y16, wq16, partials, total; };
+struct BwdLayout { size_t dp16, gd16, go16, v16, y16, wq16, partials, scale, total; };
 static size_t take(size_t& off, size_t bytes) {
   off = align_up(off, 1024);
   const size_t r = off;
@@ -132,6 +132,7 @@ static BwdLayout bwd_layout(const BdgcnShape& s) {
   int per = 1, total = 1;
   const int slices = dw_slices(s, &per, &total);
   L.partials = take(off, (size_t)slices * ceil_div(s.K, 4) * 128 * s.K * 32 * 4);
+  L.scale = take(off, 64);
   L.total = align_up(off, 1024);
   return L;
 }
@@ -157,6 +158,7 @@ long long tc_debug_offset(const BdgcnShape& s, int which) {
     case 15: return (long long)Bw.wq16;
     case 16: return (long long)Bw.partials;
     case 17: return dw_slices(s, &per, &total);
+    case 18: return (long long)Bw.scale;
     default: return -1;
   }
 }
@@ -266,7 +268,7 @@ static int run_bwd_dw(const BdgcnShape& s, const __half* z16, const __half* v16,
 }
 
 // BWD_DX: dX[b][n][c][l] = sum_{d,e} G_d[c][e] Y16[b][d][n][e][l]
-static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16, float* dX, cudaStream_t st) {
+static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16, float* dX, const float* inv_scale, cudaStream_t st) {
   const int N = s.N, K = s.K, Np = pad8(N);
   GemmParams p;
   init_params(p);
@@ -276,7 +278,7 @@ static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16
   p.bm = omap(1, kBig, K, 1, 0);                                    // plane = b*K + d
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;
   p.kb_per_seg = ceil_div(N, 64); p.kb_total = K * p.kb_per_seg;
-  p.ep.out = dX; p.ep.out_f16 = 0;
+  p.ep.out = dX; p.ep.out_f16 = 0; p.ep.alpha_dev = inv_scale;
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
   prof_set_next(PROF_BWD_DX, 2.0 * s.B * K * (double)N * N * N * 32);
@@ -342,19 +344,21 @@ int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out,
   __half* y16 = reinterpret_cast<__half*>(wb + L.y16);
   __half* wq16 = reinterpret_cast<__half*>(wb + L.wq16);
   float* partials = reinterpret_cast<float*>(wb + L.partials);
+  float* scale2 = reinterpret_cast<float*>(wb + L.scale);   // [S, 1/S]: power-of-two gradient scale (fp16 range)
 
   const __half* go_used = nullptr;
   if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 32, st));
-  if (int e = relu_bwd_prep(d_out, out, s.act, dp16, nullptr, db, (size_t)s.B * NN * 32, 32, st)) return e;
+  if (int e = grad_scale_prepare(d_out, (size_t)s.B * NN * 32, scale2, st)) return e;
+  if (int e = relu_bwd_prep(d_out, out, s.act, dp16, nullptr, db, (size_t)s.B * NN * 32, 32, scale2, st)) return e;
   if (int e = convert_supports(s, Go, Gd, go16, gd16, &go_used, st)) return e;
   if (int e = run_bwd_v(s, go_used, dp16, v16, st)) return e;
   int slices = 0, mt = 0;
   if (int e = run_bwd_dw(s, z16, v16, partials, &slices, &mt, st)) return e;
-  if (int e = reduce_dw_partials(partials, dW, slices, mt, s.K, st)) return e;
+  if (int e = reduce_dw_partials(partials, dW, slices, mt, s.K, scale2 + 1, st)) return e;
   if (dX) {
     if (int e = permute_w_bwd(W, wq16, nullptr, s.K, 32, 32, st)) return e;
     if (int e = run_mix(s, v16, wq16, y16, PROF_BWD_MIX, st)) return e;
-    if (int e = run_bwd_dx(s, gd16, y16, dX, st)) return e;
+    if (int e = run_bwd_dx(s, gd16, y16, dX, scale2 + 1, st)) return e;
   }
   return 0;
 }

@@ -38,11 +38,14 @@ int cvt_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t s);
 int cvt_f32_to_f16_padded(const float* src, __half* dst, size_t rows, int cols, int ld, cudaStream_t s);
 // d_pre = d_out * (out > 0) (relu) or d_out; fp16 and/or fp32 output; db[h] += sum (db may be null; pre-zeroed)
 int relu_bwd_prep(const float* d_out, const float* out, int relu, __half* d_pre16, float* d_pre32, float* db, size_t n, int H,
-                  cudaStream_t s);
+                  const float* scale, cudaStream_t s);
+// scale2[0] = S = 2^k with S*max|d_out| in [16,32), scale2[1] = 1/S (S = 1 for an all-zero or non-finite input).
+// fp16 has 5 exponent bits: realistic gradients (MSE mean over B*N*N cells ~ 1e-7) must be rescaled before the cast.
+int grad_scale_prepare(const float* d_out, size_t n, float* scale2, cudaStream_t s);
 // W[o][d][l][h] fp32 -> Wq[d][o][h][l] (fp16 and/or fp32)
 int permute_w_bwd(const float* W, __half* wq16, float* wq32, int K, int C, int H, cudaStream_t s);
 // dW[o][d][l][h] = sum_slices P[slice][mt][(d%4)*32 + l][o][h]   (C = H = 32)
-int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int K, cudaStream_t s);
+int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int K, const float* inv_scale, cudaStream_t s);
 
 // ---- per-cell LSTM, last hidden state (lstm_kernels.cu) ------------------------------------
 int lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,

@@ -181,7 +181,9 @@ int cvt_f32_to_f16_padded(const float* src, __half* dst, size_t rows, int cols, 
 // d_pre = d_out * [out > 0];  db[h] += sum over cells.  Thread's channel is fixed because the
 // grid stride is a multiple of H.
 __global__ void relu_bwd_prep_kernel(const float* __restrict__ d_out, const float* __restrict__ out, int relu,
-                                     __half* __restrict__ d16, float* __restrict__ d32, float* __restrict__ db, size_t n, int H) {
+                                     __half* __restrict__ d16, float* __restrict__ d32, float* __restrict__ db, size_t n, int H,
+                                     const float* __restrict__ scale) {
+  const float S = scale ? __ldg(scale) : 1.f;
   extern __shared__ float s_db[];   // [blockDim.x]
   const size_t stride = (size_t)gridDim.x * blockDim.x;   // multiple of H by construction
   float local = 0.f;
@@ -189,7 +191,7 @@ __global__ void relu_bwd_prep_kernel(const float* __restrict__ d_out, const floa
   for (size_t i = first; i < n; i += stride) {
     float g = d_out[i];
     if (relu && !(out[i] > 0.f)) g = 0.f;
-    if (d16) d16[i] = f2h_sat(g);
+    if (d16) d16[i] = f2h_sat(g * S);
     if (d32) d32[i] = g;
     local += g;
   }
@@ -207,14 +209,46 @@ __global__ void relu_bwd_prep_kernel(const float* __restrict__ d_out, const floa
 }
 
 int relu_bwd_prep(const float* d_out, const float* out, int relu, __half* d16, float* d32, float* db, size_t n, int H,
-                  cudaStream_t s) {
+                  const float* scale, cudaStream_t s) {
   if (n == 0) return 0;
   MPGCN_CHECK(H >= 1 && H <= 1024, "relu_bwd_prep: H=%d unsupported", H);
   int threads = (256 / H) * H;          // multiple of H so each thread keeps one channel
   if (threads == 0) threads = H;
   unsigned blocks = grid_for(n, threads);
   prof_count(PROF_ELEMENTWISE);
-  relu_bwd_prep_kernel<<<blocks, threads, threads * sizeof(float), s>>>(d_out, out, relu, d16, d32, db, n, H);
+  relu_bwd_prep_kernel<<<blocks, threads, threads * sizeof(float), s>>>(d_out, out, relu, d16, d32, db, n, H, scale);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// max |x| over a tensor as the bit pattern of a non-negative float (monotone as unsigned int)
+__global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));
+}
+__global__ void make_scale_kernel(float* scale2) {
+  const float amax = __uint_as_float(*reinterpret_cast<unsigned int*>(scale2));
+  float S = 1.f;
+  if (amax > 0.f && amax < 3.0e38f) {
+    int e;
+    frexpf(amax, &e);            // amax = f * 2^e, f in [0.5, 1)
+    int k = 5 - e;               // S * amax in [16, 32)
+    k = max(-100, min(100, k));
+    S = ldexpf(1.f, k);
+  }
+  scale2[0] = S;
+  scale2[1] = 1.f / S;
+}
+
+int grad_scale_prepare(const float* d_out, size_t n, float* scale2, cudaStream_t s) {
+  MPGCN_CUDA(cudaMemsetAsync(scale2, 0, 2 * sizeof(float), s));
+  prof_count(PROF_ELEMENTWISE);
+  absmax_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_out, n, reinterpret_cast<unsigned int*>(scale2));
+  prof_count(PROF_ELEMENTWISE);
+  make_scale_kernel<<<1, 1, 0, s>>>(scale2);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -240,7 +274,9 @@ int permute_w_bwd(const float* W, __half* wq16, float* wq32, int K, int C, int H
   return 0;
 }
 
-__global__ void reduce_dw_kernel(const float* __restrict__ P, float* __restrict__ dW, int slices, int MT, int K) {
+__global__ void reduce_dw_kernel(const float* __restrict__ P, float* __restrict__ dW, int slices, int MT, int K,
+                                 const float* __restrict__ inv_scale) {
+  const float a = inv_scale ? __ldg(inv_scale) : 1.f;
   // dW index i = ((o*K + d)*32 + l)*32 + h ; partial row = (d%4)*32 + l of m-tile d/4
   const int total = K * K * 32 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -252,13 +288,13 @@ __global__ void reduce_dw_kernel(const float* __restrict__ P, float* __restrict_
     const size_t row = (size_t)mt * 128 + (d % 4) * 32 + l;
     float sum = 0.f;
     for (int s = 0; s < slices; ++s) sum += P[(((size_t)s * MT * 128 + row) * K + o) * 32 + h];
-    dW[i] = sum;
+    dW[i] = sum * a;
   }
 }
 
-int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int K, cudaStream_t s) {
+int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int K, const float* inv_scale, cudaStream_t s) {
   prof_count(PROF_ELEMENTWISE);
-  reduce_dw_kernel<<<grid_for((size_t)K * K * 1024, 256), 256, 0, s>>>(P, dW, slices, MT, K);
+  reduce_dw_kernel<<<grid_for((size_t)K * K * 1024, 256), 256, 0, s>>>(P, dW, slices, MT, K, inv_scale);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -43,6 +43,7 @@ struct Epilogue {
   int relu;
   const float* bias;         // [32] or null
   float alpha;
+  const float* alpha_dev;    // optional device scalar multiplied into alpha (gradient un-scaling), may be null
 };
 
 struct alignas(64) GemmParams {
@@ -84,11 +85,11 @@ __host__ __device__ inline size_t smem_bytes(int a_stage, int R, int BK, int sta
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void store_chunk(const Epilogue& ep, const float* sbias, long long off, uint32_t (&acc)[32]) {
+__device__ __forceinline__ void store_chunk(const Epilogue& ep, float alpha, const float* sbias, long long off, uint32_t (&acc)[32]) {
   float v[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
-    float x = __uint_as_float(acc[c]) * ep.alpha;
+    float x = __uint_as_float(acc[c]) * alpha;
     if (ep.bias) x += sbias[c];
     if (ep.relu) x = fmaxf(x, 0.f);
     v[c] = x;
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int quarter = warp & 3;     // TMEM lane quarter this warp may access
+    const float alpha = p.ep.alpha_dev ? p.ep.alpha * __ldg(p.ep.alpha_dev) : p.ep.alpha;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
         tmem_ld_32x32(t_row + (uint32_t)j * 32, regs);
         tmem_ld_wait();
         const int r = nt * R + j;
-        if (i < p.ep.m_valid && r < p.ep.r_valid) store_chunk(p.ep, sbias, base + (long long)r * p.ep.sR, regs);
+        if (i < p.ep.m_valid && r < p.ep.r_valid) store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs);
       }
       tc_fence_before();
       __syncwarp();

@@ -38,7 +38,7 @@ def pattern(a, ref, dims):
     return out
 
 
-def run_case(B, N, K, dynamic, seed=0):
+def run_case(B, N, K, dynamic, seed=0, grad_mag=1.0):
     import torch
     from mpgcn_b200 import _lib
     lib = _lib.load()
@@ -53,7 +53,7 @@ def run_case(B, N, K, dynamic, seed=0):
         Go = Gd = (torch.randn(K, N, N, generator=g) / N ** 0.5).to(dev)
     W = (torch.randn(K * K * C, H, generator=g) * (2.0 / (K * K * C + H)) ** 0.5).to(dev)
     bias = (torch.randn(H, generator=g) * 0.1).to(dev)
-    d_out = torch.randn(B, N, N, H, generator=g).to(dev)
+    d_out = (torch.randn(B, N, N, H, generator=g) * grad_mag).to(dev)
     res = {}
     Np = (N + 7) // 8 * 8
     off = lambda w: lib.mpgcn_debug_tc_workspace_offset(w, B, N, K, int(dynamic))
@@ -115,19 +115,22 @@ def run_case(B, N, K, dynamic, seed=0):
     y16 = view16(wsb, off(14), (B, K, N, N, 32)).float()
     wq16 = view16(wsb, off(15), (K, K, 32, 32)).float()       # [d][o][h][l]
     dp_ref = d_out * (out > 0)
-    res["prep_dpre"] = rel(dp16, dp_ref)
+    scale = wsb[off(18):off(18) + 8].view(torch.float32)        # [S, 1/S] power-of-two gradient scale
+    S, invS = float(scale[0]), float(scale[1])
+    res["grad_scale"] = dict(S=S, invS=invS, amax=float(d_out.abs().max()))
+    res["prep_dpre"] = rel(dp16 * invS, dp_ref)
     res["db"] = rel(db, dp_ref.sum(dim=(0, 1, 2)))
     v_ref = torch.einsum("bonm,bmeh->boneh", gob, dp16)
     res["BWD_V"] = rel(v16, v_ref)
     res["BWD_V_pattern"] = pattern(v16, v_ref, ["b", "o", "n", "e", "h"])
-    dw_ref = torch.einsum("bdnel,boneh->odlh", z16, v16).reshape(K * K * C, H)
+    dw_ref = torch.einsum("bdnel,boneh->odlh", z16, v16).reshape(K * K * C, H) * invS
     res["BWD_DW"] = rel(dW, dw_ref)
     res["BWD_DW_pattern"] = pattern(dW.view(K, K, C, H), dw_ref.view(K, K, C, H), ["o", "d", "l", "h"])
     res["permute_wq"] = rel(wq16, W4.permute(1, 0, 3, 2).half().float())
     y_ref = torch.einsum("boneh,dohl->bdnel", v16, wq16)
     res["BWD_MIX"] = rel(y16, y_ref)
     res["BWD_MIX_pattern"] = pattern(y16, y_ref, ["b", "d", "n", "e", "l"])
-    dx_ref = torch.einsum("bdnel,bdce->bncl", y16, gdb)
+    dx_ref = torch.einsum("bdnel,bdce->bncl", y16, gdb) * invS
     res["BWD_DX"] = rel(dX, dx_ref)
     res["BWD_DX_pattern"] = pattern(dX, dx_ref, ["b", "n", "c", "l"])
     # end-to-end gradients vs fp32 autograd of the factored form
@@ -158,7 +161,7 @@ def main():
     a = ap.parse_args()
     if a.one:
         B, N, K, dyn = map(int, a.one.split(","))
-        print("RESULT " + json.dumps(run_case(B, N, K, dyn)))
+        print("RESULT " + json.dumps(run_case(B, N, K, dyn, grad_mag=(1e-7 if N == 47 else 1.0))))
         return
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     allres = {}
@@ -174,7 +177,7 @@ def main():
                 allres[key] = dict(error=(r.stdout[-1500:] + "\n" + r.stderr[-2500:]))
         except subprocess.TimeoutExpired:
             allres[key] = dict(error="timeout")
-        summ = {k: (v if not isinstance(v, dict) else (f"{v['linf']:.2e}" if "linf" in v else "...")) for k, v in allres[key].items()
+        summ = {k: (v if not isinstance(v, dict) else (f"{v['linf']:.2e}" if "linf" in v else str(v))) for k, v in allres[key].items()
                 if not k.endswith("_pattern")}
         print(key, json.dumps(summ), flush=True)
         with open(a.out, "w") as f:

@@ -125,8 +125,8 @@ def test_full_model_matches_reference_fixture(name, cuda_device):
             _check(p.grad, g["grad:" + k], 2e-4 if prec == "fp32" else LOOSE_FP16_GRAD, f"{name}/{prec}/grad:{k}")
 
 
-@pytest.mark.parametrize("N,K,B,dyn", [(200, 3, 2, False), (130, 6, 1, True), (257, 2, 1, False)])
-def test_tensor_path_agrees_with_fp32_path_at_size(N, K, B, dyn, cuda_device):
+@pytest.mark.parametrize("N,K,B,dyn,gmag", [(200, 3, 2, False, 1.0), (130, 6, 1, True, 1e-7), (257, 2, 1, False, 3e4)])
+def test_tensor_path_agrees_with_fp32_path_at_size(N, K, B, dyn, gmag, cuda_device):
     """Sizes the CPU oracle cannot finish in seconds: the fp16 tcgen05 path against our exact fp32 path."""
     torch.manual_seed(N + K)
     X = torch.tanh(torch.randn(B, N, N, 32, device=cuda_device))
@@ -136,7 +136,7 @@ def test_tensor_path_agrees_with_fp32_path_at_size(N, K, B, dyn, cuda_device):
         G = torch.randn(K, N, N, device=cuda_device) / N ** 0.5
     W = torch.randn(K * K * 32, 32, device=cuda_device) * (2.0 / (K * K * 32 + 32)) ** 0.5
     b = torch.randn(32, device=cuda_device) * 0.1
-    d_out = torch.randn(B, N, N, 32, device=cuda_device)
+    d_out = torch.randn(B, N, N, 32, device=cuda_device) * gmag     # realistic (tiny) and huge gradient magnitudes: fp16 range
     Go, Gd = (G if dyn else (G, G))
     out16, saved16 = abi.forward(X, Go, Gd, W, b, True, "fp16")
     out32, saved32 = abi.forward(X, Go, Gd, W, b, True, "fp32")
