@@ -197,6 +197,7 @@ def run_ours(a):
     torch.manual_seed(1234)                                   # identical weights on every rank
     model = shim.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=hid, lstm_num_layers=1, gcn_hidden_dim=hid, gcn_num_layers=3,
                        num_nodes=N, user_bias=True, activation=nn.ReLU).to(dev)
+    model.lstm_precision = a.precision
     for mod in model.modules():
         if isinstance(mod, shim.BDGCN):
             mod.precision = a.precision

@@ -72,14 +72,18 @@ MPGCN_API int mpgcn_bdgcn_backward(const float* d_out, const float* out, const f
  * state, returning only the last hidden state (reference MPGCN.py:69,80-87,100-104).
  *   x_seq [B,T,NN] (= the model input [B,T,N,N,1] unchanged, NN = N*N)
  *   w_ih [4C,1], w_hh [4C,C], b_ih [4C], b_hh [4C]   (gate order i,f,g,o)
- *   hT   [B*NN, C] */
+ *   hT   [B*NN, C]
+ * precision 0: fp32 CUDA-core kernels (C <= 64); precision 1: tcgen05 gate GEMM with the recurrent h rounded to
+ * fp16 as MMA operand, state and activations in fp32 (C == 32). */
+MPGCN_API int mpgcn_lstm_precision_supported(int T, int C, int precision);
+MPGCN_API size_t mpgcn_lstm_bwd_workspace_bytes(int B, int T, long long NN, int C, int precision);
 MPGCN_API int mpgcn_lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
-                            int B, int T, long long NN, int C, void* stream);
+                            int B, int T, long long NN, int C, int precision, void* stream);
 /* BPTT for the above. d_hT [B*NN,C]; outputs d_w_ih [4C], d_w_hh [4C,C], d_b_ih [4C], d_b_hh [4C];
- * d_x [B,T,NN] or NULL. */
+ * d_x [B,T,NN] or NULL; workspace from mpgcn_lstm_bwd_workspace_bytes (256-byte aligned). */
 MPGCN_API int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                             const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
-                             long long NN, int C, void* stream);
+                             const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
+                             size_t workspace_bytes, int B, int T, long long NN, int C, int precision, void* stream);
 
 /* Launch accounting (bench.py evidence).  Every launch of a kernel of this library is counted per tag
  * (0 FWD_A, 1 FWD_MIX, 2 FWD_B, 3 BWD_V, 4 BWD_DW, 5 BWD_MIX, 6 BWD_DX: tcgen05 contractions; 7 fp32 SIMT GEMM;

@@ -80,6 +80,7 @@ class MPGCN(nn.Module):
         self.lstm_hidden_dim = lstm_hidden_dim
         self.lstm_num_layers = lstm_num_layers
         self.gcn_num_layers = gcn_num_layers
+        self.lstm_precision = None      # None -> ops.default_precision(); or "auto" / "fp16" / "fp32"
         self.branch_models = nn.ModuleList()
         for _ in range(self.M):
             branch = nn.ModuleDict()
@@ -100,7 +101,7 @@ class MPGCN(nn.Module):
     def _temporal(self, lstm: nn.LSTM, x_seq: torch.Tensor) -> torch.Tensor:
         B, T, N, _, I = x_seq.shape
         if I == 1 and lstm.num_layers == 1 and lstm.hidden_size <= 64:
-            return ops.lstm_last(x_seq, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)
+            return ops.lstm_last(x_seq, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0, precision=self.lstm_precision)
         # configurations the trainer never builds (Model_Trainer.py:49-51 hard-codes input_dim=1, 1 layer)
         lstm_in = x_seq.permute(0, 2, 3, 1, 4).reshape(B * N * N, T, I)
         return lstm(lstm_in)[0][:, -1, :]

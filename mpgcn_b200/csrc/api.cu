@@ -89,19 +89,39 @@ long long mpgcn_debug_tc_workspace_offset(int which, int B, int N, int K, int dy
   return tc_debug_offset(mk(B, N, K, 32, 32, dynamic, 0), which);
 }
 
+int mpgcn_lstm_precision_supported(int T, int C, int precision) {
+  if (precision == PREC_FP32_SIMT) return (T >= 1 && C >= 1 && C <= 64) ? 1 : 0;
+  if (precision == PREC_FP16_TC) return lstm_tc_supported(T, C) ? 1 : 0;
+  return 0;
+}
+
+size_t mpgcn_lstm_bwd_workspace_bytes(int B, int T, long long NN, int C, int precision) {
+  (void)C;
+  return precision == PREC_FP16_TC ? lstm_tc_bwd_workspace_bytes(B, T, NN) : 256;
+}
+
 int mpgcn_lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
-                            int B, int T, long long NN, int C, void* stream) {
+                            int B, int T, long long NN, int C, int precision, void* stream) {
   MPGCN_CHECK(x_seq && w_ih && w_hh && b_ih && b_hh && hT, "mpgcn_lstm_last_forward: null pointer argument");
-  return lstm_last_forward(x_seq, w_ih, w_hh, b_ih, b_hh, hT, B, T, NN, C, static_cast<cudaStream_t>(stream));
+  MPGCN_CHECK(B >= 1 && T >= 1 && NN >= 1, "mpgcn_lstm_last_forward: empty input");
+  MPGCN_CHECK(mpgcn_lstm_precision_supported(T, C, precision), "lstm: precision %d does not support T=%d, hidden=%d", precision, T, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == PREC_FP16_TC) return lstm_last_forward_tc(x_seq, w_ih, w_hh, b_ih, b_hh, hT, B, T, NN, st);
+  return lstm_last_forward(x_seq, w_ih, w_hh, b_ih, b_hh, hT, B, T, NN, C, st);
 }
 
 int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                             const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
-                             long long NN, int C, void* stream) {
+                             const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
+                             size_t workspace_bytes, int B, int T, long long NN, int C, int precision, void* stream) {
   MPGCN_CHECK(x_seq && w_ih && w_hh && b_ih && b_hh && d_hT && d_w_ih && d_w_hh && d_b_ih && d_b_hh,
               "mpgcn_lstm_last_backward: null pointer argument");
-  return lstm_last_backward(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, B, T, NN, C,
-                            static_cast<cudaStream_t>(stream));
+  MPGCN_CHECK(B >= 1 && T >= 1 && NN >= 1, "mpgcn_lstm_last_backward: empty input");
+  MPGCN_CHECK(mpgcn_lstm_precision_supported(T, C, precision), "lstm: precision %d does not support T=%d, hidden=%d", precision, T, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == PREC_FP16_TC)
+    return lstm_last_backward_tc(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, B, T, NN, workspace,
+                                 workspace_bytes, st);
+  return lstm_last_backward(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, B, T, NN, C, st);
 }
 
 }  // extern "C"

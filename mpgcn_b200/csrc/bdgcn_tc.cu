@@ -28,9 +28,10 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline int pad8(int n) { return (n + 7) / 8 * 8; }
 const int kBig = 1 << 30;
 
-tc::OperandMap omap(int z_div, int z_mod, int z_mul, int seg_mul, int k_seg) {
+tc::OperandMap omap(int z_div, int z_mod, int z_mul, int seg_mul, int k_seg, int seg_mod = 1 << 30, int seg_hi_mul = 0) {
   tc::OperandMap m;
   m.z_div = z_div; m.z_mod = z_mod; m.z_mul = z_mul; m.seg_mul = seg_mul; m.k_seg = k_seg;
+  m.seg_mod = seg_mod; m.seg_hi_mul = seg_hi_mul;
   return m;
 }
 
@@ -87,7 +88,7 @@ static size_t g16_elems(const BdgcnShape& s) { return (size_t)(s.dynamic ? s.B :
 size_t tc_saved_bytes(const BdgcnShape& s) { return (size_t)s.B * s.K * n2(s) * s.C * sizeof(__half); }
 
 // workspace layouts (byte offsets); also served to tests by mpgcn_debug_tc_workspace_offset()
-struct FwdLayout { size_t x16, gd16, go16, w16, u16, z16, total; };
+struct FwdLayout { size_t x16, gd16, go16, w16, u16, z16, dd, dgo, total; };
 struct BwdLayout { size_t dp16, gd16, go16, v16, y16, wq16, partials, scale, total; };
 static size_t take(size_t& off, size_t bytes) {
   off = align_up(off, 1024);
@@ -101,8 +102,10 @@ static FwdLayout fwd_layout(const BdgcnShape& s) {
   L.x16 = take(off, (size_t)s.B * n2(s) * 32 * 2);
   L.gd16 = take(off, g16_elems(s) * 2);
   L.go16 = take(off, g16_elems(s) * 2);
-  L.w16 = take(off, (size_t)s.K * s.K * 32 * 32 * 2);
+  L.w16 = take(off, (size_t)2 * s.K * s.K * 32 * 32 * 2);      // [hi | lo]
   L.u16 = take(off, (size_t)s.B * s.K * n2(s) * 32 * 2);
+  L.dd = take(off, (size_t)(s.dynamic ? s.B : 1) * s.K * s.N * 4);   // support-diagonal fp16 remainders (destination / origin)
+  L.dgo = take(off, (size_t)(s.dynamic ? s.B : 1) * s.K * s.N * 4);
   L.z16 = take(off, tc_saved_bytes(s));            // used only when the caller passes no `saved` buffer
   L.total = align_up(off, 1024);
   return L;
@@ -150,6 +153,8 @@ long long tc_debug_offset(const BdgcnShape& s, int which) {
     case 2: return (long long)F.go16;
     case 3: return (long long)F.w16;
     case 4: return (long long)F.u16;
+    case 5: return (long long)F.dd;
+    case 6: return (long long)F.dgo;
     case 10: return (long long)Bw.dp16;
     case 11: return (long long)Bw.gd16;
     case 12: return (long long)Bw.go16;
@@ -167,7 +172,7 @@ long long tc_debug_offset(const BdgcnShape& s, int which) {
 // individual contractions
 // ---------------------------------------------------------------------------------------
 // FWD_A:  Z16[b][d][n][e][l] = sum_c G_d[c][e] X16[b][n][c][l]
-static int run_fwd_a(const BdgcnShape& s, const __half* gd16, const __half* x16, __half* z16, cudaStream_t st) {
+static int run_fwd_a(const BdgcnShape& s, const __half* gd16, const __half* x16, __half* z16, const float* delta_d, cudaStream_t st) {
   const int N = s.N, K = s.K, Np = pad8(N);
   GemmParams p;
   init_params(p);
@@ -180,31 +185,36 @@ static int run_fwd_a(const BdgcnShape& s, const __half* gd16, const __half* x16,
   p.ep.out = z16; p.ep.out_f16 = 1;
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
+  // Z[b,d,n,e,:] += (G_d[e,e] - fp16(G_d[e,e])) * X16[b,n,e,:]
+  p.ep.corr_src = x16; p.ep.corr_delta = delta_d; p.ep.corr_nseg = 1;
+  p.ep.cZ = (long long)N * N * 32; p.ep.cI = 32; p.ep.cR = (long long)N * 32; p.ep.cSeg = 0;
   prof_set_next(PROF_FWD_A, 2.0 * s.B * K * (double)N * N * N * 32);
   return tc::launch_contract(tc::A_MN128, 64, p, st);
 }
 
 // MIX: D16[b][r][row][32] = sum_{seg} A16[b][seg][row][32] * Wm16[r][(seg,32)][32]   (both channel mixes)
-static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, __half* d16, int tag, cudaStream_t st) {
+static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, int w_halves, __half* d16, int tag, cudaStream_t st) {
   const int K = s.K;
   const long long NN = (long long)s.N * s.N;
   GemmParams p;
   init_params(p);
   if (int e = map_planes(&p.a_map, a16, NN, (long long)s.B * K)) return e;
-  if (int e = map_chunks(&p.b_map, w16, (long long)K * 32, 32, K, (long long)K * 32 * 32, 1, (long long)K * K * 32 * 32, 32, K)) return e;
-  p.am = omap(1, kBig, K, 1, 0);        // plane = b*K + seg
-  p.bm = omap(1, 1, 0, 0, 32);          // k rows = seg*32
+  if (int e = map_chunks(&p.b_map, w16, (long long)K * 32, 32, K, (long long)K * 32 * 32, w_halves, (long long)K * K * 32 * 32, 32, K)) return e;
+  // segment s: plane = b*K + (s % K); weight rows (s % K)*32 of half s / K  (half 0 = fp16(W), half 1 = fp16(W - half 0))
+  p.am = omap(1, kBig, K, 1, 0, K, 0);
+  p.bm = omap(1, 1, 0, 0, 32, K, 1);
   p.MT = ceil_div(NN, 128); p.NT = 1; p.Z = s.B; p.R = K;
-  p.kb_total = K; p.kb_per_seg = 1;
+  p.kb_total = K * w_halves; p.kb_per_seg = 1;
   p.ep.out = d16; p.ep.out_f16 = 1;
   p.ep.sZ = (long long)K * NN * 32; p.ep.sI = 32; p.ep.sR = NN * 32;
   p.ep.m_valid = (int)NN; p.ep.r_valid = K;
-  prof_set_next(tag, 2.0 * s.B * (double)K * K * NN * 32 * 32);
+  prof_set_next(tag, 2.0 * s.B * (double)K * K * NN * 32 * 32);   // algorithmic flops (the fp16 hi/lo weight split doubles the executed MMAs)
   return tc::launch_contract(tc::A_K64, 32, p, st);
 }
 
 // FWD_B: out[b][m][e][h] = act( sum_{(o,n)} Gflat[(o,n)][m] U16[b][(o,n)][e][h] + bias[h] )
-static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16, const float* bias, float* out, cudaStream_t st) {
+static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16, const float* bias, float* out, const float* delta_o,
+                     cudaStream_t st) {
   const int N = s.N, K = s.K, Np = pad8(N);
   GemmParams p;
   init_params(p);
@@ -219,6 +229,9 @@ static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16,
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
   p.ep.bias = bias; p.ep.relu = s.act;
+  // pre[b,m,e,:] += sum_o (G_o[m,m] - fp16(G_o[m,m])) * U16[b,o,m,e,:]
+  p.ep.corr_src = u16; p.ep.corr_delta = delta_o; p.ep.corr_nseg = K;
+  p.ep.cZ = (long long)K * N * N * 32; p.ep.cSeg = (long long)N * N * 32; p.ep.cI = (long long)N * 32; p.ep.cR = 32;
   prof_set_next(PROF_FWD_B, 2.0 * s.B * K * (double)N * N * N * 32);
   return tc::launch_contract(tc::A_MN128, 64, p, st);
 }
@@ -314,16 +327,26 @@ int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const
   __half* go16 = reinterpret_cast<__half*>(wb + L.go16);
   __half* w16 = reinterpret_cast<__half*>(wb + L.w16);
   __half* u16 = reinterpret_cast<__half*>(wb + L.u16);
+  float* delta_d = reinterpret_cast<float*>(wb + L.dd);
+  float* delta_o = reinterpret_cast<float*>(wb + L.dgo);
   __half* z16 = saved ? static_cast<__half*>(saved) : reinterpret_cast<__half*>(wb + L.z16);
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(z16) & 63) == 0, "`saved` buffer must be 64-byte aligned");
 
   const __half* go_used = nullptr;
   if (int e = cvt_f32_to_f16(X, x16, (size_t)s.B * NN * 32, st)) return e;
   if (int e = convert_supports(s, Go, Gd, go16, gd16, &go_used, st)) return e;
-  if (int e = cvt_f32_to_f16(W, w16, (size_t)s.K * s.K * 32 * 32, st)) return e;
-  if (int e = run_fwd_a(s, gd16, x16, z16, st)) return e;
-  if (int e = run_mix(s, z16, w16, u16, PROF_FWD_MIX, st)) return e;
-  if (int e = run_fwd_b(s, go_used, u16, bias, out, st)) return e;
+  const size_t wn = (size_t)s.K * s.K * 32 * 32;
+  if (int e = cvt_f32_to_f16_hilo(W, w16, w16 + wn, wn, st)) return e;
+  const size_t planes = (size_t)(s.dynamic ? s.B : 1) * s.K;
+  if (int e = support_diag_delta(Gd, delta_d, planes, s.N, st)) return e;
+  const float* delta_o_used = delta_d;
+  if (Go != Gd) {
+    if (int e = support_diag_delta(Go, delta_o, planes, s.N, st)) return e;
+    delta_o_used = delta_o;
+  }
+  if (int e = run_fwd_a(s, gd16, x16, z16, delta_d, st)) return e;
+  if (int e = run_mix(s, z16, w16, 2, u16, PROF_FWD_MIX, st)) return e;
+  if (int e = run_fwd_b(s, go_used, u16, bias, out, delta_o_used, st)) return e;
   return 0;
 }
 
@@ -357,7 +380,7 @@ int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out,
   if (int e = reduce_dw_partials(partials, dW, slices, mt, s.K, scale2 + 1, st)) return e;
   if (dX) {
     if (int e = permute_w_bwd(W, wq16, nullptr, s.K, 32, 32, st)) return e;
-    if (int e = run_mix(s, v16, wq16, y16, PROF_BWD_MIX, st)) return e;
+    if (int e = run_mix(s, v16, wq16, 1, y16, PROF_BWD_MIX, st)) return e;
     if (int e = run_bwd_dx(s, gd16, y16, dX, scale2 + 1, st)) return e;
   }
   return 0;

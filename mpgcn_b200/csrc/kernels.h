@@ -34,6 +34,10 @@ int simt_sgemm(const SgemmParams& p, cudaStream_t stream);
 
 // ---- elementwise / layout helpers (prep_kernels.cu) ---------------------------------------
 int cvt_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t s);
+// hi = fp16(x), lo = fp16(x - hi): x == hi + lo to ~22 bits
+int cvt_f32_to_f16_hilo(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t s);
+// delta[p*N + i] = G[p][i][i] - float(fp16(G[p][i][i])) for `planes` N x N matrices
+int support_diag_delta(const float* G, float* delta, size_t planes, int N, cudaStream_t s);
 // [rows][cols] fp32 -> [rows][ld] fp16 (ld >= cols, padding zeroed)
 int cvt_f32_to_f16_padded(const float* src, __half* dst, size_t rows, int cols, int ld, cudaStream_t s);
 // d_pre = d_out * (out > 0) (relu) or d_out; fp16 and/or fp32 output; db[h] += sum (db may be null; pre-zeroed)
@@ -53,6 +57,15 @@ int lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, 
 int lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                        const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
                        long long NN, int C, cudaStream_t s);
+
+// tcgen05 LSTM (lstm_tc.cu): hidden size 32 only
+bool lstm_tc_supported(int T, int C);
+size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN);
+int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
+                         int B, int T, long long NN, cudaStream_t s);
+int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                          const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
+                          long long NN, void* ws, size_t ws_bytes, cudaStream_t s);
 
 // ---- BDGCN layer orchestration ---------------------------------------------------------------
 struct BdgcnShape {

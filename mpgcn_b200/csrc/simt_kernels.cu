@@ -160,6 +160,40 @@ int cvt_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t s) {
   return 0;
 }
 
+__global__ void cvt_f16_hilo_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = src[i];
+    const __half h = f2h_sat(x);
+    hi[i] = h;
+    lo[i] = f2h_sat(x - __half2float(h));
+  }
+}
+int cvt_f32_to_f16_hilo(const float* src, __half* hi, __half* lo, size_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  prof_count(PROF_ELEMENTWISE);
+  cvt_f16_hilo_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, hi, lo, n);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void diag_delta_kernel(const float* __restrict__ G, float* __restrict__ delta, size_t planes, int N) {
+  const size_t total = planes * (size_t)N;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const size_t p = t / N;
+    const int i = (int)(t - p * N);
+    const float g = G[(p * N + i) * (size_t)N + i];
+    delta[t] = g - __half2float(f2h_sat(g));
+  }
+}
+int support_diag_delta(const float* G, float* delta, size_t planes, int N, cudaStream_t s) {
+  prof_count(PROF_ELEMENTWISE);
+  diag_delta_kernel<<<grid_for(planes * N, 256), 256, 0, s>>>(G, delta, planes, N);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 __global__ void cvt_f16_padded_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t rows, int cols, int ld) {
   const size_t total = rows * (size_t)ld;
   const size_t stride = (size_t)gridDim.x * blockDim.x;

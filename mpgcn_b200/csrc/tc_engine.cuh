@@ -29,9 +29,9 @@ enum AKind : int { A_MN128 = 0, A_K128 = 1, A_K64 = 2, A_MN64 = 3 };
 
 // tile/k-block -> TMA coordinate map of one operand
 struct OperandMap {
-  int z_div, z_mod, z_mul;   // z' = ((z / z_div) % z_mod) * z_mul + seg * seg_mul
-  int seg_mul;
-  int k_seg;                 // k coordinate (elements) += seg * k_seg
+  int z_div, z_mod, z_mul;   // z' = ((z / z_div) % z_mod) * z_mul + (seg % seg_mod) * seg_mul + (seg / seg_mod) * seg_hi_mul
+  int seg_mod, seg_mul, seg_hi_mul;
+  int k_seg;                 // k coordinate (elements) += (seg % seg_mod) * k_seg
 };
 
 struct Epilogue {
@@ -44,6 +44,12 @@ struct Epilogue {
   const float* bias;         // [32] or null
   float alpha;
   const float* alpha_dev;    // optional device scalar multiplied into alpha (gradient un-scaling), may be null
+  // optional diagonal correction (forward only): out[z][i][r][:] += sum_seg delta[(zA*corr_nseg + seg)*m_valid + i] *
+  // corr_src[zB*cZ + seg*cSeg + i*cI + r*cR + :], the exact remainder of the support diagonal lost by its fp16 rounding
+  const __half* corr_src;
+  const float* corr_delta;
+  long long cZ, cI, cR, cSeg;
+  int corr_nseg;             // <= 8
 };
 
 struct alignas(64) GemmParams {
@@ -198,10 +204,12 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
           mbar_arrive_expect_tx(&full[stage], (uint32_t)(A_STAGE + B_STAGE));
           const int seg = kb / p.kb_per_seg;
           const int kk = kb - seg * p.kb_per_seg;
-          const int zA = zA0 + seg * p.am.seg_mul;
-          const int zB = zB0 + seg * p.bm.seg_mul;
-          const int kA = kk * BK + seg * p.am.k_seg;
-          const int kB = kk * BK + seg * p.bm.k_seg;
+          const int sa_lo = seg % p.am.seg_mod, sa_hi = seg / p.am.seg_mod;
+          const int sb_lo = seg % p.bm.seg_mod, sb_hi = seg / p.bm.seg_mod;
+          const int zA = zA0 + sa_lo * p.am.seg_mul + sa_hi * p.am.seg_hi_mul;
+          const int zB = zB0 + sb_lo * p.bm.seg_mul + sb_hi * p.bm.seg_hi_mul;
+          const int kA = kk * BK + sa_lo * p.am.k_seg;
+          const int kB = kk * BK + sb_lo * p.bm.k_seg;
           uint8_t* a_dst = sA + (size_t)stage * A_STAGE;
           uint8_t* b_dst = sB + (size_t)stage * B_STAGE;
           if (AK == A_MN128) {          // dims (m, k, z, 1), two 64-wide m boxes
@@ -275,12 +283,47 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
       const int i = mt * 128 + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAccCols;
       const long long base = (long long)z * p.ep.sZ + (long long)i * p.ep.sI;
+      float dl[8];
+      long long cbase = 0;
+      bool any_corr = false;
+      if (p.ep.corr_src != nullptr) {
+        const int zA = ((z / p.am.z_div) % p.am.z_mod) * p.am.z_mul;
+        const int zB = ((z / p.bm.z_div) % p.bm.z_mod) * p.bm.z_mul;
+        cbase = (long long)zB * p.ep.cZ + (long long)i * p.ep.cI;
+#pragma unroll
+        for (int sgi = 0; sgi < 8; ++sgi) {
+          dl[sgi] = (sgi < p.ep.corr_nseg && i < p.ep.m_valid)
+                        ? __ldg(p.ep.corr_delta + ((long long)zA * p.ep.corr_nseg + sgi) * p.ep.m_valid + i) : 0.f;
+          any_corr |= (dl[sgi] != 0.f);
+        }
+      }
       for (int j = 0; j < R; ++j) {
         uint32_t regs[32];
         tmem_ld_32x32(t_row + (uint32_t)j * 32, regs);
         tmem_ld_wait();
         const int r = nt * R + j;
-        if (i < p.ep.m_valid && r < p.ep.r_valid) store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs);
+        if (i < p.ep.m_valid && r < p.ep.r_valid) {
+          if (any_corr) {
+#pragma unroll
+            for (int sgi = 0; sgi < 8; ++sgi) {
+              if (sgi < p.ep.corr_nseg && dl[sgi] != 0.f) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.ep.corr_src + cbase + (long long)sgi * p.ep.cSeg + (long long)r * p.ep.cR);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 v = __ldg(src + q);
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(h2[e]);
+                    regs[8 * q + 2 * e] = __float_as_uint(fmaf(dl[sgi], f.x, __uint_as_float(regs[8 * q + 2 * e])));
+                    regs[8 * q + 2 * e + 1] = __float_as_uint(fmaf(dl[sgi], f.y, __uint_as_float(regs[8 * q + 2 * e + 1])));
+                  }
+                }
+              }
+            }
+          }
+          store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs);
+        }
       }
       tc_fence_before();
       __syncwarp();

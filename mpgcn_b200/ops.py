@@ -117,19 +117,34 @@ def bdgcn(X: torch.Tensor, G, W: torch.Tensor, b, relu: bool, precision=None) ->
     return _BDGCNFn.apply(X, G_o, G_d, W, b, dynamic, 1 if relu else 0, precision)
 
 
+def resolve_lstm_precision(name, T, C) -> int:
+    name = default_precision() if name is None else name
+    if name not in _PREC_NAMES:
+        raise ValueError(f"unknown precision {name!r}; expected one of {sorted(_PREC_NAMES)}")
+    lib = _lib.load()
+    if name == "auto":
+        return _lib.PREC_FP16_TC if lib.mpgcn_lstm_precision_supported(T, C, _lib.PREC_FP16_TC) else _lib.PREC_FP32
+    code = _PREC_NAMES[name]
+    if not lib.mpgcn_lstm_precision_supported(T, C, code):
+        raise RuntimeError(f"LSTM precision {name!r} does not support T={T}, hidden={C} (tensor path needs hidden == 32)")
+    return code
+
+
 class _LSTMLastFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_seq, w_ih, w_hh, b_ih, b_hh):
+    def forward(ctx, x_seq, w_ih, w_hh, b_ih, b_hh, precision):
         lib = _lib.load()
         B, T = x_seq.shape[0], x_seq.shape[1]
         NN = x_seq[0, 0].numel()
         C = w_hh.shape[1]
+        prec = resolve_lstm_precision(precision, T, C)
         xc = _f32c(x_seq)
         ws = [_f32c(t) for t in (w_ih, w_hh, b_ih, b_hh)]
         hT = torch.empty((B * NN, C), dtype=torch.float32, device=x_seq.device)
         with torch.cuda.device(x_seq.device):
-            _lib.check(lib.mpgcn_lstm_last_forward(_ptr(xc), *[_ptr(t) for t in ws], _ptr(hT), B, T, NN, C, _stream()), "lstm_last_forward")
-        ctx.dims = (B, T, NN, C)
+            _lib.check(lib.mpgcn_lstm_last_forward(_ptr(xc), *[_ptr(t) for t in ws], _ptr(hT), B, T, NN, C, prec, _stream()),
+                       "lstm_last_forward")
+        ctx.dims = (B, T, NN, C, prec)
         ctx.save_for_backward(xc, *ws)
         return hT
 
@@ -137,20 +152,21 @@ class _LSTMLastFn(torch.autograd.Function):
     def backward(ctx, d_hT):
         lib = _lib.load()
         xc, w_ih, w_hh, b_ih, b_hh = ctx.saved_tensors
-        B, T, NN, C = ctx.dims
+        B, T, NN, C, prec = ctx.dims
         d_hT = _f32c(d_hT)
         dev = xc.device
         g_wih, g_whh = torch.empty_like(w_ih), torch.empty_like(w_hh)
         g_bih, g_bhh = torch.empty_like(b_ih), torch.empty_like(b_hh)
         d_x = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        ws = _scratch(lib.mpgcn_lstm_bwd_workspace_bytes(B, T, NN, C, prec), dev)
         with torch.cuda.device(dev):
             _lib.check(lib.mpgcn_lstm_last_backward(_ptr(xc), _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(d_hT), _ptr(g_wih),
-                                                    _ptr(g_whh), _ptr(g_bih), _ptr(g_bhh), _ptr(d_x), B, T, NN, C, _stream()),
-                       "lstm_last_backward")
-        return d_x, g_wih, g_whh, g_bih, g_bhh
+                                                    _ptr(g_whh), _ptr(g_bih), _ptr(g_bhh), _ptr(d_x), _ptr(ws), ws.numel(), B, T, NN, C,
+                                                    prec, _stream()), "lstm_last_backward")
+        return d_x, g_wih, g_whh, g_bih, g_bhh, None
 
 
-def lstm_last(x_seq: torch.Tensor, w_ih, w_hh, b_ih, b_hh) -> torch.Tensor:
+def lstm_last(x_seq: torch.Tensor, w_ih, w_hh, b_ih, b_hh, precision=None) -> torch.Tensor:
     """h_T of a 1-layer, input-size-1 LSTM run over every OD cell of x_seq [B,T,N,N,1] -> [B*N*N, C]."""
     _require_cuda(x_seq, "x_seq")
-    return _LSTMLastFn.apply(x_seq, w_ih, w_hh, b_ih, b_hh)
+    return _LSTMLastFn.apply(x_seq, w_ih, w_hh, b_ih, b_hh, precision)

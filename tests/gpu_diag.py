@@ -76,20 +76,22 @@ def run_case(B, N, K, dynamic, seed=0, grad_mag=1.0):
     x16 = view16(ws, off(0), (B, N, N, 32)).float()
     gd16 = view16(ws, off(1), (nz, K, N, Np))[..., :N].float()
     go16 = gd16 if (not dynamic) else view16(ws, off(2), (nz, K, N, Np))[..., :N].float()
-    w16 = view16(ws, off(3), (K, K, 32, 32)).float()
+    w16 = view16(ws, off(3), (2, K, K, 32, 32)).float().sum(0)          # fp16 hi + lo halves of W
+    dd = ws[off(5):off(5) + 4 * nz * K * N].view(torch.float32).view(nz, K, N).expand(B, K, N)
+    dgo = dd if (not dynamic) else ws[off(6):off(6) + 4 * nz * K * N].view(torch.float32).view(nz, K, N).expand(B, K, N)
     u16 = view16(ws, off(4), (B, K, N, N, 32)).float()
     z16 = saved.view(torch.float16).view(B, K, N, N, 32).float()
     res["cvt_x"] = rel(x16, X)
     res["cvt_g"] = rel(gd16, Gd.view(nz, K, N, N))
     gdb = gd16.expand(B, K, N, N)
     gob = go16.expand(B, K, N, N)
-    z_ref = torch.einsum("bncl,bdce->bdnel", x16, gdb)
+    z_ref = torch.einsum("bncl,bdce->bdnel", x16, gdb) + torch.einsum("bde,bnel->bdnel", dd, x16)   # + diagonal remainder
     res["FWD_A"] = rel(z16, z_ref)
     res["FWD_A_pattern"] = pattern(z16, z_ref, ["b", "d", "n", "e", "l"])
     u_ref = torch.einsum("bdnel,odlh->boneh", z16, w16)
     res["FWD_MIX"] = rel(u16, u_ref)
     res["FWD_MIX_pattern"] = pattern(u16, u_ref, ["b", "o", "n", "e", "h"])
-    o_ref = torch.relu(torch.einsum("bonm,boneh->bmeh", gob, u16) + bias)
+    o_ref = torch.relu(torch.einsum("bonm,boneh->bmeh", gob, u16) + torch.einsum("bom,bomeh->bmeh", dgo, u16) + bias)
     res["FWD_B"] = rel(out, o_ref)
     res["FWD_B_pattern"] = pattern(out, o_ref, ["b", "m", "e", "h"])
     # end-to-end vs fp32 factored reference

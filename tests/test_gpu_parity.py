@@ -30,10 +30,11 @@ LOOSE_FP16_GRAD = 8e-2
 import abi
 
 
-def _check(a, ref, tol, what):
+def _check(a, ref, tol, what, l2_only=False):
     a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
     linf, l2 = orc.rel_errors(a, ref)
-    assert np.isfinite(linf) and linf <= tol and l2 <= tol, f"{what}: rel_Linf={linf:.3e} rel_L2={l2:.3e} > {tol}"
+    ok = np.isfinite(linf) and l2 <= tol and (l2_only or linf <= tol)
+    assert ok, f"{what}: rel_Linf={linf:.3e} rel_L2={l2:.3e} > {tol}"
     return linf, l2
 
 
@@ -76,8 +77,8 @@ def test_bdgcn_layer_matches_reference_fixture(name, cuda_device):
         else:   # gradient of the computed function: oracle backward with the engine's ReLU mask
             Gn = (g["G_o"], g["G_d"]) if int(g["dynamic"]) else g["G"]
             refs = orc.bdgcn_backward(g["X"], Gn, g["W"], g.get("b"), "relu", g["d_out"], mask_from=out.detach().cpu().numpy())
-            _check(X.grad, g["dX"], LOOSE_FP16_GRAD, f"{name}/{prec}/dX vs reference")
-            _check(layer.W.grad, g["dW"], LOOSE_FP16_GRAD, f"{name}/{prec}/dW vs reference")
+            _check(X.grad, g["dX"], LOOSE_FP16_GRAD, f"{name}/{prec}/dX vs reference", l2_only=True)   # a flipped mask element is an O(1) local change
+            _check(layer.W.grad, g["dW"], LOOSE_FP16_GRAD, f"{name}/{prec}/dW vs reference", l2_only=True)
         _check(X.grad, refs[0], tb, f"{name}/{prec}/dX")
         _check(layer.W.grad, refs[1], tb, f"{name}/{prec}/dW")
         if "b" in g:
@@ -91,13 +92,39 @@ def test_lstm_last_matches_reference_fixture(name, cuda_device):
     # the kernel reads x_seq as [B,T,NN]; fixture sequences are [S,T,1] -> one batch element, NN = S
     x = _t(np.ascontiguousarray(g["x"][:, :, 0].T)[None], cuda_device, grad=True)        # [1,T,S]
     ws = [_t(g[k], cuda_device, grad=True) for k in ("w_ih", "w_hh", "b_ih", "b_hh")]
-    hT = ops.lstm_last(x.view(1, T, S, 1, 1), *ws)
-    hT.backward(_t(g["d_hT"], cuda_device))
-    torch.cuda.synchronize()
-    _check(hT, g["hT"], 1e-4, "hT")
-    for t, k in zip(ws, ("dw_ih", "dw_hh", "db_ih", "db_hh")):
-        _check(t.grad, g[k], 2e-4, k)
-    _check(x.grad[0].T, g["dx"][:, :, 0], 2e-4, "dx")
+    C = g["w_hh"].shape[1]
+    for prec in (["fp32", "fp16"] if C == 32 else ["fp32"]):
+        for t in [x] + ws:
+            t.grad = None
+        hT = ops.lstm_last(x.view(1, T, S, 1, 1), *ws, precision=prec)
+        hT.backward(_t(g["d_hT"], cuda_device))
+        torch.cuda.synchronize()
+        # fp32 kernels: SFU exp/rcp noise only.  tcgen05 path: recurrent h (and the stashed gates in backward) in fp16.
+        tf, tb = (1e-4, 2e-4) if prec == "fp32" else (1e-3, 2e-3)
+        _check(hT, g["hT"], tf, f"{prec}/hT")
+        for t, k in zip(ws, ("dw_ih", "dw_hh", "db_ih", "db_hh")):
+            _check(t.grad, g[k], tb, f"{prec}/{k}")
+        _check(x.grad[0].T, g["dx"][:, :, 0], tb, f"{prec}/dx")
+
+
+@pytest.mark.parametrize("S,T,gmag", [(1000, 12, 1.0), (300, 7, 1e-7), (129, 1, 1.0), (4097, 3, 1e3)])
+def test_lstm_tensor_path_agrees_with_fp32_path(S, T, gmag, cuda_device):
+    """Ragged tile counts, T = 1, tiny / huge gradient magnitudes: tcgen05 LSTM vs the fp32 CUDA-core LSTM."""
+    torch.manual_seed(S + T)
+    lstm = nn.LSTM(1, 32, 1, batch_first=True).to(cuda_device)
+    ws0 = [lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0]
+    x0 = torch.rand(2, T, S, 1, 1, device=cuda_device) * 8
+    d_h = torch.randn(2 * S, 32, device=cuda_device) * gmag
+    res = {}
+    for prec in ("fp32", "fp16"):
+        ws = [w.detach().clone().requires_grad_(True) for w in ws0]
+        x = x0.clone().requires_grad_(True)
+        h = ops.lstm_last(x, *ws, precision=prec)
+        h.backward(d_h)
+        res[prec] = [h.detach()] + [w.grad for w in ws] + [x.grad]
+    names = ("hT", "dw_ih", "dw_hh", "db_ih", "db_hh", "dx")
+    for a, r, n in zip(res["fp16"], res["fp32"], names):
+        _check(a, r.cpu().numpy(), 1e-3 if n == "hT" else 2e-3, f"S={S} T={T} {n}")
 
 
 @pytest.mark.parametrize("name", golden_names("mpgcn_"))
@@ -111,6 +138,7 @@ def test_full_model_matches_reference_fixture(name, cuda_device):
                            num_nodes=N, user_bias=True, activation=nn.ReLU)
         model.load_state_dict(params)                       # a reference checkpoint, loaded unchanged
         model = model.to(cuda_device)
+        model.lstm_precision = prec
         for mod in model.modules():
             if isinstance(mod, shim.BDGCN):
                 mod.precision = prec
@@ -122,7 +150,7 @@ def test_full_model_matches_reference_fixture(name, cuda_device):
         _check(y, g["y"], tf, f"{name}/{prec}/y")
         for k, p in model.named_parameters():
             # fp32: summation-order noise only.  fp16: ReLU-mask flips in 4 stacked ReLUs (see module docstring)
-            _check(p.grad, g["grad:" + k], 2e-4 if prec == "fp32" else LOOSE_FP16_GRAD, f"{name}/{prec}/grad:{k}")
+            _check(p.grad, g["grad:" + k], 2e-4 if prec == "fp32" else LOOSE_FP16_GRAD, f"{name}/{prec}/grad:{k}", l2_only=(prec != "fp32"))
 
 
 @pytest.mark.parametrize("N,K,B,dyn,gmag", [(200, 3, 2, False, 1.0), (130, 6, 1, True, 1e-7), (257, 2, 1, False, 3e4)])
