@@ -180,7 +180,7 @@ def run_ours(a):
     from torch import nn
 
     import MPGCN as shim
-    from mpgcn_b200 import _lib
+    from mpgcn_b200 import _lib, dist as mdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,9 +188,7 @@ def run_ours(a):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the engine has no CPU path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    mdist.init_from_env("nccl", device=dev)
     lib = _lib.load()
 
     N, K, T, B, hid = a.nodes, a.supports, a.obs, a.batch, a.hidden
@@ -215,10 +213,7 @@ def run_ours(a):
             p.grad = None
         loss = crit(model(x_seq=x, G_list=[G_static, (go, gd)]), y)
         loss.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat /= world
+        mdist.allreduce_mean_gradients(params)      # the only exchange step of the batch shard (no-op for one rank)
         return loss
 
     def sync_all():
