@@ -231,22 +231,23 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
 }
 
 // ---------------------------------------------------------------------------------------
-// backward: 4 epilogue warps + 1 MMA warp per CTA
+// backward: 4 epilogue warps + 1 MMA warp per CTA, two CTAs per SM (the per-tile chain is latency bound:
+// stash loads -> math -> MMA round trip; a second resident CTA fills the gaps)
 // ---------------------------------------------------------------------------------------
 constexpr int BWD_THREADS = 160;
 constexpr int DA_BYTES = 32768;     // [128 cells][128 gates] fp16 as two [128][64] SW128 sub-tiles
 constexpr int HX_BYTES = 16384;     // [128 cells][64] fp16, SW128
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 2)
 lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ d_hT,
                    float* __restrict__ d_w_ih, float* __restrict__ d_w_hh, float* __restrict__ d_b, float* __restrict__ d_x,
                    __half* __restrict__ scratch, const float* __restrict__ scale2, long long cells, int T, long long NN) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sDA = smem;                               // 2 x 32 KB
-  uint8_t* sHX = smem + 2 * DA_BYTES;                // 2 x 16 KB
-  uint8_t* sW = sHX + 2 * HX_BYTES;                  // 8 KB
+  uint8_t* sDA = smem;                               // 32 KB (single buffer: MMA2 of step t retires long before step t-1's math ends)
+  uint8_t* sHX = smem + DA_BYTES;                    // 16 KB
+  uint8_t* sW = sHX + HX_BYTES;                      // 8 KB
   uint8_t* sH = sW + 8192;                           // 8 KB
   float* s_bias = reinterpret_cast<float*>(sH + 8192);
   float* s_wih = s_bias + G4;
@@ -299,7 +300,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
         __syncwarp();
       }
       for (int t = T - 1; t >= 0; --t) {      // backward through time
-        const int buf = (T - 1 - t) & 1;
+        const int buf = 0;
         mbar_wait(&da_ready[buf], ph_da[buf]);
         ph_da[buf] ^= 1u;
         tc_fence_after();
@@ -365,7 +366,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
         dc[u] = 0.f;
       }
       for (int t = T - 1; t >= 0; --t) {
-        const int buf = (T - 1 - t) & 1;
+        const int buf = 0;
         if (free_uses[buf] > 0) {          // the MMAs that read this buffer two steps ago must have retired
           mbar_wait(&da_free[buf], ph_free[buf]);
           ph_free[buf] ^= 1u;
@@ -479,7 +480,7 @@ bool lstm_tc_supported(int T, int C) { return C == 32 && T >= 1 && T <= 256; }
 
 static int lstm_bwd_grid(long long cells) {
   const long long tiles = (cells + lstm_tc::CELLS - 1) / lstm_tc::CELLS;
-  long long g = device_sm_count();
+  long long g = 2LL * device_sm_count();
   return (int)(g < tiles ? g : tiles);
 }
 
@@ -524,16 +525,17 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   MPGCN_CUDA(cudaMemsetAsync(d_w_ih, 0, sizeof(float) * G4, st));
   MPGCN_CUDA(cudaMemsetAsync(d_w_hh, 0, sizeof(float) * G4 * C, st));
   MPGCN_CUDA(cudaMemsetAsync(d_b_ih, 0, sizeof(float) * G4, st));
-  const size_t smem = 1024 + 2 * DA_BYTES + 2 * HX_BYTES + 2 * 8192 + 2 * G4 * sizeof(float) + 256;
+  const size_t smem = 1024 + DA_BYTES + HX_BYTES + 2 * 8192 + 2 * G4 * sizeof(float) + 256;
+  const int kBwdSmem = 100 * 1024;      // exactly two CTAs per SM (2 x 256 TMEM columns)
   static bool attr = false;
   if (!attr) {
-    MPGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    MPGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     attr = true;
   }
-  MPGCN_CHECK(smem <= 160 * 1024, "internal: lstm backward smem");
+  MPGCN_CHECK(smem <= (size_t)kBwdSmem, "internal: lstm backward smem");
   const int grid = lstm_bwd_grid(cells);
   prof_begin(PROF_LSTM_BWD, 16.0 * C * (C + 1) * (double)cells * T, st);
-  lstm_bwd_tc_kernel<<<grid, BWD_THREADS, 160 * 1024, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x, scratch, scale2,
+  lstm_bwd_tc_kernel<<<grid, BWD_THREADS, kBwdSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x, scratch, scale2,
                                                             cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());

@@ -231,9 +231,9 @@ def fc_relu_forward(x, w, b):
     return np.maximum(x @ w.T + b, 0)
 
 
-def fc_relu_backward(x, w, b, d_y):
+def fc_relu_backward(x, w, b, d_y, mask_from=None):
     pre = x @ w.T + b
-    d_pre = d_y * (pre > 0)
+    d_pre = d_y * ((pre if mask_from is None else np.asarray(mask_from)) > 0)
     dw = np.tensordot(d_pre, x, axes=(list(range(x.ndim - 1)), list(range(x.ndim - 1))))
     db = d_pre.reshape(-1, d_pre.shape[-1]).sum(axis=0)
     return d_pre @ w, dw, db
@@ -270,10 +270,14 @@ def mpgcn_forward(params, x_seq, G_list, M, gcn_num_layers, act="relu"):
     return y[:, None]                                                # MPGCN.py:112
 
 
-def mpgcn_forward_backward(params, x_seq, G_list, M, gcn_num_layers, d_y, act="relu"):
+def mpgcn_forward_backward(params, x_seq, G_list, M, gcn_num_layers, d_y, act="relu", masks=None):
     """Forward + gradients of every parameter (what `loss.backward()` produces through
     MPGCN.py:89-112).  d_y [B,1,N,N,I] is dL/d(output).  Returns (y, grads dict keyed like
-    the state_dict)."""
+    the state_dict).
+
+    masks: optional {m: {"layers": [out_0, .., out_{L-1}], "fc": fc_out}} -- forward outputs of another
+    implementation whose signs replace the oracle's own ReLU masks in the backward pass (see
+    bdgcn_backward's `mask_from`): the gradient of the function that implementation computed."""
     x_seq = np.asarray(x_seq)
     Bsz, T, N, _, I = x_seq.shape
     lstm_in = np.transpose(x_seq, (0, 2, 3, 1, 4)).reshape(Bsz * N * N, T, I)
@@ -296,12 +300,15 @@ def mpgcn_forward_backward(params, x_seq, G_list, M, gcn_num_layers, d_y, act="r
         pre = f"branch_models.{m}."
         lw, acts = tapes[m]
         d = d_y[:, 0] / M
-        d, dw, db = fc_relu_backward(acts[-1], _p(params, pre + "fc.0.weight"), _p(params, pre + "fc.0.bias"), d)
+        mk = None if masks is None else masks[m]
+        d, dw, db = fc_relu_backward(acts[-1], _p(params, pre + "fc.0.weight"), _p(params, pre + "fc.0.bias"), d,
+                                     mask_from=None if mk is None else mk["fc"])
         grads[pre + "fc.0.weight"], grads[pre + "fc.0.bias"] = dw, db
         for n in reversed(range(gcn_num_layers)):
             bkey = pre + f"spatial.{n}.b"
             d, dW, dbb = bdgcn_backward(acts[n], G_list[m], _p(params, pre + f"spatial.{n}.W"),
-                                        _p(params, bkey) if bkey in params else None, act, d)
+                                        _p(params, bkey) if bkey in params else None, act, d,
+                                        mask_from=None if mk is None else mk["layers"][n])
             grads[pre + f"spatial.{n}.W"] = dW
             if dbb is not None:
                 grads[bkey] = dbb

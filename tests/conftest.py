@@ -34,3 +34,24 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+PARITY_REPORT = []
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Dump every measured parity error (tests call record_parity) next to the GPU run's other artefacts."""
+    if not PARITY_REPORT:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_report.json"), "w") as f:
+            json.dump(PARITY_REPORT, f, indent=1)
+    except OSError:
+        pass
+
+
+def record_parity(what, linf, l2, tol):
+    PARITY_REPORT.append(dict(what=what, rel_linf=linf, rel_l2=l2, tol=tol))
