@@ -80,6 +80,15 @@ int map_planes(CUtensorMap* m, const __half* t, long long rows, long long planes
 }
 }  // namespace
 
+// launch an N^3 contraction on the 2-CTA kernel when the M extent allows it (p prepared for the 1-CTA kernel)
+static int launch_big(int ak, GemmParams& p, int m_rows, cudaStream_t st) {
+  if (tc::use_2cta(m_rows)) {
+    p.MT = ceil_div(m_rows, 256);
+    return tc::launch_contract_2cta(ak, p, st);
+  }
+  return tc::launch_contract(ak, 64, p, st);
+}
+
 bool tc_supported(const BdgcnShape& s) { return s.C == 32 && s.H == 32 && s.K >= 1 && s.K <= 8 && s.N >= 1 && s.B >= 1; }
 
 static size_t n2(const BdgcnShape& s) { return (size_t)s.N * s.N; }
@@ -177,7 +186,7 @@ static int run_fwd_a(const BdgcnShape& s, const __half* gd16, const __half* x16,
   GemmParams p;
   init_params(p);
   if (int e = map_support_mn(&p.a_map, gd16, N, Np, N, (long long)(s.dynamic ? s.B : 1) * K)) return e;
-  if (int e = map_chunks(&p.b_map, x16, N, 32, N, (long long)N * 32, s.B, (long long)N * N * 32, 64, 8)) return e;
+  if (int e = map_chunks(&p.b_map, x16, N, 32, N, (long long)N * 32, s.B, (long long)N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
   p.am = omap(1, s.dynamic ? kBig : K, 1, 0, 0);        // z = b*K + d -> support index
   p.bm = omap(K, kBig, 1, 0, 0);                        // -> b
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B * K; p.R = 8;
@@ -189,7 +198,7 @@ static int run_fwd_a(const BdgcnShape& s, const __half* gd16, const __half* x16,
   p.ep.corr_src = x16; p.ep.corr_delta = delta_d; p.ep.corr_nseg = 1;
   p.ep.cZ = (long long)N * N * 32; p.ep.cI = 32; p.ep.cR = (long long)N * 32; p.ep.cSeg = 0;
   prof_set_next(PROF_FWD_A, 2.0 * s.B * K * (double)N * N * N * 32);
-  return tc::launch_contract(tc::A_MN128, 64, p, st);
+  return launch_big(tc::A_MN128, p, N, st);
 }
 
 // MIX: D16[b][r][row][32] = sum_{seg} A16[b][seg][row][32] * Wm16[r][(seg,32)][32]   (both channel mixes)
@@ -233,7 +242,7 @@ static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16,
   p.ep.corr_src = u16; p.ep.corr_delta = delta_o; p.ep.corr_nseg = K;
   p.ep.cZ = (long long)K * N * N * 32; p.ep.cSeg = (long long)N * N * 32; p.ep.cI = (long long)N * 32; p.ep.cR = 32;
   prof_set_next(PROF_FWD_B, 2.0 * s.B * K * (double)N * N * N * 32);
-  return tc::launch_contract(tc::A_MN128, 64, p, st);
+  return launch_big(tc::A_MN128, p, N, st);
 }
 
 // BWD_V: V16[b][o][n][e][h] = sum_m G_o[n][m] dP16[b][m][e][h]
@@ -252,7 +261,7 @@ static int run_bwd_v(const BdgcnShape& s, const __half* go16, const __half* dp16
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
   prof_set_next(PROF_BWD_V, 2.0 * s.B * K * (double)N * N * N * 32);
-  return tc::launch_contract(tc::A_K128, 64, p, st);
+  return launch_big(tc::A_K128, p, N, st);
 }
 
 // BWD_DW: P[slice][mt][(d%4)*32+l][o][h] = sum over the slice's (b,row) range of Z16[b][d][row][l] V16[b][o][row][h]
@@ -286,7 +295,7 @@ static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16
   GemmParams p;
   init_params(p);
   if (int e = map_support_k(&p.a_map, gd16, N, Np, (long long)(s.dynamic ? s.B : 1) * K)) return e;
-  if (int e = map_chunks(&p.b_map, y16, N, 32, N, (long long)N * 32, (long long)s.B * K, (long long)N * N * 32, 64, 8)) return e;
+  if (int e = map_chunks(&p.b_map, y16, N, 32, N, (long long)N * 32, (long long)s.B * K, (long long)N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
   p.am = omap(1, s.dynamic ? kBig : 1, s.dynamic ? K : 0, 1, 0);   // support index = (b*K) + d
   p.bm = omap(1, kBig, K, 1, 0);                                    // plane = b*K + d
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;
@@ -295,7 +304,7 @@ static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
   prof_set_next(PROF_BWD_DX, 2.0 * s.B * K * (double)N * N * N * 32);
-  return tc::launch_contract(tc::A_K128, 64, p, st);
+  return launch_big(tc::A_K128, p, N, st);
 }
 
 static int convert_supports(const BdgcnShape& s, const float* Go, const float* Gd, __half* go16, __half* gd16, const __half** go_used,

@@ -4,6 +4,7 @@
 #include <mutex>
 #include <vector>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mpgcn {
@@ -186,6 +187,66 @@ static int launch_impl(GemmParams& p, cudaStream_t stream) {
   prof_end(stream);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int AK>
+static int launch2_impl(GemmParams& p, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    MPGCN_CUDA(cudaFuncSetAttribute(contract2_kernel<AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    attr_done = true;
+  }
+  MPGCN_CHECK(p.R == 8 && !p.split_k, "2-CTA kernel needs R = 8 and no split-K");
+  const size_t stage_bytes = 32768;
+  int stages = (int)((kMaxSmem - 1024 - 512) / stage_bytes);
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const long long tiles = (long long)p.MT * p.NT * p.Z;
+  MPGCN_CHECK(tiles > 0 && tiles < (1ll << 31), "bad tile count %lld", tiles);
+  MPGCN_CHECK(p.kb_total > 0 && p.kb_per_seg > 0, "empty contraction");
+  long long pairs = device_sm_count() / 2;
+  if (pairs > tiles) pairs = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kMaxSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const int tag = g_prof.next_tag;
+  const double fl = g_prof.next_flops;
+  g_prof.next_tag = -1;
+  g_prof.next_flops = 0;
+  prof_begin(tag, fl, stream);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, contract2_kernel<AK>, p);
+  prof_end(stream);
+  if (e != cudaSuccess) {
+    set_error("cudaLaunchKernelEx(contract2_kernel) failed: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+int launch_contract_2cta(int ak, GemmParams& p, cudaStream_t stream) {
+  if (ak == A_MN128) return launch2_impl<A_MN128>(p, stream);
+  if (ak == A_K128) return launch2_impl<A_K128>(p, stream);
+  set_error("no 2-CTA contraction kernel for A kind %d", ak);
+  return 1;
+}
+
+// the pair tile is 256 rows: worthwhile once a second 128-row tile exists (env MPGCN_B200_NO_2CTA=1 disables it)
+bool use_2cta(int n_rows) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("MPGCN_B200_NO_2CTA");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !disabled && n_rows > 128;
 }
 
 int launch_contract(int ak, int bk, GemmParams& p, cudaStream_t stream) {

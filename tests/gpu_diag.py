@@ -151,6 +151,7 @@ def run_case(B, N, K, dynamic, seed=0, grad_mag=1.0):
 
 CASES = {
     "small": [(1, 32, 1, 0), (2, 33, 3, 1), (1, 47, 3, 0), (2, 200, 3, 0), (1, 128, 6, 1)],
+    "mid": [(1, 47, 3, 0), (2, 200, 3, 0), (1, 257, 2, 0), (2, 300, 3, 1), (1, 130, 6, 1), (1, 512, 3, 0)],
     "all": [(1, 32, 1, 0), (2, 33, 3, 1), (1, 47, 3, 0), (2, 200, 3, 0), (1, 128, 6, 1), (2, 500, 3, 0), (1, 1000, 3, 0), (2, 130, 8, 0)],
 }
 
