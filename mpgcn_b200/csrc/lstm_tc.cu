@@ -61,13 +61,19 @@ __device__ void load_weights(uint8_t* sW, float* s_bias, float* s_wih, const flo
 
 // One LSTM step for one cell given the gate pre-activation accumulators in TMEM (or zero when !has_mma).
 // Updates c[], returns h[]; optionally emits the post-activation gates, c and h (fp16, 16-byte stores).
+// Stash layout (per CTA): [t][24 chunks = 6 blocks (i f g o c h) x 4][128 cells][8 halves]: the 32 lanes of a warp
+// touch 32 consecutive 16-byte chunks, i.e. every stash load / store is fully coalesced.
+constexpr int STASH_CHUNKS = 24;
+__device__ __forceinline__ __half* stash_at(__half* base, int t, int chunk) {
+  return base + ((size_t)(t * STASH_CHUNKS + chunk) * CELLS) * 8;
+}
 __device__ __forceinline__ void st_half8(__half* dst, const float* v) {
   *reinterpret_cast<uint4*>(dst) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
 }
 
 template <bool STASH_OUT>
 __device__ __forceinline__ void cell_step(uint32_t t_row, bool has_mma, float xv, const float* s_bias, const float* s_wih, float (&c)[C],
-                                          float (&h)[C], __half* stash) {
+                                          float (&h)[C], __half* stash, int t_stash) {
   uint32_t r[32];
   float ig[C];
   // input gate
@@ -76,7 +82,7 @@ __device__ __forceinline__ void cell_step(uint32_t t_row, bool has_mma, float xv
   for (int u = 0; u < C; ++u) ig[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[u], xv, s_bias[u]));
   if (STASH_OUT) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) st_half8(stash + 0 * C + 8 * q, ig + 8 * q);
+    for (int q = 0; q < 4; ++q) st_half8(stash_at(stash, t_stash, 0 * 4 + q), ig + 8 * q);
   }
   // cell candidate
   if (has_mma) { tmem_ld_32x32(t_row + 2 * C, r); tmem_ld_wait(); }
@@ -86,7 +92,7 @@ __device__ __forceinline__ void cell_step(uint32_t t_row, bool has_mma, float xv
     for (int u = 0; u < C; ++u) g[u] = tanh_((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[2 * C + u], xv, s_bias[2 * C + u]));
     if (STASH_OUT) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) st_half8(stash + 2 * C + 8 * q, g + 8 * q);
+      for (int q = 0; q < 4; ++q) st_half8(stash_at(stash, t_stash, 2 * 4 + q), g + 8 * q);
     }
 #pragma unroll
     for (int u = 0; u < C; ++u) ig[u] *= g[u];
@@ -99,14 +105,14 @@ __device__ __forceinline__ void cell_step(uint32_t t_row, bool has_mma, float xv
     for (int u = 0; u < C; ++u) f[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[C + u], xv, s_bias[C + u]));
     if (STASH_OUT) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) st_half8(stash + 1 * C + 8 * q, f + 8 * q);
+      for (int q = 0; q < 4; ++q) st_half8(stash_at(stash, t_stash, 1 * 4 + q), f + 8 * q);
     }
 #pragma unroll
     for (int u = 0; u < C; ++u) c[u] = fmaf(f[u], c[u], ig[u]);
   }
   if (STASH_OUT) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) st_half8(stash + 4 * C + 8 * q, c + 8 * q);
+    for (int q = 0; q < 4; ++q) st_half8(stash_at(stash, t_stash, 4 * 4 + q), c + 8 * q);
   }
   // output gate
   if (has_mma) { tmem_ld_32x32(t_row + 3 * C, r); tmem_ld_wait(); }
@@ -116,14 +122,14 @@ __device__ __forceinline__ void cell_step(uint32_t t_row, bool has_mma, float xv
     for (int u = 0; u < C; ++u) o[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[3 * C + u], xv, s_bias[3 * C + u]));
     if (STASH_OUT) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) st_half8(stash + 3 * C + 8 * q, o + 8 * q);
+      for (int q = 0; q < 4; ++q) st_half8(stash_at(stash, t_stash, 3 * 4 + q), o + 8 * q);
     }
 #pragma unroll
     for (int u = 0; u < C; ++u) h[u] = o[u] * tanh_(c[u]);
   }
   if (STASH_OUT) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) st_half8(stash + 5 * C + 8 * q, h + 8 * q);
+    for (int q = 0; q < 4; ++q) st_half8(stash_at(stash, t_stash, 5 * 4 + q), h + 8 * q);
   }
 }
 
@@ -209,7 +215,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           ph ^= 1u;
           tc_fence_after();
         }
-        cell_step<false>(t_row, t > 0, xv, s_bias, s_wih, c, h, nullptr);
+        cell_step<false>(t_row, t > 0, xv, s_bias, s_wih, c, h, nullptr, 0);
         if (t + 1 < T) {
           write_h_tile(myH, row, h);
           fence_proxy_async_smem();
@@ -331,7 +337,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
     // ---------------- epilogue warps: thread = cell (row) / gate row j for the final flush ----------------
     const int row = warp * 32 + lane;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    __half* my_stash = scratch + ((size_t)blockIdx.x * T * CELLS + row) * STASH;    // + t * CELLS * STASH
+    __half* my_stash = scratch + (size_t)blockIdx.x * T * CELLS * STASH + (size_t)row * 8;   // see stash_at()
     uint32_t ph_g = 0, ph_dh = 0, ph_free[2] = {0, 0};
     int free_uses[2] = {0, 0};
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -349,7 +355,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
             ph_g ^= 1u;
             tc_fence_after();
           }
-          cell_step<true>(TM_GATES + lane_base, t > 0, xv, s_bias, s_wih, c, h, my_stash + (size_t)t * CELLS * STASH);
+          cell_step<true>(TM_GATES + lane_base, t > 0, xv, s_bias, s_wih, c, h, my_stash, t);
           if (t + 1 < T) {
             write_h_tile(sH, row, h);
             fence_proxy_async_smem();
@@ -361,10 +367,13 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
       // ---- (2) backward through time ----
       float dh[C], dc[C];
 #pragma unroll
-      for (int u = 0; u < C; ++u) {
-        dh[u] = live ? d_hT[(size_t)cell * C + u] * S : 0.f;
-        dc[u] = 0.f;
+      for (int q = 0; q < 8; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) v = *reinterpret_cast<const float4*>(d_hT + (size_t)cell * C + 4 * q);
+        dh[4 * q] = v.x * S; dh[4 * q + 1] = v.y * S; dh[4 * q + 2] = v.z * S; dh[4 * q + 3] = v.w * S;
       }
+#pragma unroll
+      for (int u = 0; u < C; ++u) dc[u] = 0.f;
       for (int t = T - 1; t >= 0; --t) {
         const int buf = 0;
         if (free_uses[buf] > 0) {          // the MMAs that read this buffer two steps ago must have retired
@@ -372,8 +381,6 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           ph_free[buf] ^= 1u;
         }
         free_uses[buf]++;
-        const __half* st = my_stash + (size_t)t * CELLS * STASH;
-        const __half* stp = my_stash + (size_t)(t - 1) * CELLS * STASH;
         const float xv = live ? x_seq[x_index(cell, t, T, NN)] : 0.f;
         uint8_t* da_t = sDA + buf * DA_BYTES;
         uint8_t* hx_t = sHX + buf * HX_BYTES;
@@ -382,13 +389,13 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float di[8], df[8], dg[8], d_o[8];
-          const uint4 vi = *reinterpret_cast<const uint4*>(st + 0 * C + 8 * q);
-          const uint4 vf = *reinterpret_cast<const uint4*>(st + 1 * C + 8 * q);
-          const uint4 vg = *reinterpret_cast<const uint4*>(st + 2 * C + 8 * q);
-          const uint4 vo = *reinterpret_cast<const uint4*>(st + 3 * C + 8 * q);
-          const uint4 vc = *reinterpret_cast<const uint4*>(st + 4 * C + 8 * q);
+          const uint4 vi = *reinterpret_cast<const uint4*>(stash_at(my_stash, t, 0 * 4 + q));
+          const uint4 vf = *reinterpret_cast<const uint4*>(stash_at(my_stash, t, 1 * 4 + q));
+          const uint4 vg = *reinterpret_cast<const uint4*>(stash_at(my_stash, t, 2 * 4 + q));
+          const uint4 vo = *reinterpret_cast<const uint4*>(stash_at(my_stash, t, 3 * 4 + q));
+          const uint4 vc = *reinterpret_cast<const uint4*>(stash_at(my_stash, t, 4 * 4 + q));
           uint4 vcp = make_uint4(0, 0, 0, 0);
-          if (t > 0) vcp = *reinterpret_cast<const uint4*>(stp + 4 * C + 8 * q);
+          if (t > 0) vcp = *reinterpret_cast<const uint4*>(stash_at(my_stash, t - 1, 4 * 4 + q));
           const __half* hi_ = reinterpret_cast<const __half*>(&vi);
           const __half* hf = reinterpret_cast<const __half*>(&vf);
           const __half* hg = reinterpret_cast<const __half*>(&vg);
@@ -422,7 +429,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
 #undef MPGCN_ST_DA
           // h_{t-1} chunk q of the [h | x | 1 | 0] row
           uint4 vh = make_uint4(0, 0, 0, 0);
-          if (t > 0) vh = *reinterpret_cast<const uint4*>(stp + 5 * C + 8 * q);
+          if (t > 0) vh = *reinterpret_cast<const uint4*>(stash_at(my_stash, t - 1, 5 * 4 + q));
           *reinterpret_cast<uint4*>(hx_t + sw128_off(row, q)) = vh;
         }
         st_shared_v4(hx_t + sw128_off(row, 4), pack2(xv, 1.f), 0u, 0u, 0u);
