@@ -17,6 +17,7 @@
 #include "kernels.h"
 #include "tc_engine.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace mpgcn {
@@ -79,6 +80,16 @@ int map_planes(CUtensorMap* m, const __half* t, long long rows, long long planes
   return make_tmap_f16(m, t, 4, dims, str, box, TMAP_SW64);
 }
 }  // namespace
+
+// MPGCN_B200_FLAT_B=1: load the flat B operands (U16, dP16) as one 32-column box per chunk instead of one permuted box
+static bool flat_b_boxes() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MPGCN_B200_FLAT_B");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 // launch an N^3 contraction on the 2-CTA kernel when the M extent allows it (p prepared for the 1-CTA kernel)
 static int launch_big(int ak, GemmParams& p, int m_rows, cudaStream_t st) {
@@ -228,10 +239,16 @@ static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16,
   GemmParams p;
   init_params(p);
   if (int e = map_support_mn(&p.a_map, go16, N, Np, (long long)K * N, s.dynamic ? s.B : 1)) return e;
-  if (int e = map_flat(&p.b_map, u16, (long long)N * 32, (long long)K * N, s.B, 64)) return e;
+  // U16 [b][(o,n)][e][h] read as (h, k = (o,n) rows, r = e, b): dims listed with non-monotonic strides (the r stride,
+  // 64 B, is smaller than the k stride) so that ONE box (32 ch, 64 k, 4|8 r) lands in the canonical [r][k][64 B] layout
+  if (flat_b_boxes()) {
+    if (int e = map_flat(&p.b_map, u16, (long long)N * 32, (long long)K * N, s.B, 64)) return e;
+    p.b_flat = 1;
+  } else {
+    if (int e = map_chunks(&p.b_map, u16, (long long)K * N, (long long)N * 32, N, 32, s.B, (long long)K * N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
+  }
   p.am = omap(1, s.dynamic ? kBig : 1, 1, 0, 0);
   p.bm = omap(1, kBig, 1, 0, 0);
-  p.b_flat = 1;
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;
   p.kb_total = p.kb_per_seg = ceil_div((long long)K * N, 64);
   p.ep.out = out; p.ep.out_f16 = 0;
@@ -251,10 +268,14 @@ static int run_bwd_v(const BdgcnShape& s, const __half* go16, const __half* dp16
   GemmParams p;
   init_params(p);
   if (int e = map_support_k(&p.a_map, go16, N, Np, (long long)(s.dynamic ? s.B : 1) * K)) return e;
-  if (int e = map_flat(&p.b_map, dp16, (long long)N * 32, N, s.B, 64)) return e;
+  if (flat_b_boxes()) {
+    if (int e = map_flat(&p.b_map, dp16, (long long)N * 32, N, s.B, 64)) return e;
+    p.b_flat = 1;
+  } else {   // dP16 [b][m][e][h] read as (h, k = m, r = e, b), see run_fwd_b
+    if (int e = map_chunks(&p.b_map, dp16, N, (long long)N * 32, N, 32, s.B, (long long)N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
+  }
   p.am = omap(1, s.dynamic ? kBig : K, 1, 0, 0);        // z = b*K + o
   p.bm = omap(K, kBig, 1, 0, 0);
-  p.b_flat = 1;
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B * K; p.R = 8;
   p.kb_total = p.kb_per_seg = ceil_div(N, 64);
   p.ep.out = v16; p.ep.out_f16 = 1;
