@@ -37,12 +37,17 @@ constexpr int MMA_WARP = 8;
 __device__ __forceinline__ uint32_t sw64_off(int row, int chunk) { return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4); }
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
 
-__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+// sigmoid / tanh on the SFU: one ex2.approx + one rcp.approx each (2 ulp), no range fix-ups: for |x| large ex2 saturates to
+// 0 or +inf and rcp(1 + inf) = 0, which are the correct limits.
+__device__ __forceinline__ float ex2_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigm(float x) { return rcp_(1.f + ex2_(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_(float x) { return fmaf(2.f, rcp_(1.f + ex2_(-2.8853900817779268f * x)), -1.f); }
 
-__device__ __forceinline__ size_t x_index(long long cell, int t, int T, long long NN) {
+// x_seq is [B][T][NN]: element (cell, t) = x_base(cell) + t * NN; the 64-bit division is done once per tile
+__device__ __forceinline__ size_t x_base(long long cell, int T, long long NN) {
   const long long b = cell / NN;
-  return (size_t)((b * T + t) * NN + (cell - b * NN));
+  return (size_t)(b * T * NN + (cell - b * NN));
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -221,9 +226,10 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
       float c[UN], h[UN];
 #pragma unroll
       for (int u = 0; u < UN; ++u) c[u] = 0.f;
-      float xv = live ? x_seq[x_index(cell, 0, T, NN)] : 0.f;
+      const size_t xb = live ? x_base(cell, T, NN) : 0;
+      float xv = live ? x_seq[xb] : 0.f;
       for (int t = 0; t < T; ++t) {
-        const float xn = (live && t + 1 < T) ? x_seq[x_index(cell, t + 1, T, NN)] : 0.f;   // prefetch next step's input
+        const float xn = (live && t + 1 < T) ? x_seq[xb + (size_t)(t + 1) * NN] : 0.f;   // prefetch next step's input
         if (t > 0) {
           mbar_wait(g_ready, ph);
           ph ^= 1u;
@@ -356,13 +362,14 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const long long cell = tile * CELLS + row;
       const bool live = cell < cells;
+      const size_t xb = live ? x_base(cell, T, NN) : 0;
       // ---- (1) recompute forward, stash per step ----
       {
         float c[UN], h[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) c[u] = 0.f;
         for (int t = 0; t < T; ++t) {
-          const float xv = live ? x_seq[x_index(cell, t, T, NN)] : 0.f;
+          const float xv = live ? x_seq[xb + (size_t)t * NN] : 0.f;
           if (t > 0) {
             mbar_wait(g_ready, ph_g);
             ph_g ^= 1u;
@@ -405,7 +412,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
             vh[q] = *stash_at(my_stash, t - 1, 5 * 4 + ch);
           }
         }
-        const float xv = live ? x_seq[x_index(cell, t, T, NN)] : 0.f;
+        const float xv = live ? x_seq[xb + (size_t)t * NN] : 0.f;
         if (da_uses > 0) {                 // the MMAs that read the da / [h|x|1] tiles one step ago must have retired
           mbar_wait(da_free, ph_free);
           ph_free ^= 1u;
@@ -450,7 +457,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           *reinterpret_cast<uint4*>(sHX + sw128_off(row, 6)) = make_uint4(0u, 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(sHX + sw128_off(row, 7)) = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (d_x != nullptr && live) atomicAdd(&d_x[x_index(cell, t, T, NN)], dx_acc * invS);   // two halves per cell
+        if (d_x != nullptr && live) atomicAdd(&d_x[xb + (size_t)t * NN], dx_acc * invS);   // two halves per cell
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(da_ready);
