@@ -147,7 +147,7 @@ def sample_text(d, a):
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     for _ in range(a.warmup):
         cpu_sample(a)
     ts, detail = [], None
@@ -168,7 +168,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
@@ -284,7 +284,7 @@ def run_ours(a):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
 
     # ---- roofline of the dominant kernel (the N^3 tcgen05 contractions) -------------------------
     peaks = measured_peaks()
@@ -322,17 +322,24 @@ def run_ours(a):
         "dtype": "f16" if a.precision != "fp32" else "f32", "data": "synthetic", "config": workload_config(a, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def main():
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    # Libraries (NCCL's version banner, torchrun notices) may write to fd 1; the contract is ONE JSON line on stdout.
+    # Route everything else to stderr and hand the real stdout only to the final print.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    try:
+        line = run_reference(a) if a.impl == "reference" else run_ours(a)
+    finally:
+        sys.stdout = real_stdout
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
