@@ -22,6 +22,8 @@
 // resident warps (18 per SM) and keeps the per-thread state small enough to issue a whole step's loads at once.
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace mpgcn {
 namespace lstm_tc {
 
@@ -510,7 +512,12 @@ bool lstm_tc_supported(int T, int C) { return C == 32 && T >= 1 && T <= 256; }
 
 static int lstm_grid(long long cells) {
   const long long tiles = (cells + lstm_tc::CELLS - 1) / lstm_tc::CELLS;
-  long long g = 2LL * device_sm_count();     // two CTAs per SM
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("MPGCN_B200_LSTM_CTAS_PER_SM");      // tuning knob: 1 or 2 (default) resident CTAs per SM
+    per_sm = (e && e[0] == '1') ? 1 : 2;
+  }
+  long long g = (long long)per_sm * device_sm_count();
   return (int)(g < tiles ? g : tiles);
 }
 
