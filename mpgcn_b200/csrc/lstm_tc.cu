@@ -79,6 +79,19 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // W_hh (fp32 [128][32]) -> fp16 smem tile [128 rows j][64 B], SWIZZLE_64B (serves as K-major B with N=j and as
 // MN-major B with K=j); bias = b_ih + b_hh; wih.
 __device__ void load_weights(uint8_t* sW, float* s_bias, float* s_wih, const float* w_ih, const float* w_hh, const float* b_ih,
@@ -97,7 +110,7 @@ __device__ void load_weights(uint8_t* sW, float* s_bias, float* s_wih, const flo
 // touch 32 consecutive 16-byte chunks, i.e. every stash load / store is fully coalesced.
 constexpr int STASH_CHUNKS = 24;
 __device__ __forceinline__ uint4* stash_at(__half* base, int t, int chunk) {
-  return reinterpret_cast<uint4*>(base + ((size_t)(t * STASH_CHUNKS + chunk) * CELLS) * 8);
+  return reinterpret_cast<uint4*>(base + (size_t)t * (STASH_CHUNKS * CELLS * 8)) + chunk * CELLS;   // chunk is a compile-time constant at every call site
 }
 
 // One LSTM step for 16 hidden units of one cell.  t_col = TMEM address of (lane quarter, column 16*hh) of the gate
@@ -112,7 +125,7 @@ __device__ __forceinline__ void cell_step(uint32_t t_col, bool has_mma, float xv
   for (int u = 0; u < UN; ++u) ig[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[u0 + u], xv, s_bias[u0 + u]));
   if (STASH_OUT) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 0 * 4 + 2 * hh + q) = pack8(ig + 8 * q);
+    for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 0 * 4 + q) = pack8(ig + 8 * q);
   }
   if (has_mma) { tmem_ld_32x16(t_col + 2 * C, r); tmem_ld_wait(); }
   {
@@ -121,7 +134,7 @@ __device__ __forceinline__ void cell_step(uint32_t t_col, bool has_mma, float xv
     for (int u = 0; u < UN; ++u) g[u] = tanh_((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[2 * C + u0 + u], xv, s_bias[2 * C + u0 + u]));
     if (STASH_OUT) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 2 * 4 + 2 * hh + q) = pack8(g + 8 * q);
+      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 2 * 4 + q) = pack8(g + 8 * q);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) ig[u] *= g[u];
@@ -133,14 +146,14 @@ __device__ __forceinline__ void cell_step(uint32_t t_col, bool has_mma, float xv
     for (int u = 0; u < UN; ++u) f[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[C + u0 + u], xv, s_bias[C + u0 + u]));
     if (STASH_OUT) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 1 * 4 + 2 * hh + q) = pack8(f + 8 * q);
+      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 1 * 4 + q) = pack8(f + 8 * q);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) c[u] = fmaf(f[u], c[u], ig[u]);
   }
   if (STASH_OUT) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 4 * 4 + 2 * hh + q) = pack8(c + 8 * q);
+    for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 4 * 4 + q) = pack8(c + 8 * q);
   }
   if (has_mma) { tmem_ld_32x16(t_col + 3 * C, r); tmem_ld_wait(); }
   {
@@ -149,14 +162,14 @@ __device__ __forceinline__ void cell_step(uint32_t t_col, bool has_mma, float xv
     for (int u = 0; u < UN; ++u) o[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[3 * C + u0 + u], xv, s_bias[3 * C + u0 + u]));
     if (STASH_OUT) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 3 * 4 + 2 * hh + q) = pack8(o + 8 * q);
+      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 3 * 4 + q) = pack8(o + 8 * q);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) h[u] = o[u] * tanh_(c[u]);
   }
   if (STASH_OUT) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 5 * 4 + 2 * hh + q) = pack8(h + 8 * q);
+    for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 5 * 4 + q) = pack8(h + 8 * q);
   }
 }
 
@@ -168,7 +181,7 @@ __device__ __forceinline__ void write_h_tile(uint8_t* sH, int row, int hh, const
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __maxnreg__(112)
 lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ hT, long long cells, int T,
                    long long NN) {
@@ -264,7 +277,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
 constexpr int DA_BYTES = 32768;     // [128 cells][128 gates] fp16 as two [128][64] SW128 sub-tiles
 constexpr int HX_BYTES = 16384;     // [128 cells][64] fp16, SW128
 
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __maxnreg__(112)
 lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ d_hT,
                    float* __restrict__ d_w_ih, float* __restrict__ d_w_hh, float* __restrict__ d_b, float* __restrict__ d_x,
@@ -358,7 +371,8 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
     const int row = (warp & 3) * 32 + lane;
     const int u0 = UN * hh;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    __half* my_stash = scratch + (size_t)blockIdx.x * T * CELLS * STASH + (size_t)row * 8;   // see stash_at()
+    // per-thread stash base: CTA ring + this thread's row + its unit half (chunks 2*hh, 2*hh+1 of every block); see stash_at()
+    __half* my_stash = scratch + (size_t)blockIdx.x * T * CELLS * STASH + (size_t)(2 * hh) * CELLS * 8 + (size_t)row * 8;
     uint32_t ph_g = 0, ph_dh = 0, ph_free = 0;
     long long da_uses = 0;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -387,32 +401,40 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
         }
       }
       // ---- (2) backward through time ----
-      float dh[UN], dc[UN];
+      // The running gradients dh, dc (fp32, power-of-two scaled) live in TMEM, not in registers: dh in the columns the
+      // dh MMA writes (TM_DH), dc in the gate-accumulator columns, which are idle during this phase.  Seed them here.
+      const uint32_t t_dh = TM_DH + lane_base + u0, t_dc = TM_GATES + lane_base + u0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) v = *reinterpret_cast<const float4*>(d_hT + (size_t)cell * C + u0 + 4 * q);
-        dh[4 * q] = v.x * S; dh[4 * q + 1] = v.y * S; dh[4 * q + 2] = v.z * S; dh[4 * q + 3] = v.w * S;
+      for (int q = 0; q < 2; ++q) {
+        uint32_t r[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live) v = *reinterpret_cast<const float4*>(d_hT + (size_t)cell * C + u0 + 8 * q + e);
+          r[e] = __float_as_uint(v.x * S); r[e + 1] = __float_as_uint(v.y * S);
+          r[e + 2] = __float_as_uint(v.z * S); r[e + 3] = __float_as_uint(v.w * S);
+        }
+        tmem_st_32x8(t_dh + 8 * q, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = 0u;
+        tmem_st_32x8(t_dc + 8 * q, r);
       }
+      tmem_st_wait();
+      // c(t) is carried from the previous iteration (where it was loaded as c(t-1)); seed it with c(T-1)
+      uint4 vc[2];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) dc[u] = 0.f;
+      for (int q = 0; q < 2; ++q) vc[q] = *stash_at(my_stash, T - 1, 4 * 4 + q);
       for (int t = T - 1; t >= 0; --t) {
-        // issue the whole step's stash loads first (own 16 units of i f g o c; c and h of step t-1)
-        uint4 vi[2], vf[2], vg[2], vo[2], vc[2], vcp[2], vh[2];
+        // issue the step's stash loads first (own 16 units of i f g o; c of step t-1); h(t-1) goes global -> smem directly
+        uint4 vi[2], vf[2], vg[2], vo[2], vcp[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const int ch = 2 * hh + q;
-          vi[q] = *stash_at(my_stash, t, 0 * 4 + ch);
-          vf[q] = *stash_at(my_stash, t, 1 * 4 + ch);
-          vg[q] = *stash_at(my_stash, t, 2 * 4 + ch);
-          vo[q] = *stash_at(my_stash, t, 3 * 4 + ch);
-          vc[q] = *stash_at(my_stash, t, 4 * 4 + ch);
+          vi[q] = *stash_at(my_stash, t, 0 * 4 + q);
+          vf[q] = *stash_at(my_stash, t, 1 * 4 + q);
+          vg[q] = *stash_at(my_stash, t, 2 * 4 + q);
+          vo[q] = *stash_at(my_stash, t, 3 * 4 + q);
           vcp[q] = make_uint4(0, 0, 0, 0);
-          vh[q] = make_uint4(0, 0, 0, 0);
-          if (t > 0) {
-            vcp[q] = *stash_at(my_stash, t - 1, 4 * 4 + ch);
-            vh[q] = *stash_at(my_stash, t - 1, 5 * 4 + ch);
-          }
+          if (t > 0) vcp[q] = *stash_at(my_stash, t - 1, 4 * 4 + q);
         }
         const float xv = live ? x_seq[xb + (size_t)t * NN] : 0.f;
         if (da_uses > 0) {                 // the MMAs that read the da / [h|x|1] tiles one step ago must have retired
@@ -420,23 +442,36 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           ph_free ^= 1u;
         }
         da_uses++;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {       // h_{t-1}, this thread's 16 units, straight into the [h | x | 1 | 0] tile
+          uint8_t* dst = sHX + sw128_off(row, 2 * hh + q);
+          if (t > 0) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(stash_at(my_stash, t - 1, 5 * 4 + q)) : "memory");
+          } else {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         float dx_acc = 0.f;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           float fi[8], ff[8], fg[8], fo[8], fc[8], fcp[8];
           unpack8(vi[q], fi); unpack8(vf[q], ff); unpack8(vg[q], fg); unpack8(vo[q], fo); unpack8(vc[q], fc); unpack8(vcp[q], fcp);
           float di[8], df[8], dg[8], d_o[8];
+          uint32_t rdh[8], rdc[8];
+          tmem_ld_32x8(t_dh + 8 * q, rdh);
+          tmem_ld_32x8(t_dc + 8 * q, rdc);
+          tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int u = 8 * q + e;
             const float tcv = tanh_(fc[e]);
-            const float dhv = dh[u];
-            const float dcv = fmaf(dhv * fo[e], 1.f - tcv * tcv, dc[u]);
+            const float dhv = __uint_as_float(rdh[e]);
+            const float dcv = fmaf(dhv * fo[e], 1.f - tcv * tcv, __uint_as_float(rdc[e]));
             d_o[e] = dhv * tcv * fo[e] * (1.f - fo[e]);
             di[e] = dcv * fg[e] * fi[e] * (1.f - fi[e]);
             df[e] = dcv * fcp[e] * ff[e] * (1.f - ff[e]);
             dg[e] = dcv * fi[e] * (1.f - fg[e] * fg[e]);
-            dc[u] = dcv * ff[e];
+            rdc[e] = __float_as_uint(dcv * ff[e]);
             if (d_x != nullptr)
               dx_acc += di[e] * s_wih[u0 + u] + df[e] * s_wih[C + u0 + u] + dg[e] * s_wih[2 * C + u0 + u] + d_o[e] * s_wih[3 * C + u0 + u];
           }
@@ -449,7 +484,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           MPGCN_ST_DA(2, dg);
           MPGCN_ST_DA(3, d_o);
 #undef MPGCN_ST_DA
-          *reinterpret_cast<uint4*>(sHX + sw128_off(row, 2 * hh + q)) = vh[q];     // h_{t-1}, this thread's 16 units
+          tmem_st_32x8(t_dc + 8 * q, rdc);
         }
         // columns 32..63 of the [h | x | 1 | 0] row: half 0 writes chunks 4,5 and half 1 chunks 6,7
         if (hh == 0) {
@@ -460,19 +495,17 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           *reinterpret_cast<uint4*>(sHX + sw128_off(row, 7)) = make_uint4(0u, 0u, 0u, 0u);
         }
         if (d_x != nullptr && live) atomicAdd(&d_x[xb + (size_t)t * NN], dx_acc * invS);   // two halves per cell
+#pragma unroll
+        for (int q = 0; q < 2; ++q) vc[q] = vcp[q];
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(da_ready);
-        if (t > 0) {
+        if (t > 0) {                        // dh_{t-1} is complete in TMEM once the dh MMA of this step retires
           mbar_wait(dh_ready, ph_dh);
           ph_dh ^= 1u;
           tc_fence_after();
-          uint32_t r[UN];
-          tmem_ld_32x16(TM_DH + lane_base + u0, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int u = 0; u < UN; ++u) dh[u] = __uint_as_float(r[u]);
-          tc_fence_before();
         }
       }
     }
@@ -526,7 +559,10 @@ size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN) {
   return 1024 + (size_t)lstm_grid(cells) * T * lstm_tc::CELLS * lstm_tc::STASH * sizeof(__half);
 }
 
-static const int kLstmSmem = 100 * 1024;      // forces exactly two CTAs per SM (their TMEM allocations always fit)
+// dynamic shared memory requests: just what the kernels carve (registers already limit residency to two CTAs per SM,
+// whose TMEM allocations -- 2 x 128 / 2 x 256 columns -- always fit); the rest of the 228 KB stays L1
+static const int kLstmFwdSmem = 24 * 1024;
+static const int kLstmSmem = 72 * 1024;
 
 int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
                          int B, int T, long long NN, cudaStream_t st) {
@@ -534,11 +570,11 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
   const long long cells = (long long)B * NN;
   static bool attr = false;
   if (!attr) {
-    MPGCN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmSmem));
+    MPGCN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmFwdSmem));
     attr = true;
   }
   prof_begin(PROF_LSTM_FWD, 8.0 * C * (C + 1) * (double)cells * T, st);
-  lstm_fwd_tc_kernel<<<lstm_grid(cells), THREADS, kLstmSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, cells, T, NN);
+  lstm_fwd_tc_kernel<<<lstm_grid(cells), THREADS, kLstmFwdSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
