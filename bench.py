@@ -260,20 +260,38 @@ def run_ours(a):
         del x, go, gd
         h2d = sum(t.numel() * t.element_size() for t in (x_host, y_host, go_host, gd_host))
 
-        def e2e_step():
-            xs = x_host.to(dev, non_blocking=True)
-            ys = y_host.to(dev, non_blocking=True)
-            gos = go_host.to(dev, non_blocking=True)
-            gds = gd_host.to(dev, non_blocking=True)
-            return float(step(xs, ys, gos, gds).item())      # device -> host read of the loss
+        # Double-buffered input pipeline, as a prefetching data loader would do it: step k's inputs are copied from pinned
+        # host memory on a side stream while step k-1 computes; every step still pays its own H2D copies and reads its loss
+        # back (D2H) inside the timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+        hosts = (x_host, y_host, go_host, gd_host)
 
-        for _ in range(2):
-            e2e_step()
+        def stage():
+            with torch.cuda.stream(copy_stream):
+                bufs = [t.to(dev, non_blocking=True) for t in hosts]
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return bufs, ev
+
+        def e2e_loop(n):
+            nxt = stage()
+            losses = []
+            for k in range(n):
+                bufs, ev = nxt
+                torch.cuda.current_stream().wait_event(ev)
+                for b in bufs:
+                    b.record_stream(torch.cuda.current_stream())
+                if k + 1 < n:
+                    nxt = stage()
+                loss = step(*bufs)
+                losses.append(float(loss.item()))            # device -> host read of the loss, every step
+            return losses
+
+        e2e_loop(2)
         sync_all()
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(a.steps):
-            e2e_step()
+        e2e_loop(a.steps)
         e1.record()
         sync_all()
         wall_ms = (time.perf_counter() - t0) * 1e3

@@ -194,6 +194,30 @@ def test_tensor_path_agrees_with_fp32_path_at_size(N, K, B, dyn, gmag, cuda_devi
     assert flipped < 2e-3, f"ReLU mask flips {flipped:.2e}"
 
 
+@pytest.mark.parametrize("N,K,B,dyn", [(500, 3, 2, True), (1000, 6, 1, False), (2000, 3, 1, False)])
+def test_baseline_config_sizes_forward_and_backward(N, K, B, dyn, cuda_device):
+    """BASELINE.json configs[2..4] shapes (N=500/K=3, N=1000/K=6, N=2000/K=3; batch reduced to keep the fp32 cross-check
+    short): fp16 tcgen05 path (2-CTA kernels, ragged 256-row tiles) vs our exact fp32 path, forward and backward."""
+    torch.manual_seed(N)
+    X = torch.tanh(torch.randn(B, N, N, 32, device=cuda_device))
+    if dyn:
+        Go = torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5
+        Gd = torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5
+    else:
+        Go = Gd = torch.randn(K, N, N, device=cuda_device) / N ** 0.5
+    W = torch.randn(K * K * 32, 32, device=cuda_device) * (2.0 / (K * K * 32 + 32)) ** 0.5
+    b = torch.randn(32, device=cuda_device) * 0.1
+    d_out = torch.randn(B, N, N, 32, device=cuda_device) * 1e-6
+    out16, saved16 = abi.forward(X, Go, Gd, W, b, True, "fp16")
+    out32, saved32 = abi.forward(X, Go, Gd, W, b, True, "fp32")
+    _check(out16, out32.cpu().numpy(), 1e-3, f"cfg N={N} K={K} out")
+    g16 = abi.backward(d_out, out16, Go, Gd, W, True, saved16, "fp16")
+    del saved16
+    g32 = abi.backward(d_out, out16, Go, Gd, W, True, saved32, "fp32")
+    for a, r, what in zip(g16, g32, ("dX", "dW", "db")):
+        _check(a, r.cpu().numpy(), 2e-3, f"cfg N={N} K={K} {what}")
+
+
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
 def test_size_independent_properties(prec, cuda_device):
     """Linearity in X (no activation), identity supports, static == broadcast dynamic; N = 300."""
