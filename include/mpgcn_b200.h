@@ -85,6 +85,16 @@ MPGCN_API int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, co
                              const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
                              size_t workspace_bytes, int B, int T, long long NN, int C, int precision, void* stream);
 
+/* FC head + multi-perspective fusion (reference MPGCN.py:74-76,107,110,112), one pass:
+ *     y[cell] = (1/M) * sum_m relu( g_m[cell,:] . w[m,:] + bias[m] )      (Linear(C -> 1) + ReLU per branch, mean over the M branches)
+ *   g    HOST array of M device pointers, each [cells, C] (cells = B*N*N);  w [M,C], bias [M];  y [cells]
+ *   pre  [M,cells] pre-activations kept for backward, or NULL (inference)
+ * backward: dy [cells]; dg HOST array of M device pointers [cells, C] (or NULL / NULL entries), dw [M,C], db [M]. */
+MPGCN_API int mpgcn_head_forward(const float* const* g, const float* w, const float* bias, float* y, float* pre, long long cells, int C, int M,
+                       void* stream);
+MPGCN_API int mpgcn_head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
+                        long long cells, int C, int M, void* stream);
+
 /* Launch accounting (bench.py evidence).  Every launch of a kernel of this library is counted per tag
  * (0 FWD_A, 1 FWD_MIX, 2 FWD_B, 3 BWD_V, 4 BWD_DW, 5 BWD_MIX, 6 BWD_DX: tcgen05 contractions; 7 fp32 SIMT GEMM;
  * 8 elementwise/layout; 9 LSTM forward; 10 LSTM backward).  With profiling enabled, tags 0-6, 9, 10 are also

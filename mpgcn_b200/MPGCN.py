@@ -111,12 +111,20 @@ class MPGCN(nn.Module):
         assert (len(x_seq.shape) == 5) & (self.num_nodes == x_seq.shape[2] == x_seq.shape[3])
         assert len(G_list) == self.M
         B, N = x_seq.shape[0], self.num_nodes
-        branch_out = []
+        feats = []
         for m in range(self.M):
             branch = self.branch_models[m]
             gcn_in = self._temporal(branch['temporal'], x_seq).reshape(B, N, N, self.lstm_hidden_dim)
             for layer in branch['spatial']:
                 gcn_in = layer(gcn_in, G_list[m])
-            branch_out.append(branch['fc'](gcn_in))
-        ensemble_out = torch.mean(torch.stack(branch_out, dim=-1), dim=-1)
+            feats.append(gcn_in)
+        fcs = [self.branch_models[m]['fc'][0] for m in range(self.M)]
+        if all(fc.out_features == 1 for fc in fcs) and feats[0].shape[-1] % 4 == 0 and self.M <= 8:
+            # Linear(C -> 1) + ReLU per branch and the mean over branches in one fused pass (reference MPGCN.py:107,110)
+            w = torch.cat([fc.weight for fc in fcs], dim=0)            # [M, C]
+            b = torch.cat([fc.bias for fc in fcs], dim=0)              # [M]
+            ensemble_out = ops.fc_relu_mean(feats, w, b)               # [B, N, N, 1]
+        else:
+            branch_out = [self.branch_models[m]['fc'](feats[m]) for m in range(self.M)]
+            ensemble_out = torch.mean(torch.stack(branch_out, dim=-1), dim=-1)
         return ensemble_out.unsqueeze(dim=1)

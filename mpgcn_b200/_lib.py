@@ -31,6 +31,10 @@ _SIGS = {
                             + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     "mpgcn_bdgcn_backward": (ctypes.c_int, [_c_f, _c_f, _c_f, _c_f, ctypes.c_int, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, _c_f,
                                             ctypes.c_size_t] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    "mpgcn_head_forward": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), _c_f, _c_f, _c_f, _c_f, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p]),
+    "mpgcn_head_backward": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), _c_f, _c_f, _c_f, ctypes.POINTER(ctypes.c_void_p), _c_f, _c_f,
+                                           ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "mpgcn_profile_enable": (None, [ctypes.c_int]),
     "mpgcn_profile_reset": (None, []),
     "mpgcn_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),

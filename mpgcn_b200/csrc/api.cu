@@ -77,6 +77,18 @@ int mpgcn_bdgcn_backward(const float* d_out, const float* out, const float* G_o,
   return bdgcn_backward_simt(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, st);
 }
 
+int mpgcn_head_forward(const float* const* g, const float* w, const float* bias, float* y, float* pre, long long cells, int C, int M,
+                       void* stream) {
+  MPGCN_CHECK(g && w && bias && y && cells >= 1, "mpgcn_head_forward: null pointer or empty input");
+  return head_forward(g, w, bias, y, pre, cells, C, M, static_cast<cudaStream_t>(stream));
+}
+
+int mpgcn_head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
+                        long long cells, int C, int M, void* stream) {
+  MPGCN_CHECK(g && w && pre && dy && dw && db && cells >= 1, "mpgcn_head_backward: null pointer or empty input");
+  return head_backward(g, w, pre, dy, dg, dw, db, cells, C, M, static_cast<cudaStream_t>(stream));
+}
+
 void mpgcn_profile_enable(int on) { prof_enable(on); }
 void mpgcn_profile_reset(void) { prof_reset(); }
 int mpgcn_profile_read(int tag, long long* launches, double* flops, double* ms) {

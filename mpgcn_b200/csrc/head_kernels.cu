@@ -1,0 +1,122 @@
+// FC head + branch fusion of the MPGCN model in one pass (reference: /root/reference/MPGCN.py:74-76,107,110,112):
+//     y[b,n,c] = (1/M) * sum_m relu( g_m[b,n,c,:] . w_m + bias_m )          (Linear(C -> 1) + ReLU per branch, mean over branches)
+// HBM-bound elementwise work: each cell reads M x C floats and writes one.  Eight threads share a cell (a float4 each for
+// C = 32; generally C/8 strided elements), so a warp reads four consecutive cells = 512 contiguous bytes per branch.
+#include "kernels.h"
+
+namespace mpgcn {
+
+constexpr int kMaxBranches = 8;
+
+struct HeadPtrs {
+  const float* g[kMaxBranches];      // [cells][C] per branch
+  float* dg[kMaxBranches];           // backward: [cells][C] per branch
+};
+
+__global__ void head_fwd_kernel(HeadPtrs p, const float* __restrict__ w /*[M][C]*/, const float* __restrict__ bias /*[M]*/,
+                                float* __restrict__ y, float* __restrict__ pre /*[M][cells] or null*/, long long cells, int C, int M) {
+  const int sub = threadIdx.x & 7;
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
+  for (long long cell = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); cell < cells; cell += stride) {
+    float acc = 0.f;
+    for (int m = 0; m < M; ++m) {
+      const float* g = p.g[m] + cell * C;
+      float s = 0.f;
+      for (int l = sub * 4; l < C; l += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(g + l);
+        const float4 ww = *reinterpret_cast<const float4*>(w + m * C + l);
+        s += v.x * ww.x + v.y * ww.y + v.z * ww.z + v.w * ww.w;
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += bias[m];
+      if (pre != nullptr && sub == 0) pre[(long long)m * cells + cell] = s;
+      acc += fmaxf(s, 0.f);
+    }
+    if (sub == 0) y[cell] = acc / (float)M;
+  }
+}
+
+// d g_m[cell,:] = dy[cell]/M * [pre_m > 0] * w_m ;  dw_m += sum_cell d_pre * g_m[cell,:] ;  db_m += sum_cell d_pre
+__global__ void head_bwd_kernel(HeadPtrs p, const float* __restrict__ w, const float* __restrict__ pre, const float* __restrict__ dy,
+                                float* __restrict__ dw /*[M][C]*/, float* __restrict__ db /*[M]*/, long long cells, int C, int M) {
+  extern __shared__ float s_acc[];     // [M][C + 1] block-level accumulators
+  for (int i = threadIdx.x; i < M * (C + 1); i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
+  const float inv_m = 1.f / (float)M;
+  // per-thread partial sums for the (few) weight elements this thread touches: C/8 per branch, kept in registers for C = 32
+  for (int m = 0; m < M; ++m) {
+    float wacc[4] = {0.f, 0.f, 0.f, 0.f}, bacc = 0.f;     // C <= 32 fast path; larger C falls through to smem atomics below
+    for (long long cell = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); cell < cells; cell += stride) {
+      const float d = (pre[(long long)m * cells + cell] > 0.f) ? dy[cell] * inv_m : 0.f;
+      const float* g = p.g[m] + cell * C;
+      float* dg = p.dg[m] ? p.dg[m] + cell * C : nullptr;
+      for (int l = sub * 4; l < C; l += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(g + l);
+        const float4 ww = *reinterpret_cast<const float4*>(w + m * C + l);
+        if (dg) *reinterpret_cast<float4*>(dg + l) = make_float4(d * ww.x, d * ww.y, d * ww.z, d * ww.w);
+        if (l < 32) {
+          wacc[0] += d * v.x; wacc[1] += d * v.y; wacc[2] += d * v.z; wacc[3] += d * v.w;
+        } else {
+          atomicAdd(&s_acc[m * (C + 1) + l], d * v.x); atomicAdd(&s_acc[m * (C + 1) + l + 1], d * v.y);
+          atomicAdd(&s_acc[m * (C + 1) + l + 2], d * v.z); atomicAdd(&s_acc[m * (C + 1) + l + 3], d * v.w);
+        }
+      }
+      if (sub == 0) bacc += d;
+    }
+    if (sub * 4 < C) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(&s_acc[m * (C + 1) + sub * 4 + e], wacc[e]);
+    }
+    if (sub == 0) atomicAdd(&s_acc[m * (C + 1) + C], bacc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M * (C + 1); i += blockDim.x) {
+    const int m = i / (C + 1), l = i % (C + 1);
+    if (l < C) atomicAdd(&dw[m * C + l], s_acc[i]);
+    else atomicAdd(&db[m], s_acc[i]);
+  }
+}
+
+static int head_grid(long long cells) {
+  long long b = (cells + 31) / 32;
+  const long long cap = (long long)device_sm_count() * 8;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+int head_forward(const float* const* g, const float* w, const float* bias, float* y, float* pre, long long cells, int C, int M,
+                 cudaStream_t st) {
+  MPGCN_CHECK(M >= 1 && M <= kMaxBranches, "head: %d branches unsupported (1..%d)", M, kMaxBranches);
+  MPGCN_CHECK(C >= 4 && C % 4 == 0, "head: C=%d must be a multiple of 4", C);
+  HeadPtrs p{};
+  for (int m = 0; m < M; ++m) {
+    MPGCN_CHECK(g[m] != nullptr && (reinterpret_cast<uintptr_t>(g[m]) & 15) == 0, "head: branch %d input null or misaligned", m);
+    p.g[m] = g[m];
+  }
+  prof_count(PROF_ELEMENTWISE);
+  head_fwd_kernel<<<head_grid(cells), 256, 0, st>>>(p, w, bias, y, pre, cells, C, M);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
+                  long long cells, int C, int M, cudaStream_t st) {
+  MPGCN_CHECK(M >= 1 && M <= kMaxBranches, "head: %d branches unsupported (1..%d)", M, kMaxBranches);
+  MPGCN_CHECK(C >= 4 && C % 4 == 0, "head: C=%d must be a multiple of 4", C);
+  HeadPtrs p{};
+  for (int m = 0; m < M; ++m) {
+    p.g[m] = g[m];
+    p.dg[m] = dg ? dg[m] : nullptr;
+  }
+  MPGCN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * M * C, st));
+  MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * M, st));
+  prof_count(PROF_ELEMENTWISE);
+  head_bwd_kernel<<<head_grid(cells), 256, sizeof(float) * M * (C + 1), st>>>(p, w, pre, dy, dw, db, cells, C, M);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mpgcn

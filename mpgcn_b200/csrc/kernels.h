@@ -58,6 +58,12 @@ int lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh,
                        const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
                        long long NN, int C, cudaStream_t s);
 
+// FC head + branch mean (head_kernels.cu); g / dg are HOST arrays of M device pointers
+int head_forward(const float* const* g, const float* w, const float* bias, float* y, float* pre, long long cells, int C, int M,
+                 cudaStream_t st);
+int head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
+                  long long cells, int C, int M, cudaStream_t st);
+
 // tcgen05 LSTM (lstm_tc.cu): hidden size 32 only
 bool lstm_tc_supported(int T, int C);
 size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN);

@@ -170,3 +170,48 @@ def lstm_last(x_seq: torch.Tensor, w_ih, w_hh, b_ih, b_hh, precision=None) -> to
     """h_T of a 1-layer, input-size-1 LSTM run over every OD cell of x_seq [B,T,N,N,1] -> [B*N*N, C]."""
     _require_cuda(x_seq, "x_seq")
     return _LSTMLastFn.apply(x_seq, w_ih, w_hh, b_ih, b_hh, precision)
+
+
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, b, *gs):
+        import ctypes
+        lib = _lib.load()
+        M = len(gs)
+        C = gs[0].shape[-1]
+        cells = gs[0].numel() // C
+        gc = [_f32c(g) for g in gs]
+        wc, bc = _f32c(w), _f32c(b)
+        y = torch.empty(gs[0].shape[:-1] + (1,), dtype=torch.float32, device=gs[0].device)
+        need = any(ctx.needs_input_grad)
+        pre = torch.empty((M, cells), dtype=torch.float32, device=y.device) if need else None
+        ptrs = (ctypes.c_void_p * M)(*[g.data_ptr() for g in gc])
+        with torch.cuda.device(y.device):
+            _lib.check(lib.mpgcn_head_forward(ptrs, _ptr(wc), _ptr(bc), _ptr(y), _ptr(pre), cells, C, M, _stream()), "head_forward")
+        ctx.dims = (M, C, cells)
+        ctx.save_for_backward(wc, pre if pre is not None else torch.empty(0, device=y.device), *gc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes
+        lib = _lib.load()
+        wc, pre, *gc = ctx.saved_tensors
+        M, C, cells = ctx.dims
+        dy = _f32c(dy)
+        dgs = [torch.empty_like(g) if ctx.needs_input_grad[2 + m] else None for m, g in enumerate(gc)]
+        dw = torch.empty_like(wc)
+        db = torch.empty(M, dtype=torch.float32, device=dy.device)
+        ptrs = (ctypes.c_void_p * M)(*[g.data_ptr() for g in gc])
+        dptrs = (ctypes.c_void_p * M)(*[(d.data_ptr() if d is not None else None) for d in dgs])
+        with torch.cuda.device(dy.device):
+            _lib.check(lib.mpgcn_head_backward(ptrs, _ptr(wc), _ptr(pre), _ptr(dy), dptrs, _ptr(dw), _ptr(db), cells, C, M, _stream()),
+                       "head_backward")
+        return (dw, db) + tuple(dgs)
+
+
+def fc_relu_mean(gs, w, b) -> torch.Tensor:
+    """(1/M) * sum_m relu(g_m @ w[m] + b[m]) for M branch activations g_m [..., C]; w [M, C], b [M] -> [..., 1]."""
+    for g in gs:
+        _require_cuda(g, "branch activation")
+    return _HeadFn.apply(w, b, *gs)

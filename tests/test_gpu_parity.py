@@ -128,6 +128,27 @@ def test_lstm_tensor_path_agrees_with_fp32_path(S, T, gmag, cuda_device):
         _check(a, r.cpu().numpy(), 1e-3 if n == "hT" else 2e-3, f"S={S} T={T} {n}")
 
 
+@pytest.mark.parametrize("M,C,cells", [(2, 32, 1000), (1, 8, 77), (3, 64, 4099)])
+def test_fused_head_matches_oracle(M, C, cells, cuda_device):
+    """Linear(C->1)+ReLU per branch and branch mean in one kernel (reference MPGCN.py:74-76,107,110) vs the numpy oracle."""
+    rng = np.random.default_rng(M * 100 + C)
+    gs = [rng.standard_normal((cells, C)).astype(np.float32) for _ in range(M)]
+    w = (rng.standard_normal((M, C)) / C ** 0.5).astype(np.float32)
+    b = (rng.standard_normal(M) * 0.1).astype(np.float32)
+    dy = rng.standard_normal((cells, 1)).astype(np.float32)
+    gt = [_t(g, cuda_device, grad=True) for g in gs]
+    wt, bt = _t(w, cuda_device, grad=True), _t(b, cuda_device, grad=True)
+    y = ops.fc_relu_mean(gt, wt, bt)
+    y.backward(_t(dy, cuda_device))
+    outs = [orc.fc_relu_forward(gs[m], w[m:m + 1], b[m:m + 1]) for m in range(M)]
+    _check(y, np.mean(np.stack(outs, -1), -1), 1e-5, "head y")
+    for m in range(M):
+        dg, dw, db = orc.fc_relu_backward(gs[m], w[m:m + 1], b[m:m + 1], dy / M)
+        _check(gt[m].grad, dg, 1e-5, f"head dg{m}")
+        _check(wt.grad[m:m + 1], dw, 1e-4, f"head dw{m}")
+        _check(bt.grad[m:m + 1], db, 1e-4, f"head db{m}")
+
+
 @pytest.mark.parametrize("name", golden_names("mpgcn_"))
 def test_full_model_matches_reference_fixture(name, cuda_device):
     g = load_golden(name)
@@ -150,12 +171,14 @@ def test_full_model_matches_reference_fixture(name, cuda_device):
         for m in range(2):
             for layer in model.branch_models[m]['spatial']:
                 hooks.append(layer.register_forward_hook(lambda mod, inp, out, m=m: caps[m]["layers"].append(out.detach().cpu().numpy())))
-            hooks.append(model.branch_models[m]['fc'].register_forward_hook(lambda mod, inp, out, m=m: caps[m].__setitem__("fc", out.detach().cpu().numpy())))
         y = model(x_seq=_t(g["x_seq"], cuda_device), G_list=G_list)     # keyword call, as Model_Trainer.py:107
         y.backward(_t(g["d_y"], cuda_device))
         torch.cuda.synchronize()
         for h in hooks:
             h.remove()
+        for m in range(2):     # the fused head never materialises the per-branch FC output; rebuild its ReLU mask from the last layer
+            fc = model.branch_models[m]['fc'][0]
+            caps[m]["fc"] = orc.fc_relu_forward(caps[m]["layers"][-1], fc.weight.detach().cpu().numpy(), fc.bias.detach().cpu().numpy())
         tf, tb = TOL[prec]
         _check(y, g["y"], tf, f"{name}/{prec}/y")
         if prec == "fp32":
