@@ -113,63 +113,152 @@ __device__ __forceinline__ uint4* stash_at(__half* base, int t, int chunk) {
   return reinterpret_cast<uint4*>(base + (size_t)t * (STASH_CHUNKS * CELLS * 8)) + chunk * CELLS;   // chunk is a compile-time constant at every call site
 }
 
+// Two activations with ONE reciprocal: 1/a and 1/b from r = 1/(a*b).  The SFU is the bottleneck of the forward pass
+// (10 transcendental ops per hidden unit and step: 5 ex2 + 5 rcp); pairing (i,g) and (f,o) removes two of the five rcp.
+// Exponent arguments are clamped to +-43.28 (= 30 * log2 e) so that a*b <= (1 + e^30)^2 ~ 1e26 cannot overflow; the clamp is
+// lossless in fp32 (sigmoid(30) = 1 - 9e-14, tanh(15) = 1 - 2e-13).
+__device__ __forceinline__ float exp_arg(float x, float scale) { return fminf(fmaxf(x * scale, -43.280851f), 43.280851f); }
+// returns sigmoid(xa) and tanh(xb)
+__device__ __forceinline__ void sig_tanh_pair(float xa, float xb, float& sa, float& tb) {
+  const float a = 1.f + ex2_(exp_arg(xa, -1.4426950408889634f));
+  const float b = 1.f + ex2_(exp_arg(xb, -2.8853900817779268f));
+  const float r = rcp_(a * b);
+  sa = r * b;
+  tb = fmaf(2.f * r, a, -1.f);
+}
+// returns sigmoid(xa) and sigmoid(xb)
+__device__ __forceinline__ void sig_sig_pair(float xa, float xb, float& sa, float& sb) {
+  const float a = 1.f + ex2_(exp_arg(xa, -1.4426950408889634f));
+  const float b = 1.f + ex2_(exp_arg(xb, -1.4426950408889634f));
+  const float r = rcp_(a * b);
+  sa = r * b;
+  sb = r * a;
+}
+
 // One LSTM step for 16 hidden units of one cell.  t_col = TMEM address of (lane quarter, column 16*hh) of the gate
 // accumulator; u0 = 16*hh.  Updates c[], returns h[]; optionally stashes gates, c and h.
-template <bool STASH_OUT>
+#ifndef MPGCN_LSTM_BWD_PAIRED
+#define MPGCN_LSTM_BWD_PAIRED 1
+#endif
+
+template <bool STASH_OUT, bool PAIRED = true>
 __device__ __forceinline__ void cell_step(uint32_t t_col, bool has_mma, float xv, const float* s_bias, const float* s_wih, int u0,
                                           float (&c)[UN], float (&h)[UN], __half* stash, int t_stash, int hh) {
-  uint32_t r[UN];
-  float ig[UN];
-  if (has_mma) { tmem_ld_32x16(t_col + 0 * C, r); tmem_ld_wait(); }
+  if (!PAIRED) {      // one gate block at a time (lower register pressure, 10 SFU ops per unit)
+    uint32_t r[UN];
+    float ig[UN];
+    if (has_mma) { tmem_ld_32x16(t_col + 0 * C, r); tmem_ld_wait(); }
 #pragma unroll
-  for (int u = 0; u < UN; ++u) ig[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[u0 + u], xv, s_bias[u0 + u]));
-  if (STASH_OUT) {
+    for (int u = 0; u < UN; ++u) ig[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[u0 + u], xv, s_bias[u0 + u]));
+    if (STASH_OUT) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 0 * 4 + q) = pack8(ig + 8 * q);
+      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 0 * 4 + q) = pack8(ig + 8 * q);
+    }
+    if (has_mma) { tmem_ld_32x16(t_col + 2 * C, r); tmem_ld_wait(); }
+    {
+      float g[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) g[u] = tanh_((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[2 * C + u0 + u], xv, s_bias[2 * C + u0 + u]));
+      if (STASH_OUT) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 2 * 4 + q) = pack8(g + 8 * q);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) ig[u] *= g[u];
+    }
+    if (has_mma) { tmem_ld_32x16(t_col + 1 * C, r); tmem_ld_wait(); }
+    {
+      float f[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) f[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[C + u0 + u], xv, s_bias[C + u0 + u]));
+      if (STASH_OUT) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 1 * 4 + q) = pack8(f + 8 * q);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) c[u] = fmaf(f[u], c[u], ig[u]);
+    }
+    if (STASH_OUT) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 4 * 4 + q) = pack8(c + 8 * q);
+    }
+    if (has_mma) { tmem_ld_32x16(t_col + 3 * C, r); tmem_ld_wait(); }
+    {
+      float o[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) o[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[3 * C + u0 + u], xv, s_bias[3 * C + u0 + u]));
+      if (STASH_OUT) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 3 * 4 + q) = pack8(o + 8 * q);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) h[u] = o[u] * tanh_(c[u]);
+    }
+    if (STASH_OUT) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 5 * 4 + q) = pack8(h + 8 * q);
+    }
+    return;
   }
-  if (has_mma) { tmem_ld_32x16(t_col + 2 * C, r); tmem_ld_wait(); }
+  uint32_t ra[UN], rb[UN];
+  float ig[UN];
+  // ---- input gate and cell candidate ----
+  if (has_mma) {
+    tmem_ld_32x16(t_col + 0 * C, ra);
+    tmem_ld_32x16(t_col + 2 * C, rb);
+    tmem_ld_wait();
+  }
   {
     float g[UN];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) g[u] = tanh_((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[2 * C + u0 + u], xv, s_bias[2 * C + u0 + u]));
+    for (int u = 0; u < UN; ++u) {
+      const float ai = (has_mma ? __uint_as_float(ra[u]) : 0.f) + fmaf(s_wih[u0 + u], xv, s_bias[u0 + u]);
+      const float ag = (has_mma ? __uint_as_float(rb[u]) : 0.f) + fmaf(s_wih[2 * C + u0 + u], xv, s_bias[2 * C + u0 + u]);
+      sig_tanh_pair(ai, ag, ig[u], g[u]);
+    }
     if (STASH_OUT) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 2 * 4 + q) = pack8(g + 8 * q);
+      for (int q = 0; q < 2; ++q) {
+        *stash_at(stash, t_stash, 0 * 4 + q) = pack8(ig + 8 * q);
+        *stash_at(stash, t_stash, 2 * 4 + q) = pack8(g + 8 * q);
+      }
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) ig[u] *= g[u];
   }
-  if (has_mma) { tmem_ld_32x16(t_col + 1 * C, r); tmem_ld_wait(); }
+  // ---- forget and output gates ----
+  if (has_mma) {
+    tmem_ld_32x16(t_col + 1 * C, ra);
+    tmem_ld_32x16(t_col + 3 * C, rb);
+    tmem_ld_wait();
+  }
   {
-    float f[UN];
+    float f[UN], o[UN];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) f[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[C + u0 + u], xv, s_bias[C + u0 + u]));
+    for (int u = 0; u < UN; ++u) {
+      const float af = (has_mma ? __uint_as_float(ra[u]) : 0.f) + fmaf(s_wih[C + u0 + u], xv, s_bias[C + u0 + u]);
+      const float ao = (has_mma ? __uint_as_float(rb[u]) : 0.f) + fmaf(s_wih[3 * C + u0 + u], xv, s_bias[3 * C + u0 + u]);
+      sig_sig_pair(af, ao, f[u], o[u]);
+    }
     if (STASH_OUT) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 1 * 4 + q) = pack8(f + 8 * q);
+      for (int q = 0; q < 2; ++q) {
+        *stash_at(stash, t_stash, 1 * 4 + q) = pack8(f + 8 * q);
+        *stash_at(stash, t_stash, 3 * 4 + q) = pack8(o + 8 * q);
+      }
     }
 #pragma unroll
-    for (int u = 0; u < UN; ++u) c[u] = fmaf(f[u], c[u], ig[u]);
+    for (int u = 0; u < UN; ++u) {
+      c[u] = fmaf(f[u], c[u], ig[u]);
+      h[u] = o[u] * tanh_(c[u]);
+    }
   }
   if (STASH_OUT) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 4 * 4 + q) = pack8(c + 8 * q);
-  }
-  if (has_mma) { tmem_ld_32x16(t_col + 3 * C, r); tmem_ld_wait(); }
-  {
-    float o[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) o[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[3 * C + u0 + u], xv, s_bias[3 * C + u0 + u]));
-    if (STASH_OUT) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 3 * 4 + q) = pack8(o + 8 * q);
+    for (int q = 0; q < 2; ++q) {
+      *stash_at(stash, t_stash, 4 * 4 + q) = pack8(c + 8 * q);
+      *stash_at(stash, t_stash, 5 * 4 + q) = pack8(h + 8 * q);
     }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) h[u] = o[u] * tanh_(c[u]);
-  }
-  if (STASH_OUT) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 5 * 4 + q) = pack8(h + 8 * q);
   }
 }
 
@@ -391,7 +480,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
             ph_g ^= 1u;
             tc_fence_after();
           }
-          cell_step<true>(TM_GATES + lane_base + u0, t > 0, xv, s_bias, s_wih, u0, c, h, my_stash, t, hh);
+          cell_step<true, (MPGCN_LSTM_BWD_PAIRED != 0)>(TM_GATES + lane_base + u0, t > 0, xv, s_bias, s_wih, u0, c, h, my_stash, t, hh);
           if (t + 1 < T) {
             write_h_tile(sH, row, hh, h);
             fence_proxy_async_smem();
