@@ -137,8 +137,15 @@ __device__ __forceinline__ void sig_sig_pair(float xa, float xb, float& sa, floa
 
 // One LSTM step for 16 hidden units of one cell.  t_col = TMEM address of (lane quarter, column 16*hh) of the gate
 // accumulator; u0 = 16*hh.  Updates c[], returns h[]; optionally stashes gates, c and h.
+// tuning switches (measured on B200, N=1000, B=4, T=12)
 #ifndef MPGCN_LSTM_BWD_PAIRED
-#define MPGCN_LSTM_BWD_PAIRED 1
+#define MPGCN_LSTM_BWD_PAIRED 0
+#endif
+#ifndef MPGCN_LSTM_FWD_PAIRED
+#define MPGCN_LSTM_FWD_PAIRED 1
+#endif
+#ifndef MPGCN_LSTM_FWD_LB
+#define MPGCN_LSTM_FWD_LB 1
 #endif
 
 template <bool STASH_OUT, bool PAIRED = true>
@@ -270,7 +277,13 @@ __device__ __forceinline__ void write_h_tile(uint8_t* sH, int row, int hh, const
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
+#if MPGCN_LSTM_FWD_LB == 1
+__global__ void __launch_bounds__(THREADS, 2)
+#elif MPGCN_LSTM_FWD_LB == 2
+__global__ void __launch_bounds__(THREADS)          // with -maxrregcount=112 for this file
+#else
 __global__ void __maxnreg__(112)
+#endif
 lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ hT, long long cells, int T,
                    long long NN) {
@@ -339,7 +352,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           ph ^= 1u;
           tc_fence_after();
         }
-        cell_step<false>(t_col, t > 0, xv, s_bias, s_wih, u0, c, h, nullptr, 0, hh);
+        cell_step<false, (MPGCN_LSTM_FWD_PAIRED != 0)>(t_col, t > 0, xv, s_bias, s_wih, u0, c, h, nullptr, 0, hh);
         if (t + 1 < T) {
           write_h_tile(sH, row, hh, h);
           fence_proxy_async_smem();
@@ -366,7 +379,14 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
 constexpr int DA_BYTES = 32768;     // [128 cells][128 gates] fp16 as two [128][64] SW128 sub-tiles
 constexpr int HX_BYTES = 16384;     // [128 cells][64] fp16, SW128
 
+#ifndef MPGCN_LSTM_BWD_LB
+#define MPGCN_LSTM_BWD_LB 0
+#endif
+#if MPGCN_LSTM_BWD_LB == 2
+__global__ void __launch_bounds__(THREADS)          // with -maxrregcount=112 for this file
+#else
 __global__ void __maxnreg__(112)
+#endif
 lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ d_hT,
                    float* __restrict__ d_w_ih, float* __restrict__ d_w_hh, float* __restrict__ d_b, float* __restrict__ d_x,
@@ -668,8 +688,14 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
     MPGCN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmFwdSmem));
     attr = true;
   }
+  static int fwd_smem = 0;
+  if (fwd_smem == 0) {
+    const char* e = getenv("MPGCN_B200_LSTM_FWD_SMEM_KB");     // tuning knob: dynamic smem request (L1 carve-out)
+    fwd_smem = e ? atoi(e) * 1024 : kLstmFwdSmem;
+    if (fwd_smem > kLstmFwdSmem) MPGCN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem));
+  }
   prof_begin(PROF_LSTM_FWD, 8.0 * C * (C + 1) * (double)cells * T, st);
-  lstm_fwd_tc_kernel<<<lstm_grid(cells), THREADS, kLstmFwdSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, cells, T, NN);
+  lstm_fwd_tc_kernel<<<lstm_grid(cells), THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
   return 0;

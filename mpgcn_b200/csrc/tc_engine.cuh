@@ -199,13 +199,15 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
         const int kb1 = p.split_k ? min(kb0 + p.kb_per_slice, p.kb_total) : p.kb_total;
         const int zA0 = ((z / p.am.z_div) % p.am.z_mod) * p.am.z_mul;
         const int zB0 = ((z / p.bm.z_div) % p.bm.z_mod) * p.bm.z_mul;
+        // segment / k-block counters are advanced incrementally: the channel-mix contractions spend only ~100 clk of MMA
+        // per k-block, so integer divisions in this single-thread loop would bound the whole kernel
+        int seg = kb0 / p.kb_per_seg;
+        int kk = kb0 - seg * p.kb_per_seg;
+        int sa_lo = seg % p.am.seg_mod, sa_hi = seg / p.am.seg_mod;
+        int sb_lo = seg % p.bm.seg_mod, sb_hi = seg / p.bm.seg_mod;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], (uint32_t)(A_STAGE + B_STAGE));
-          const int seg = kb / p.kb_per_seg;
-          const int kk = kb - seg * p.kb_per_seg;
-          const int sa_lo = seg % p.am.seg_mod, sa_hi = seg / p.am.seg_mod;
-          const int sb_lo = seg % p.bm.seg_mod, sb_hi = seg / p.bm.seg_mod;
           const int zA = zA0 + sa_lo * p.am.seg_mul + sa_hi * p.am.seg_hi_mul;
           const int zB = zB0 + sb_lo * p.bm.seg_mul + sb_hi * p.bm.seg_hi_mul;
           const int kA = kk * BK + sa_lo * p.am.k_seg;
@@ -227,6 +229,11 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
               tma_load_4d(b_dst + (size_t)j * BK * 64, &p.b_map, &full[stage], (nt * R + j) * 32, kB, zB, 0);
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
+          if (++kk == p.kb_per_seg) {
+            kk = 0;
+            if (++sa_lo == p.am.seg_mod) { sa_lo = 0; ++sa_hi; }
+            if (++sb_lo == p.bm.seg_mod) { sb_lo = 0; ++sb_hi; }
+          }
         }
       }
     }
@@ -414,13 +421,10 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
         const int m0 = mt * 256 + (int)rank * 128;
         const int zA0 = ((z / p.am.z_div) % p.am.z_mod) * p.am.z_mul;
         const int zB0 = ((z / p.bm.z_div) % p.bm.z_mod) * p.bm.z_mul;
+        int kk = 0, sa_lo = 0, sa_hi = 0, sb_lo = 0, sb_hi = 0;
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           if (rank == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 * (A_STAGE + B_STAGE)));
-          const int seg = kb / p.kb_per_seg;
-          const int kk = kb - seg * p.kb_per_seg;
-          const int sa_lo = seg % p.am.seg_mod, sa_hi = seg / p.am.seg_mod;
-          const int sb_lo = seg % p.bm.seg_mod, sb_hi = seg / p.bm.seg_mod;
           const int zA = zA0 + sa_lo * p.am.seg_mul + sa_hi * p.am.seg_hi_mul;
           const int zB = zB0 + sb_lo * p.bm.seg_mul + sb_hi * p.bm.seg_hi_mul;
           const int kA = kk * BK + sa_lo * p.am.k_seg;
@@ -441,6 +445,11 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
               tma_load_4d_2cta(b_dst + (size_t)j * BK * 64, &p.b_map, &full[stage], (r0 + j) * 32, kB, zB, 0);
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
+          if (++kk == p.kb_per_seg) {
+            kk = 0;
+            if (++sa_lo == p.am.seg_mod) { sa_lo = 0; ++sa_hi; }
+            if (++sb_lo == p.bm.seg_mod) { sb_lo = 0; ++sb_hi; }
+          }
         }
       }
     }
