@@ -390,7 +390,7 @@ __global__ void __maxnreg__(112)
 lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ d_hT,
                    float* __restrict__ d_w_ih, float* __restrict__ d_w_hh, float* __restrict__ d_b, float* __restrict__ d_x,
-                   __half* __restrict__ scratch, const float* __restrict__ scale2, long long cells, int T, long long NN, int dbg) {
+                   __half* __restrict__ scratch, const float* __restrict__ scale2, long long cells, int T, long long NN) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sDA = smem;                               // 32 KB (single buffer: MMA2 of step t retires long before step t-1's math ends)
@@ -448,7 +448,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
         }
         __syncwarp();
       }
-      for (int t = (dbg & 1) ? -1 : T - 1; t >= 0; --t) {      // backward through time (dbg bit 0: timing experiment, skipped)
+      for (int t = T - 1; t >= 0; --t) {      // backward through time
         mbar_wait(da_ready, ph_da);
         ph_da ^= 1u;
         tc_fence_after();
@@ -472,7 +472,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
         __syncwarp();
       }
     }
-    if (lane == 0 && !(dbg & 1)) umma_commit(acc_done);
+    if (lane == 0) umma_commit(acc_done);
     __syncwarp();
   } else {
     // ---------------- epilogue warps: thread = (cell row, unit half) ----------------
@@ -533,7 +533,7 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
       uint4 vc[2];
 #pragma unroll
       for (int q = 0; q < 2; ++q) vc[q] = *stash_at(my_stash, T - 1, 4 * 4 + q);
-      for (int t = (dbg & 1) ? -1 : T - 1; t >= 0; --t) {
+      for (int t = T - 1; t >= 0; --t) {
         // issue the step's stash loads first (own 16 units of i f g o; c of step t-1); h(t-1) goes global -> smem directly
         uint4 vi[2], vf[2], vg[2], vo[2], vcp[2];
 #pragma unroll
@@ -619,9 +619,9 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
       }
     }
     // ---- flush the weight-gradient accumulator: TMEM lane = gate row j, this thread's 16 columns ----
-    if (!(dbg & 1)) mbar_wait(acc_done, 0);
+    mbar_wait(acc_done, 0);
     tc_fence_after();
-    if (tiles > (long long)blockIdx.x && !(dbg & 1)) {
+    if (tiles > (long long)blockIdx.x) {
       uint32_t r[UN];
       tmem_ld_32x16(TM_DW + lane_base + u0, r);
       tmem_ld_wait();
@@ -651,12 +651,6 @@ __global__ void copy_vec_kernel(const float* src, float* dst, int n) {
 // host
 // ---------------------------------------------------------------------------------------
 bool lstm_tc_supported(int T, int C) { return C == 32 && T >= 1 && T <= 256; }
-
-static int lstm_dbg() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MPGCN_B200_LSTM_DBG"); v = e ? atoi(e) : 0; }   // timing experiments only (wrong results)
-  return v;
-}
 
 static int lstm_grid(long long cells) {
   const long long tiles = (cells + lstm_tc::CELLS - 1) / lstm_tc::CELLS;
@@ -725,7 +719,7 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   MPGCN_CHECK(smem <= (size_t)kLstmSmem, "internal: lstm backward smem");
   prof_begin(PROF_LSTM_BWD, 16.0 * C * (C + 1) * (double)cells * T, st);
   lstm_bwd_tc_kernel<<<lstm_grid(cells), THREADS, kLstmSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x, scratch,
-                                                                   scale2, cells, T, NN, lstm_dbg());
+                                                                   scale2, cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
   prof_count(PROF_ELEMENTWISE);
