@@ -92,13 +92,7 @@ static bool flat_b_boxes() {
 }
 
 // launch an N^3 contraction on the 2-CTA kernel when the M extent allows it (p prepared for the 1-CTA kernel)
-static int b_box_r(int n_rows) { return tc::use_4cta(n_rows) ? 2 : tc::use_2cta(n_rows) ? 4 : 8; }
-
 static int launch_big(int ak, GemmParams& p, int m_rows, cudaStream_t st) {
-  if (tc::use_4cta(m_rows)) {
-    p.MT = ceil_div(m_rows, 512);
-    return tc::launch_contract_4cta(ak, p, st);
-  }
   if (tc::use_2cta(m_rows)) {
     p.MT = ceil_div(m_rows, 256);
     return tc::launch_contract_2cta(ak, p, st);
@@ -203,7 +197,7 @@ static int run_fwd_a(const BdgcnShape& s, const __half* gd16, const __half* x16,
   GemmParams p;
   init_params(p);
   if (int e = map_support_mn(&p.a_map, gd16, N, Np, N, (long long)(s.dynamic ? s.B : 1) * K)) return e;
-  if (int e = map_chunks(&p.b_map, x16, N, 32, N, (long long)N * 32, s.B, (long long)N * N * 32, 64, b_box_r(N))) return e;
+  if (int e = map_chunks(&p.b_map, x16, N, 32, N, (long long)N * 32, s.B, (long long)N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
   p.am = omap(1, s.dynamic ? kBig : K, 1, 0, 0);        // z = b*K + d -> support index
   p.bm = omap(K, kBig, 1, 0, 0);                        // -> b
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B * K; p.R = 8;
@@ -251,7 +245,7 @@ static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16,
     if (int e = map_flat(&p.b_map, u16, (long long)N * 32, (long long)K * N, s.B, 64)) return e;
     p.b_flat = 1;
   } else {
-    if (int e = map_chunks(&p.b_map, u16, (long long)K * N, (long long)N * 32, N, 32, s.B, (long long)K * N * N * 32, 64, b_box_r(N))) return e;
+    if (int e = map_chunks(&p.b_map, u16, (long long)K * N, (long long)N * 32, N, 32, s.B, (long long)K * N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
   }
   p.am = omap(1, s.dynamic ? kBig : 1, 1, 0, 0);
   p.bm = omap(1, kBig, 1, 0, 0);
@@ -278,7 +272,7 @@ static int run_bwd_v(const BdgcnShape& s, const __half* go16, const __half* dp16
     if (int e = map_flat(&p.b_map, dp16, (long long)N * 32, N, s.B, 64)) return e;
     p.b_flat = 1;
   } else {   // dP16 [b][m][e][h] read as (h, k = m, r = e, b), see run_fwd_b
-    if (int e = map_chunks(&p.b_map, dp16, N, (long long)N * 32, N, 32, s.B, (long long)N * N * 32, 64, b_box_r(N))) return e;
+    if (int e = map_chunks(&p.b_map, dp16, N, (long long)N * 32, N, 32, s.B, (long long)N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
   }
   p.am = omap(1, s.dynamic ? kBig : K, 1, 0, 0);        // z = b*K + o
   p.bm = omap(K, kBig, 1, 0, 0);
@@ -322,7 +316,7 @@ static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16
   GemmParams p;
   init_params(p);
   if (int e = map_support_k(&p.a_map, gd16, N, Np, (long long)(s.dynamic ? s.B : 1) * K)) return e;
-  if (int e = map_chunks(&p.b_map, y16, N, 32, N, (long long)N * 32, (long long)s.B * K, (long long)N * N * 32, 64, b_box_r(N))) return e;
+  if (int e = map_chunks(&p.b_map, y16, N, 32, N, (long long)N * 32, (long long)s.B * K, (long long)N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
   p.am = omap(1, s.dynamic ? kBig : 1, s.dynamic ? K : 0, 1, 0);   // support index = (b*K) + d
   p.bm = omap(1, kBig, K, 1, 0);                                    // plane = b*K + d
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;

@@ -116,17 +116,6 @@ __device__ __forceinline__ void tma_load_4d_2cta(void* smem_dst, const CUtensorM
       : "memory");
 }
 
-// 2-CTA load multicast to the CTAs in `cta_mask` (same shared-memory offset in each); bytes are credited to the barrier of the
-// leader of each destination CTA's pair.
-__device__ __forceinline__ void tma_load_4d_2cta_mc(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar, uint16_t cta_mask,
-                                                    int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(leader_bar) & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
 // ----------------------------------------------------------------------------------------
 // device: thread-block clusters
 // ----------------------------------------------------------------------------------------
@@ -201,11 +190,6 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t a_desc, 
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void umma_commit_2cta_mask(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
 // 32 lanes x 32 columns of 32-bit accumulators -> 32 registers per thread (thread = lane).

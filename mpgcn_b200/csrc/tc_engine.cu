@@ -232,65 +232,6 @@ static int launch2_impl(GemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
-template <int AK>
-static int launch4_impl(GemmParams& p, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    MPGCN_CUDA(cudaFuncSetAttribute(contract4_kernel<AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_done = true;
-  }
-  MPGCN_CHECK(p.R == 8 && !p.split_k, "4-CTA kernel needs R = 8 and no split-K");
-  int stages = (int)((kMaxSmem - 1024 - 512) / 32768);
-  if (stages > 8) stages = 8;
-  p.stages = stages;
-  const long long tiles = (long long)p.MT * p.NT * p.Z;
-  MPGCN_CHECK(tiles > 0 && tiles < (1ll << 31), "bad tile count %lld", tiles);
-  MPGCN_CHECK(p.kb_total > 0 && p.kb_per_seg > 0, "empty contraction");
-  long long quads = device_sm_count() / 4;
-  if (quads > tiles) quads = tiles;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(4 * quads));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kMaxSmem;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 4;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  const int tag = g_prof.next_tag;
-  const double fl = g_prof.next_flops;
-  g_prof.next_tag = -1;
-  g_prof.next_flops = 0;
-  prof_begin(tag, fl, stream);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, contract4_kernel<AK>, p);
-  prof_end(stream);
-  if (e != cudaSuccess) {
-    set_error("cudaLaunchKernelEx(contract4_kernel) failed: %s", cudaGetErrorString(e));
-    return 2;
-  }
-  return 0;
-}
-
-int launch_contract_4cta(int ak, GemmParams& p, cudaStream_t stream) {
-  if (ak == A_MN128) return launch4_impl<A_MN128>(p, stream);
-  if (ak == A_K128) return launch4_impl<A_K128>(p, stream);
-  set_error("no 4-CTA contraction kernel for A kind %d", ak);
-  return 1;
-}
-
-// 512-row cluster tiles only when they waste no more rows than 256-row pair tiles (MPGCN_B200_4CTA=1 enables the variant)
-bool use_4cta(int n_rows) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("MPGCN_B200_4CTA");
-    enabled = (e && e[0] == '1') ? 1 : 0;
-  }
-  return enabled && use_2cta(n_rows) && ((n_rows + 511) / 512) * 512 == ((n_rows + 255) / 256) * 256;
-}
-
 int launch_contract_2cta(int ak, GemmParams& p, cudaStream_t stream) {
   if (ak == A_MN128) return launch2_impl<A_MN128>(p, stream);
   if (ak == A_K128) return launch2_impl<A_K128>(p, stream);

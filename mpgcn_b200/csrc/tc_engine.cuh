@@ -563,226 +563,6 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
     tmem_dealloc_2cta(tmem_base, kTmemCols);
   }
 }
-
-// ---------------------------------------------------------------------------------------------------------
-// 4-CTA cluster variant: two cta_group::2 pairs stacked along M (512 x 256 per cluster) share the B tile.  Each CTA still
-// receives its 16 KB half of B in shared memory, but loads only a QUARTER itself and gets the other quarter by TMA
-// multicast from the same-rank CTA of the other pair: L2 -> SM traffic per CTA and k-block drops from 32 KB to 24 KB
-// (the 2-CTA kernel measures 69 % L2 throughput at 52-60 % tensor-pipe activity).
-// ---------------------------------------------------------------------------------------------------------
-template <int AK>
-__global__ void __launch_bounds__(kThreads, 1) contract4_kernel(const __grid_constant__ GemmParams p) {
-  static_assert(AK == A_MN128 || AK == A_K128, "2-CTA kernel serves the N^3 contractions only");
-  constexpr int BK = 64;
-  using C = Cfg<AK, BK>;
-  constexpr int A_STAGE = C::A_STAGE;          // 16 KB: this CTA's 128 rows
-  constexpr int B_STAGE = 4 * BK * 64;         // 16 KB: this CTA's 4 chunks (128 of the 256 columns)
-  const int S = p.stages;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)S * A_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)S * B_STAGE);
-  uint64_t* empty = full + S;
-  uint64_t* tfull = empty + S;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();    // 0..3: two CTA pairs {0,1} and {2,3} stacked along M, sharing the B tile
-  const uint32_t rank = crank & 1u;            // rank within the pair, 0 = the pair's leader
-  const uint32_t pr = crank >> 1;              // pair index within the cluster
-  const int pair = blockIdx.x >> 2;            // (cluster index: one 512 x 256 tile per cluster)
-  const int num_pairs = gridDim.x >> 2;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.a_map);
-    tma_prefetch_desc(&p.b_map);
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full[s], 1);       // leader's is the live one: its producer's arrive.expect_tx (both CTAs' bytes)
-      mbar_init(&empty[s], 2);      // multicast commits of BOTH pairs' MMA warps (the B quarter loads land in both pairs)
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull[a], 1);      // multicast commit
-      mbar_init(&tempty[a], 8);     // leader's: 4 epilogue warps of each CTA
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc_2cta(tmem_slot, kTmemCols);
-    tmem_relinquish_2cta();
-  }
-  if (warp == 2) sbias[lane] = p.ep.bias ? p.ep.bias[lane] : 0.f;
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();               // peer barriers are initialised before anyone signals them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int num_tiles = p.MT * p.NT * p.Z;     // MT counts 256-row tiles here
-
-  if (warp == 0) {
-    // ------------------------------ TMA producer (both CTAs) ------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
-        const int mt = t % p.MT;
-        const int rest = t / p.MT;
-        const int nt = rest % p.NT;
-        const int z = rest / p.NT;
-        const int m0 = mt * 512 + (int)pr * 256 + (int)rank * 128;
-        const int zA0 = ((z / p.am.z_div) % p.am.z_mod) * p.am.z_mul;
-        const int zB0 = ((z / p.bm.z_div) % p.bm.z_mod) * p.bm.z_mul;
-        int kk = 0, sa_lo = 0, sa_hi = 0, sb_lo = 0, sb_hi = 0;
-        for (int kb = 0; kb < p.kb_total; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
-          if (rank == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 * (A_STAGE + B_STAGE)));
-          const int zA = zA0 + sa_lo * p.am.seg_mul + sa_hi * p.am.seg_hi_mul;
-          const int zB = zB0 + sb_lo * p.bm.seg_mul + sb_hi * p.bm.seg_hi_mul;
-          const int kA = kk * BK + sa_lo * p.am.k_seg;
-          const int kB = kk * BK + sb_lo * p.bm.k_seg;
-          uint8_t* a_dst = sA + (size_t)stage * A_STAGE;
-          uint8_t* b_dst = sB + (size_t)stage * B_STAGE;
-          if (AK == A_MN128) {
-            tma_load_4d_2cta(a_dst, &p.a_map, &full[stage], m0, kA, zA, 0);
-            tma_load_4d_2cta(a_dst + BK * 128, &p.a_map, &full[stage], m0 + 64, kA, zA, 0);
-          } else {
-            tma_load_4d_2cta(a_dst, &p.a_map, &full[stage], kA, m0, zA, 0);
-          }
-          // this CTA needs chunks rank*4 .. +3 of the 8-chunk tile; it loads the quarter pr*2, pr*2+1 of them and multicasts
-          // it to the CTA of the same rank in the other pair (which loads the other quarter for both)
-          const int r0 = nt * 8 + (int)rank * 4 + (int)pr * 2;
-          const uint16_t mc = (uint16_t)(0x5u << rank);       // ranks {0,2} or {1,3}
-          uint8_t* q_dst = b_dst + (size_t)pr * 2 * BK * 64;
-          if (!p.b_flat) {              // dims (ch, k, r, z), box (32, 64, 2)
-            tma_load_4d_2cta_mc(q_dst, &p.b_map, &full[stage], mc, 0, kB, r0, zB);
-          } else {
-            for (int j = 0; j < 2; ++j)
-              tma_load_4d_2cta_mc(q_dst + (size_t)j * BK * 64, &p.b_map, &full[stage], mc, (r0 + j) * 32, kB, zB, 0);
-          }
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-          if (++kk == p.kb_per_seg) {
-            kk = 0;
-            if (++sa_lo == p.am.seg_mod) { sa_lo = 0; ++sa_hi; }
-            if (++sb_lo == p.bm.seg_mod) { sb_lo = 0; ++sb_hi; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
-    if (rank == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const uint32_t idesc = umma_idesc_f16(256, 256, C::A_MN ? 1 : 0, 1);
-      const uint64_t a_hi = umma_desc_hi(C::A_SBO, C::A_LAYOUT);
-      const uint64_t b_hi = umma_desc_hi(C::B_SBO, 4u);
-      for (int t = pair; t < num_tiles; t += num_pairs) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
-        for (int kb = 0; kb < p.kb_total; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE);
-            const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_STAGE);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t ad = umma_desc(a_hi, a_addr + k * C::A_KSTEP, C::A_LBO);
-              const uint64_t bd = umma_desc(b_hi, b_addr + k * C::B_KSTEP, C::B_LBO);
-              umma_f16_2cta(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit_2cta_mask(&empty[stage], (uint16_t)0xF);                        // frees the slot in all four CTAs
-            if (kb == p.kb_total - 1) umma_commit_2cta_mask(&tfull[acc], (uint16_t)(0x3u << (2 * pr)));   // this pair's epilogues
-          }
-          __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
-      }
-    }
-  } else {
-    // ------------------------------ epilogue (warps 2..5 of both CTAs) ------------------------------
-    const int quarter = warp & 3;
-    const float alpha = p.ep.alpha_dev ? p.ep.alpha * __ldg(p.ep.alpha_dev) : p.ep.alpha;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int mt = t % p.MT;
-      const int rest = t / p.MT;
-      const int nt = rest % p.NT;
-      const int z = rest / p.NT;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const int i = mt * 512 + (int)pr * 256 + (int)rank * 128 + quarter * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAccCols;
-      const long long base = (long long)z * p.ep.sZ + (long long)i * p.ep.sI;
-      float dl[8];
-      long long cbase = 0;
-      bool any_corr = false;
-      if (p.ep.corr_src != nullptr) {
-        const int zA = ((z / p.am.z_div) % p.am.z_mod) * p.am.z_mul;
-        const int zB = ((z / p.bm.z_div) % p.bm.z_mod) * p.bm.z_mul;
-        cbase = (long long)zB * p.ep.cZ + (long long)i * p.ep.cI;
-#pragma unroll
-        for (int sgi = 0; sgi < 8; ++sgi) {
-          dl[sgi] = (sgi < p.ep.corr_nseg && i < p.ep.m_valid)
-                        ? __ldg(p.ep.corr_delta + ((long long)zA * p.ep.corr_nseg + sgi) * p.ep.m_valid + i) : 0.f;
-          any_corr |= (dl[sgi] != 0.f);
-        }
-      }
-      for (int j = 0; j < 8; ++j) {
-        uint32_t regs[32];
-        tmem_ld_32x32(t_row + (uint32_t)j * 32, regs);
-        tmem_ld_wait();
-        const int r = nt * 8 + j;
-        if (i < p.ep.m_valid && r < p.ep.r_valid) {
-          if (any_corr) {
-#pragma unroll
-            for (int sgi = 0; sgi < 8; ++sgi) {
-              if (sgi < p.ep.corr_nseg && dl[sgi] != 0.f) {
-                const uint4* src = reinterpret_cast<const uint4*>(p.ep.corr_src + cbase + (long long)sgi * p.ep.cSeg + (long long)r * p.ep.cR);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const uint4 v = __ldg(src + q);
-                  const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(h2[e]);
-                    regs[8 * q + 2 * e] = __float_as_uint(fmaf(dl[sgi], f.x, __uint_as_float(regs[8 * q + 2 * e])));
-                    regs[8 * q + 2 * e + 1] = __float_as_uint(fmaf(dl[sgi], f.y, __uint_as_float(regs[8 * q + 2 * e + 1])));
-                  }
-                }
-              }
-            }
-          }
-          store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tempty[acc], crank & ~1u);    // tell this pair's MMA warp the accumulator is drained
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();               // nobody leaves (or frees TMEM) while the peer may still touch this CTA
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_2cta(tmem_base, kTmemCols);
-  }
-}
 #endif  // __CUDACC__
 
 // Launch one contraction (implemented in tc_engine.cu).  ak/bk select the instantiation.
@@ -790,9 +570,6 @@ int launch_contract(int ak, int bk, GemmParams& p, cudaStream_t stream);
 // 2-CTA (256 x 256 pair tile) launch for A_MN128 / A_K128 with R = 8; p.MT must count 256-row tiles and the B tensor
 // map must have box_r = 4 (chunk mode).
 int launch_contract_2cta(int ak, GemmParams& p, cudaStream_t stream);
-// 4-CTA cluster (512 x 256) launch: p.MT counts 512-row tiles, chunk-mode B maps need box_r = 2.
-int launch_contract_4cta(int ak, GemmParams& p, cudaStream_t stream);
-bool use_4cta(int n_rows);
 bool use_2cta(int n_rows);
 
 }  // namespace tc
