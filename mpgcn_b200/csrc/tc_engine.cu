@@ -200,7 +200,16 @@ static int launch2_impl(GemmParams& p, cudaStream_t stream) {
   const size_t stage_bytes = 32768;
   int stages = (int)((kMaxSmem - 1024 - 512) / stage_bytes);
   if (stages > 8) stages = 8;
+  static int knob_stages = -1, knob_order = -1;
+  if (knob_stages < 0) {
+    const char* e = getenv("MPGCN_B200_STAGES");
+    knob_stages = e ? atoi(e) : 0;
+    const char* o = getenv("MPGCN_B200_TILE_ORDER");
+    knob_order = o ? atoi(o) : 0;
+  }
+  if (knob_stages >= 2 && knob_stages < stages) stages = knob_stages;
   p.stages = stages;
+  p.nt_fastest = knob_order;
   const long long tiles = (long long)p.MT * p.NT * p.Z;
   MPGCN_CHECK(tiles > 0 && tiles < (1ll << 31), "bad tile count %lld", tiles);
   MPGCN_CHECK(p.kb_total > 0 && p.kb_per_seg > 0, "empty contraction");

@@ -62,6 +62,7 @@ struct alignas(64) GemmParams {
   int kb_total, kb_per_seg;  // k-blocks over all segments / per segment
   int split_k, kb_per_slice; // split-K: z is a k-slice [z*kb_per_slice, ...)
   int stages;
+  int nt_fastest;            // tile order: 0 = m-tiles vary fastest (default), 1 = n-tiles vary fastest
   Epilogue ep;
 };
 
@@ -414,10 +415,9 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
-        const int mt = t % p.MT;
-        const int rest = t / p.MT;
-        const int nt = rest % p.NT;
-        const int z = rest / p.NT;
+        int mt, nt, z;
+        if (p.nt_fastest) { nt = t % p.NT; const int rest = t / p.NT; mt = rest % p.MT; z = rest / p.MT; }
+        else { mt = t % p.MT; const int rest = t / p.MT; nt = rest % p.NT; z = rest / p.NT; }
         const int m0 = mt * 256 + (int)rank * 128;
         const int zA0 = ((z / p.am.z_div) % p.am.z_mod) * p.am.z_mul;
         const int zB0 = ((z / p.bm.z_div) % p.bm.z_mod) * p.bm.z_mul;
@@ -496,10 +496,9 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int mt = t % p.MT;
-      const int rest = t / p.MT;
-      const int nt = rest % p.NT;
-      const int z = rest / p.NT;
+      int mt, nt, z;
+      if (p.nt_fastest) { nt = t % p.NT; const int rest = t / p.NT; mt = rest % p.MT; z = rest / p.MT; }
+      else { mt = t % p.MT; const int rest = t / p.MT; nt = rest % p.NT; z = rest / p.NT; }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int i = mt * 256 + (int)rank * 128 + quarter * 32 + lane;
