@@ -85,6 +85,16 @@ MPGCN_API int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, co
                              const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
                              size_t workspace_bytes, int B, int T, long long NN, int C, int precision, void* stream);
 
+/* Support-matrix builder = Adj_Processor(kernel_type, K).process(flow) (reference GCN.py:56-138), batched on the device:
+ *   flow [B,N,N] -> supports [B,Ks,N,N], Ks = mpgcn_adj_num_supports(kernel_type, K)
+ *   kernel_type: 0 localpool (K ignored, Ks = 1), 1 chebyshev (Ks = K+1; lambda_max = 2, the branch the reference always
+ *   takes on torch >= 2), 2 random_walk_diffusion (Ks = K+1), 3 dual_random_walk_diffusion (Ks = 2K+1); anything else is an
+ *   error with the reference's message. */
+MPGCN_API int mpgcn_adj_num_supports(int kernel_type, int K);
+MPGCN_API size_t mpgcn_adj_workspace_bytes(int B, int N, int kernel_type, int K);
+MPGCN_API int mpgcn_adj_process(const float* flow, float* supports, int B, int N, int kernel_type, int K, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* FC head + multi-perspective fusion (reference MPGCN.py:74-76,107,110,112), one pass:
  *     y[cell] = (1/M) * sum_m relu( g_m[cell,:] . w[m,:] + bias[m] )      (Linear(C -> 1) + ReLU per branch, mean over the M branches)
  *   g    HOST array of M device pointers, each [cells, C] (cells = B*N*N);  w [M,C], bias [M];  y [cells]

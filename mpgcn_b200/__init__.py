@@ -6,5 +6,6 @@ Layout:  csrc/  CUDA kernels + C ABI (libmpgcn_b200.so; header in include/mpgcn_
 """
 from . import _lib, ops            # noqa: F401
 from .MPGCN import BDGCN, MPGCN    # noqa: F401
+from .GCN import Adj_Processor   # noqa: F401
 
-__all__ = ["BDGCN", "MPGCN", "ops"]
+__all__ = ["BDGCN", "MPGCN", "Adj_Processor", "ops"]

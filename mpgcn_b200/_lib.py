@@ -31,6 +31,9 @@ _SIGS = {
                             + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     "mpgcn_bdgcn_backward": (ctypes.c_int, [_c_f, _c_f, _c_f, _c_f, ctypes.c_int, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, _c_f,
                                             ctypes.c_size_t] + [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    "mpgcn_adj_num_supports": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "mpgcn_adj_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 4),
+    "mpgcn_adj_process": (ctypes.c_int, [_c_f, _c_f, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_f, ctypes.c_size_t, ctypes.c_void_p]),
     "mpgcn_head_forward": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), _c_f, _c_f, _c_f, _c_f, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p]),
     "mpgcn_head_backward": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), _c_f, _c_f, _c_f, ctypes.POINTER(ctypes.c_void_p), _c_f, _c_f,

@@ -77,6 +77,14 @@ int mpgcn_bdgcn_backward(const float* d_out, const float* out, const float* G_o,
   return bdgcn_backward_simt(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, st);
 }
 
+int mpgcn_adj_num_supports(int kernel_type, int K) { return adj_num_supports(kernel_type, K); }
+size_t mpgcn_adj_workspace_bytes(int B, int N, int kernel_type, int K) { return adj_workspace_bytes(B, N, kernel_type, K); }
+int mpgcn_adj_process(const float* flow, float* supports, int B, int N, int kernel_type, int K, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  MPGCN_CHECK(flow && supports, "mpgcn_adj_process: null pointer argument");
+  return adj_process(flow, supports, B, N, kernel_type, K, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int mpgcn_head_forward(const float* const* g, const float* w, const float* bias, float* y, float* pre, long long cells, int C, int M,
                        void* stream) {
   MPGCN_CHECK(g && w && bias && y && cells >= 1, "mpgcn_head_forward: null pointer or empty input");

@@ -29,6 +29,9 @@ struct SgemmParams {
   const float* bias;
   int bias_mod;
   int relu;
+  const float* Cin;            // optional: D = alpha*A*B + beta*Cin (Cin indexed like D); ksplit must be 1
+  float beta;
+  long long c_sz[3];
 };
 int simt_sgemm(const SgemmParams& p, cudaStream_t stream);
 
@@ -63,6 +66,12 @@ int head_forward(const float* const* g, const float* w, const float* bias, float
                  cudaStream_t st);
 int head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
                   long long cells, int C, int M, cudaStream_t st);
+
+// support-matrix builder (adj_kernels.cu): reference GCN.Adj_Processor.process
+enum AdjKernel { ADJ_LOCALPOOL = 0, ADJ_CHEBYSHEV = 1, ADJ_RANDOM_WALK = 2, ADJ_DUAL_RANDOM_WALK = 3 };
+int adj_num_supports(int kernel_type, int K);
+size_t adj_workspace_bytes(int B, int N, int kernel_type, int K);
+int adj_process(const float* flow, float* supports, int B, int N, int kernel_type, int K, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // tcgen05 LSTM (lstm_tc.cu): hidden size 32 only
 bool lstm_tc_supported(int T, int C);

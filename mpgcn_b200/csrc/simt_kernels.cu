@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p, int til
   const float* A = p.A + z0 * p.a_sz[0] + z1 * p.a_sz[1] + z2 * p.a_sz[2];
   const float* B = p.B + z0 * p.b_sz[0] + z1 * p.b_sz[1] + z2 * p.b_sz[2];
   float* D = p.D + z0 * p.d_sz[0] + z1 * p.d_sz[1] + z2 * p.d_sz[2];
+  const float* Cin = p.Cin ? p.Cin + z0 * p.c_sz[0] + z1 * p.c_sz[1] + z2 * p.c_sz[2] : nullptr;
 
   const int tid = threadIdx.x;
   const int ty = tid / 16, tx = tid % 16;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p, int til
       if (p.ksplit > 1) {
         atomicAdd(dst, v);
       } else {
+        if (Cin) v = fmaf(p.beta, Cin[gi * p.d_si + gj], v);
         if (p.bias) v += p.bias[gj % p.bias_mod];
         if (p.relu) v = fmaxf(v, 0.f);
         *dst = v;
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p, int til
 
 int simt_sgemm(const SgemmParams& p, cudaStream_t stream) {
   MPGCN_CHECK(p.M > 0 && p.N > 0 && p.K > 0 && p.nseg > 0 && p.ksplit > 0, "simt_sgemm: empty problem");
+  MPGCN_CHECK(p.Cin == nullptr || p.ksplit == 1, "simt_sgemm: Cin needs ksplit == 1");
   const int bn = (p.N <= 32) ? 32 : 64;
   const int tiles_m = (p.M + 63) / 64;
   const int tiles_n = (p.N + bn - 1) / bn;

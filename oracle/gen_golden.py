@@ -164,6 +164,31 @@ def gen_model(ref_mpgcn, ref_gcn):
         print("wrote", name, "y", y.shape)
 
 
+ADJ_CASES = [
+    # name, kernel, K (order), N, B
+    ("adj_localpool_n9", "localpool", 1, 9, 2),
+    ("adj_cheb_k2_n16", "chebyshev", 2, 16, 2),
+    ("adj_cheb_k3_n33", "chebyshev", 3, 33, 1),
+    ("adj_rw_k1_n12", "random_walk_diffusion", 1, 12, 2),
+    ("adj_rw_k2_n47", "random_walk_diffusion", 2, 47, 2),
+    ("adj_rw_k4_n20", "random_walk_diffusion", 4, 20, 1),
+    ("adj_dual_k2_n21", "dual_random_walk_diffusion", 2, 21, 2),
+    ("adj_rw_k2_n10_zero_row", "random_walk_diffusion", 2, 10, 1),
+]
+
+
+def gen_adj(ref_gcn):
+    for idx, (name, kind, K, N, B) in enumerate(ADJ_CASES):
+        rng = np.random.default_rng(4000 + idx)
+        flow = rng.random((B, N, N)).astype(np.float32) * 5
+        if "zero_row" in name:
+            flow[0, 3, :] = 0        # zero out-degree: random_walk_normalize maps 1/0 -> 0 (GCN.py:105)
+        proc = ref_gcn.Adj_Processor(kind, K)
+        sup = _np(proc.process(torch.from_numpy(flow)))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), flow=flow, supports=sup, kernel_type=kind, K=K)
+        print("wrote", name, sup.shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -174,6 +199,7 @@ def main():
     gen_bdgcn(ref_mpgcn, ref_gcn)
     gen_lstm()
     gen_model(ref_mpgcn, ref_gcn)
+    gen_adj(ref_gcn)
 
 
 if __name__ == "__main__":

@@ -28,7 +28,7 @@ import numpy as np
 __all__ = [
     "bdgcn_forward", "bdgcn_backward", "lstm_last_forward", "lstm_last_backward",
     "fc_relu_forward", "fc_relu_backward", "mpgcn_forward", "mpgcn_forward_backward",
-    "bdgcn_forward_factored", "rel_errors",
+    "bdgcn_forward_factored", "rel_errors", "adj_process",
 ]
 
 
@@ -316,3 +316,60 @@ def mpgcn_forward_backward(params, x_seq, G_list, M, gcn_num_layers, d_y, act="r
         grads[pre + "temporal.weight_ih_l0"], grads[pre + "temporal.weight_hh_l0"] = dwi, dwh
         grads[pre + "temporal.bias_ih_l0"], grads[pre + "temporal.bias_hh_l0"] = dbi, dbh
     return y, grads
+
+
+# --------------------------------------------------------------------------------------
+# support-matrix builder   (reference: GCN.py:49-138 Adj_Processor)
+# --------------------------------------------------------------------------------------
+def _rw_normalize(A):
+    """D^-1 A with 1/0 -> 0 (GCN.py:103-108)."""
+    s = A.sum(axis=1)
+    with np.errstate(divide="ignore"):
+        dinv = np.where(s == 0, 0, 1.0 / s).astype(A.dtype)
+    return dinv[:, None] * A
+
+
+def _sym_normalize(A):
+    """D^-1/2 A D^-1/2, no zero-degree guard (GCN.py:111-114)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.power(A.sum(axis=1), -0.5).astype(A.dtype)
+    return (d[:, None] * A) * d[None, :]
+
+
+def _cheb_series(x, K):
+    """T_0 = I, T_1 = x, T_k = 2 x T_{k-1} - T_{k-2} for k = 0..K (GCN.py:128-138)."""
+    N = x.shape[0]
+    T = [np.eye(N, dtype=x.dtype)]
+    if K >= 1:
+        T.append(x)
+    for k in range(2, K + 1):
+        T.append(2 * (x @ T[k - 1]) - T[k - 2])
+    return T
+
+
+def adj_process(flow, kernel_type, K):
+    """Adj_Processor(kernel_type, K).process(flow): flow [B,N,N] -> supports [B,Ks,N,N] (GCN.py:56-100).
+    chebyshev uses lambda_max = 2 -- the branch the reference always takes on torch >= 2 (`torch.eig` was removed, the bare
+    `except` at GCN.py:122 catches the error)."""
+    flow = np.asarray(flow)
+    if kernel_type == "localpool":
+        K = 1
+    out = []
+    for A in flow:
+        N = A.shape[0]
+        eye = np.eye(N, dtype=A.dtype)
+        if kernel_type == "localpool":
+            ks = [eye + _sym_normalize(A)]                                   # GCN.py:69-72
+        elif kernel_type == "chebyshev":
+            L = eye - _sym_normalize(A)                                      # GCN.py:75
+            ks = _cheb_series((2 / 2) * L - eye, K)                          # GCN.py:76-77,125
+        elif kernel_type == "random_walk_diffusion":
+            ks = _cheb_series(_rw_normalize(A).T, K)                         # GCN.py:79-82
+        elif kernel_type == "dual_random_walk_diffusion":
+            f = _cheb_series(_rw_normalize(A).T, K)                          # GCN.py:84-91
+            bk = _cheb_series(_rw_normalize(A.T).T, K)
+            ks = f + bk[1:]
+        else:
+            raise ValueError("Invalid kernel_type. Must be one of [chebyshev, localpool, random_walk_diffusion, dual_random_walk_diffusion].")
+        out.append(np.stack(ks, axis=0))
+    return np.stack(out, axis=0)

@@ -128,6 +128,27 @@ def test_lstm_tensor_path_agrees_with_fp32_path(S, T, gmag, cuda_device):
         _check(a, r.cpu().numpy(), 1e-3 if n == "hT" else 2e-3, f"S={S} T={T} {n}")
 
 
+@pytest.mark.parametrize("name", golden_names("adj_"))
+def test_adj_processor_matches_reference_fixture(name, cuda_device):
+    """GPU support-matrix builder vs fixtures produced by the reference's Adj_Processor (fp32: summation-order noise only)."""
+    import GCN as gshim
+    g = load_golden(name)
+    proc = gshim.Adj_Processor(str(g["kernel_type"]), int(g["K"]))
+    sup = proc.process(torch.from_numpy(g["flow"]))                 # CPU tensor in, as the trainer passes it
+    assert sup.is_cuda and tuple(sup.shape) == g["supports"].shape
+    _check(sup, g["supports"], 2e-5, f"{name}/supports")
+    _check(proc.process(torch.from_numpy(g["flow"]).to(cuda_device)), g["supports"], 2e-5, f"{name}/supports (cuda in)")
+
+
+@pytest.mark.parametrize("kind,K,N,B", [("random_walk_diffusion", 2, 500, 3), ("chebyshev", 3, 257, 2), ("dual_random_walk_diffusion", 2, 130, 2)])
+def test_adj_processor_at_size_vs_oracle(kind, K, N, B, cuda_device):
+    import GCN as gshim
+    rng = np.random.default_rng(N)
+    flow = (rng.random((B, N, N)) * 5).astype(np.float32)
+    sup = gshim.Adj_Processor(kind, K).process(_t(flow, cuda_device))
+    _check(sup, orc.adj_process(flow.astype(np.float64), kind, K), 2e-5, f"adj {kind} N={N}")
+
+
 @pytest.mark.parametrize("M,C,cells", [(2, 32, 1000), (1, 8, 77), (3, 64, 4099)])
 def test_fused_head_matches_oracle(M, C, cells, cuda_device):
     """Linear(C->1)+ReLU per branch and branch mean in one kernel (reference MPGCN.py:74-76,107,110) vs the numpy oracle."""

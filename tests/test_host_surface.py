@@ -107,3 +107,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("test oracle", ""), f"{f} references the oracle"
+
+
+def test_adj_processor_surface_and_errors():
+    import GCN as gshim
+    p = gshim.Adj_Processor("localpool", 5)
+    assert (p.kernel_type, p.K) == ("localpool", 1)                 # reference GCN.py:53
+    assert gshim.Adj_Processor("random_walk_diffusion", 2).num_supports() == 3          # Model_Trainer.py:30
+    assert gshim.Adj_Processor("dual_random_walk_diffusion", 2).num_supports() == 5     # Model_Trainer.py:32
+    assert gshim.Adj_Processor("chebyshev", 3).num_supports() == 4
+    with pytest.raises(ValueError, match="Invalid kernel_type"):
+        gshim.Adj_Processor("bogus", 2).process(torch.zeros(1, 4, 4))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            gshim.Adj_Processor("localpool", 1).process(torch.ones(1, 4, 4))
+    # static helpers behave like the reference's on plain tensors
+    A = torch.tensor([[0., 2.], [0., 0.]])
+    P = gshim.Adj_Processor.random_walk_normalize(A)
+    assert torch.equal(P, torch.tensor([[0., 1.], [0., 0.]]))     # 1/0 -> 0 guard (reference GCN.py:105)

@@ -99,3 +99,12 @@ def test_torch_port_matches_reference_fixture(name):
     _check(out.detach().numpy(), g["out"], what="out")
     _check(X.grad.numpy(), g["dX"], what="dX")
     _check(W.grad.numpy(), g["dW"], what="dW")
+
+
+@pytest.mark.parametrize("name", golden_names("adj_"))
+def test_adj_process_matches_reference(name):
+    """Support-matrix builder (reference GCN.Adj_Processor.process) vs fixtures produced by the reference itself."""
+    g = load_golden(name)
+    sup = orc.adj_process(g["flow"], str(g["kernel_type"]), int(g["K"]))
+    assert sup.shape == g["supports"].shape
+    _check(sup, g["supports"], tol=2e-5, what="supports")
