@@ -293,8 +293,13 @@ def test_inference_mode_needs_no_stash_and_trainer_call_pattern(cuda_device):
                        num_nodes=N, user_bias=True, activation=nn.ReLU).to(cuda_device)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     crit = nn.MSELoss()
-    G = torch.rand(K, N, N, device=cuda_device) / N
-    dyn = (torch.rand(B, K, N, N, device=cuda_device) / N, torch.rand(B, K, N, N, device=cuda_device) / N)
+    # supports exactly as the trainer builds them (Model_Trainer.py:38-42,82-84,106): static graph once, dynamic O/D graphs per
+    # step from CPU tensors, through the drop-in GCN.Adj_Processor
+    import GCN as gshim
+    adj_pre = gshim.Adj_Processor("random_walk_diffusion", K - 1)
+    G = adj_pre.process(torch.rand(1, N, N)).squeeze(dim=0).to(cuda_device)
+    dyn = (adj_pre.process(torch.rand(B, N, N)).to(cuda_device), adj_pre.process(torch.rand(B, N, N)).to(cuda_device))
+    assert tuple(G.shape) == (K, N, N) and tuple(dyn[0].shape) == (B, K, N, N)
     x = torch.rand(B, T, N, N, 1, device=cuda_device) * 8
     y_true = torch.rand(B, 1, N, N, 1, device=cuda_device)
     losses = []
