@@ -325,3 +325,19 @@ def test_inference_mode_needs_no_stash_and_trainer_call_pattern(cuda_device):
     model2.load_state_dict(sd)
     with torch.no_grad():
         assert torch.equal(model2(x_seq=x, G_list=[G, dyn]), model(x_seq=x, G_list=[G, dyn]))
+
+
+def test_cuda_graph_rollout_equals_eager_loop(cuda_device):
+    """Model_Trainer.test's autoregressive loop (Model_Trainer.py:157-165): CUDA-graph replay vs the eager loop, N = 47."""
+    from mpgcn_b200 import rollout
+    torch.manual_seed(3)
+    N, K, B, T, P = 47, 3, 2, 7, 5
+    model = shim.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=32, lstm_num_layers=1, gcn_hidden_dim=32, gcn_num_layers=3,
+                       num_nodes=N, user_bias=True, activation=nn.ReLU).to(cuda_device)
+    G = torch.rand(K, N, N, device=cuda_device) / N
+    dyn = (torch.rand(B, K, N, N, device=cuda_device) / N, torch.rand(B, K, N, N, device=cuda_device) / N)
+    x = torch.rand(B, T, N, N, 1, device=cuda_device) * 8
+    eager = rollout.forecast(model, x, [G, dyn], P, use_cuda_graph=False)
+    graphed = rollout.forecast(model, x, [G, dyn], P, use_cuda_graph=True)
+    assert tuple(graphed.shape) == (B, P, N, N, 1)
+    assert torch.equal(eager, graphed)
