@@ -68,6 +68,13 @@ MPGCN_API int mpgcn_bdgcn_backward(const float* d_out, const float* out, const f
                          const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
                          int K, int C, int H, int precision, void* stream);
 
+/* Same, with the gradient-magnitude hand-over used by the fp16 path: d_out_absmax (nullable) = device scalar already holding
+ * max|d_out| (as written by the call that produced d_out; skips one pass over d_out); dX_absmax (nullable) receives max|dX|
+ * (0 when unknown).  Pure optimisation: results are identical with or without the hints. */
+MPGCN_API int mpgcn_bdgcn_backward_ex(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
+                            const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
+                            int K, int C, int H, int precision, const float* d_out_absmax, float* dX_absmax, void* stream);
+
 /* nn.LSTM(input_size=1, hidden=C, layers=1, batch_first) over the B*NN OD cells with zero initial
  * state, returning only the last hidden state (reference MPGCN.py:69,80-87,100-104).
  *   x_seq [B,T,NN] (= the model input [B,T,N,N,1] unchanged, NN = N*N)
@@ -95,15 +102,21 @@ MPGCN_API size_t mpgcn_adj_workspace_bytes(int B, int N, int kernel_type, int K)
 MPGCN_API int mpgcn_adj_process(const float* flow, float* supports, int B, int N, int kernel_type, int K, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+MPGCN_API int mpgcn_lstm_last_backward_ex(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
+                                size_t workspace_bytes, int B, int T, long long NN, int C, int precision, const float* d_hT_absmax,
+                                void* stream);
+
 /* FC head + multi-perspective fusion (reference MPGCN.py:74-76,107,110,112), one pass:
  *     y[cell] = (1/M) * sum_m relu( g_m[cell,:] . w[m,:] + bias[m] )      (Linear(C -> 1) + ReLU per branch, mean over the M branches)
  *   g    HOST array of M device pointers, each [cells, C] (cells = B*N*N);  w [M,C], bias [M];  y [cells]
  *   pre  [M,cells] pre-activations kept for backward, or NULL (inference)
- * backward: dy [cells]; dg HOST array of M device pointers [cells, C] (or NULL / NULL entries), dw [M,C], db [M]. */
+ * backward: dy [cells]; dg HOST array of M device pointers [cells, C] (or NULL / NULL entries), dw [M,C], db [M];
+ * dg_absmax [M] (nullable) receives max|dg_m| per branch (see mpgcn_bdgcn_backward_ex). */
 MPGCN_API int mpgcn_head_forward(const float* const* g, const float* w, const float* bias, float* y, float* pre, long long cells, int C, int M,
                        void* stream);
 MPGCN_API int mpgcn_head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
-                        long long cells, int C, int M, void* stream);
+                        float* dg_absmax, long long cells, int C, int M, void* stream);
 
 /* Launch accounting (bench.py evidence).  Every launch of a kernel of this library is counted per tag
  * (0 FWD_A, 1 FWD_MIX, 2 FWD_B, 3 BWD_V, 4 BWD_DW, 5 BWD_MIX, 6 BWD_DX: tcgen05 contractions; 7 fp32 SIMT GEMM;

@@ -66,14 +66,27 @@ int mpgcn_bdgcn_forward(const float* X, const float* G_o, const float* G_d, int 
   return bdgcn_forward_simt(s, X, G_o, G_d, W, bias, out, saved, workspace, workspace_bytes, st);
 }
 
+int mpgcn_bdgcn_backward_ex(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
+                            const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
+                            int K, int C, int H, int precision, const float* d_out_absmax, float* dX_absmax, void* stream);
+
 int mpgcn_bdgcn_backward(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
                          const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
                          int K, int C, int H, int precision, void* stream) {
+  return mpgcn_bdgcn_backward_ex(d_out, out, G_o, G_d, dynamic, W, act, saved, dX, dW, db, workspace, workspace_bytes, B, N, K, C, H,
+                                 precision, nullptr, nullptr, stream);
+}
+
+int mpgcn_bdgcn_backward_ex(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
+                            const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
+                            int K, int C, int H, int precision, const float* d_out_absmax, float* dX_absmax, void* stream) {
   const BdgcnShape s = mk(B, N, K, C, H, dynamic ? 1 : 0, act);
   if (int e = check_shape(s, precision)) return e;
   MPGCN_CHECK(d_out && out && G_o && G_d && W && saved && dW && workspace, "mpgcn_bdgcn_backward: null pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (precision == PREC_FP16_TC) return bdgcn_backward_tc(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, st);
+  if (precision == PREC_FP16_TC)
+    return bdgcn_backward_tc(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, d_out_absmax, dX_absmax, st);
+  if (dX_absmax) MPGCN_CUDA(cudaMemsetAsync(dX_absmax, 0, sizeof(float), st));   // fp32 path: no hint produced (0 = "unknown")
   return bdgcn_backward_simt(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, st);
 }
 
@@ -92,9 +105,9 @@ int mpgcn_head_forward(const float* const* g, const float* w, const float* bias,
 }
 
 int mpgcn_head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
-                        long long cells, int C, int M, void* stream) {
+                        float* dg_absmax, long long cells, int C, int M, void* stream) {
   MPGCN_CHECK(g && w && pre && dy && dw && db && cells >= 1, "mpgcn_head_backward: null pointer or empty input");
-  return head_backward(g, w, pre, dy, dg, dw, db, cells, C, M, static_cast<cudaStream_t>(stream));
+  return head_backward(g, w, pre, dy, dg, dw, db, dg_absmax, cells, C, M, static_cast<cudaStream_t>(stream));
 }
 
 void mpgcn_profile_enable(int on) { prof_enable(on); }
@@ -130,9 +143,22 @@ int mpgcn_lstm_last_forward(const float* x_seq, const float* w_ih, const float* 
   return lstm_last_forward(x_seq, w_ih, w_hh, b_ih, b_hh, hT, B, T, NN, C, st);
 }
 
+int mpgcn_lstm_last_backward_ex(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
+                                size_t workspace_bytes, int B, int T, long long NN, int C, int precision, const float* d_hT_absmax,
+                                void* stream);
+
 int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                              const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
                              size_t workspace_bytes, int B, int T, long long NN, int C, int precision, void* stream) {
+  return mpgcn_lstm_last_backward_ex(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, workspace, workspace_bytes,
+                                     B, T, NN, C, precision, nullptr, stream);
+}
+
+int mpgcn_lstm_last_backward_ex(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
+                                size_t workspace_bytes, int B, int T, long long NN, int C, int precision, const float* d_hT_absmax,
+                                void* stream) {
   MPGCN_CHECK(x_seq && w_ih && w_hh && b_ih && b_hh && d_hT && d_w_ih && d_w_hh && d_b_ih && d_b_hh,
               "mpgcn_lstm_last_backward: null pointer argument");
   MPGCN_CHECK(B >= 1 && T >= 1 && NN >= 1, "mpgcn_lstm_last_backward: empty input");
@@ -140,7 +166,7 @@ int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (precision == PREC_FP16_TC)
     return lstm_last_backward_tc(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, B, T, NN, workspace,
-                                 workspace_bytes, st);
+                                 workspace_bytes, d_hT_absmax, st);
   return lstm_last_backward(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, B, T, NN, C, st);
 }
 

@@ -311,7 +311,8 @@ static int run_bwd_dw(const BdgcnShape& s, const __half* z16, const __half* v16,
 }
 
 // BWD_DX: dX[b][n][c][l] = sum_{d,e} G_d[c][e] Y16[b][d][n][e][l]
-static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16, float* dX, const float* inv_scale, cudaStream_t st) {
+static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16, float* dX, const float* inv_scale, float* dx_absmax,
+                      cudaStream_t st) {
   const int N = s.N, K = s.K, Np = pad8(N);
   GemmParams p;
   init_params(p);
@@ -321,7 +322,7 @@ static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16
   p.bm = omap(1, kBig, K, 1, 0);                                    // plane = b*K + d
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;
   p.kb_per_seg = ceil_div(N, 64); p.kb_total = K * p.kb_per_seg;
-  p.ep.out = dX; p.ep.out_f16 = 0; p.ep.alpha_dev = inv_scale;
+  p.ep.out = dX; p.ep.out_f16 = 0; p.ep.alpha_dev = inv_scale; p.ep.absmax_out = dx_absmax;
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
   prof_set_next(PROF_BWD_DX, 2.0 * s.B * K * (double)N * N * N * 32);
@@ -381,7 +382,8 @@ int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const
 }
 
 int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out, const float* Go, const float* Gd, const float* W,
-                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, const float* d_out_absmax,
+                      float* dx_absmax, cudaStream_t st) {
   MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d K=%d)", s.C, s.H, s.K);
   MPGCN_CHECK(saved != nullptr, "bdgcn_backward: forward was run without a `saved` buffer");
   const size_t NN = n2(s);
@@ -401,7 +403,7 @@ int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out,
 
   const __half* go_used = nullptr;
   if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 32, st));
-  if (int e = grad_scale_prepare(d_out, (size_t)s.B * NN * 32, scale2, st)) return e;
+  if (int e = grad_scale_prepare(d_out, (size_t)s.B * NN * 32, scale2, d_out_absmax, st)) return e;
   if (int e = relu_bwd_prep(d_out, out, s.act, dp16, nullptr, db, (size_t)s.B * NN * 32, 32, scale2, st)) return e;
   if (int e = convert_supports(s, Go, Gd, go16, gd16, &go_used, st)) return e;
   if (int e = run_bwd_v(s, go_used, dp16, v16, st)) return e;
@@ -409,9 +411,10 @@ int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out,
   if (int e = run_bwd_dw(s, z16, v16, partials, &slices, &mt, st)) return e;
   if (int e = reduce_dw_partials(partials, dW, slices, mt, s.K, scale2 + 1, st)) return e;
   if (dX) {
+    if (dx_absmax) MPGCN_CUDA(cudaMemsetAsync(dx_absmax, 0, sizeof(float), st));
     if (int e = permute_w_bwd(W, wq16, nullptr, s.K, 32, 32, st)) return e;
     if (int e = run_mix(s, v16, wq16, 1, y16, PROF_BWD_MIX, st)) return e;
-    if (int e = run_bwd_dx(s, gd16, y16, dX, scale2 + 1, st)) return e;
+    if (int e = run_bwd_dx(s, gd16, y16, dX, scale2 + 1, dx_absmax, st)) return e;
   }
   return 0;
 }

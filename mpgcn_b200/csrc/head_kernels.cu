@@ -40,7 +40,8 @@ __global__ void head_fwd_kernel(HeadPtrs p, const float* __restrict__ w /*[M][C]
 
 // d g_m[cell,:] = dy[cell]/M * [pre_m > 0] * w_m ;  dw_m += sum_cell d_pre * g_m[cell,:] ;  db_m += sum_cell d_pre
 __global__ void head_bwd_kernel(HeadPtrs p, const float* __restrict__ w, const float* __restrict__ pre, const float* __restrict__ dy,
-                                float* __restrict__ dw /*[M][C]*/, float* __restrict__ db /*[M]*/, long long cells, int C, int M) {
+                                float* __restrict__ dw /*[M][C]*/, float* __restrict__ db /*[M]*/, float* __restrict__ dg_absmax /*[M] or null*/,
+                                long long cells, int C, int M) {
   extern __shared__ float s_acc[];     // [M][C + 1] block-level accumulators
   for (int i = threadIdx.x; i < M * (C + 1); i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
@@ -50,6 +51,7 @@ __global__ void head_bwd_kernel(HeadPtrs p, const float* __restrict__ w, const f
   // per-thread partial sums for the (few) weight elements this thread touches: C/8 per branch, kept in registers for C = 32
   for (int m = 0; m < M; ++m) {
     float wacc[4] = {0.f, 0.f, 0.f, 0.f}, bacc = 0.f;     // C <= 32 fast path; larger C falls through to smem atomics below
+    float amax = 0.f;
     for (long long cell = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); cell < cells; cell += stride) {
       const float d = (pre[(long long)m * cells + cell] > 0.f) ? dy[cell] * inv_m : 0.f;
       const float* g = p.g[m] + cell * C;
@@ -57,7 +59,11 @@ __global__ void head_bwd_kernel(HeadPtrs p, const float* __restrict__ w, const f
       for (int l = sub * 4; l < C; l += 32) {
         const float4 v = *reinterpret_cast<const float4*>(g + l);
         const float4 ww = *reinterpret_cast<const float4*>(w + m * C + l);
-        if (dg) *reinterpret_cast<float4*>(dg + l) = make_float4(d * ww.x, d * ww.y, d * ww.z, d * ww.w);
+        if (dg) {
+          const float4 o = make_float4(d * ww.x, d * ww.y, d * ww.z, d * ww.w);
+          *reinterpret_cast<float4*>(dg + l) = o;
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+        }
         if (l < 32) {
           wacc[0] += d * v.x; wacc[1] += d * v.y; wacc[2] += d * v.z; wacc[3] += d * v.w;
         } else {
@@ -72,6 +78,10 @@ __global__ void head_bwd_kernel(HeadPtrs p, const float* __restrict__ w, const f
       for (int e = 0; e < 4; ++e) atomicAdd(&s_acc[m * (C + 1) + sub * 4 + e], wacc[e]);
     }
     if (sub == 0) atomicAdd(&s_acc[m * (C + 1) + C], bacc);
+    if (dg_absmax) {
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(dg_absmax + m), __float_as_uint(amax));
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < M * (C + 1); i += blockDim.x) {
@@ -103,7 +113,7 @@ int head_forward(const float* const* g, const float* w, const float* bias, float
 }
 
 int head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
-                  long long cells, int C, int M, cudaStream_t st) {
+                  float* dg_absmax, long long cells, int C, int M, cudaStream_t st) {
   MPGCN_CHECK(M >= 1 && M <= kMaxBranches, "head: %d branches unsupported (1..%d)", M, kMaxBranches);
   MPGCN_CHECK(C >= 4 && C % 4 == 0, "head: C=%d must be a multiple of 4", C);
   HeadPtrs p{};
@@ -113,8 +123,9 @@ int head_backward(const float* const* g, const float* w, const float* pre, const
   }
   MPGCN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * M * C, st));
   MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * M, st));
+  if (dg_absmax) MPGCN_CUDA(cudaMemsetAsync(dg_absmax, 0, sizeof(float) * M, st));
   prof_count(PROF_ELEMENTWISE);
-  head_bwd_kernel<<<head_grid(cells), 256, sizeof(float) * M * (C + 1), st>>>(p, w, pre, dy, dw, db, cells, C, M);
+  head_bwd_kernel<<<head_grid(cells), 256, sizeof(float) * M * (C + 1), st>>>(p, w, pre, dy, dw, db, dg_absmax, cells, C, M);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }

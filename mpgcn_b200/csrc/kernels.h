@@ -48,7 +48,8 @@ int relu_bwd_prep(const float* d_out, const float* out, int relu, __half* d_pre1
                   const float* scale, cudaStream_t s);
 // scale2[0] = S = 2^k with S*max|d_out| in [16,32), scale2[1] = 1/S (S = 1 for an all-zero or non-finite input).
 // fp16 has 5 exponent bits: realistic gradients (MSE mean over B*N*N cells ~ 1e-7) must be rescaled before the cast.
-int grad_scale_prepare(const float* d_out, size_t n, float* scale2, cudaStream_t s);
+// absmax_hint: optional device scalar already holding max|d_out| (produced by the epilogue that wrote d_out): skips the pass
+int grad_scale_prepare(const float* d_out, size_t n, float* scale2, const float* absmax_hint, cudaStream_t s);
 // W[o][d][l][h] fp32 -> Wq[d][o][h][l] (fp16 and/or fp32)
 int permute_w_bwd(const float* W, __half* wq16, float* wq32, int K, int C, int H, cudaStream_t s);
 // dW[o][d][l][h] = sum_slices P[slice][mt][(d%4)*32 + l][o][h]   (C = H = 32)
@@ -65,7 +66,7 @@ int lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh,
 int head_forward(const float* const* g, const float* w, const float* bias, float* y, float* pre, long long cells, int C, int M,
                  cudaStream_t st);
 int head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
-                  long long cells, int C, int M, cudaStream_t st);
+                  float* dg_absmax /*[M] or null*/, long long cells, int C, int M, cudaStream_t st);
 
 // support-matrix builder (adj_kernels.cu): reference GCN.Adj_Processor.process
 enum AdjKernel { ADJ_LOCALPOOL = 0, ADJ_CHEBYSHEV = 1, ADJ_RANDOM_WALK = 2, ADJ_DUAL_RANDOM_WALK = 3 };
@@ -80,7 +81,7 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
                          int B, int T, long long NN, cudaStream_t s);
 int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                           const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
-                          long long NN, void* ws, size_t ws_bytes, cudaStream_t s);
+                          long long NN, void* ws, size_t ws_bytes, const float* d_hT_absmax, cudaStream_t s);
 
 // ---- BDGCN layer orchestration ---------------------------------------------------------------
 struct BdgcnShape {
@@ -102,6 +103,7 @@ int bdgcn_backward_simt(const BdgcnShape& s, const float* d_out, const float* ou
 int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const float* Gd, const float* W, const float* bias,
                      float* out, void* saved, void* ws, size_t ws_bytes, cudaStream_t st);
 int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out, const float* Go, const float* Gd, const float* W,
-                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
+                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, const float* d_out_absmax,
+                      float* dx_absmax, cudaStream_t st);
 
 }  // namespace mpgcn

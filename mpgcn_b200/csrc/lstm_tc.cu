@@ -697,7 +697,7 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
 
 int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                           const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
-                          long long NN, void* ws, size_t ws_bytes, cudaStream_t st) {
+                          long long NN, void* ws, size_t ws_bytes, const float* d_hT_absmax, cudaStream_t st) {
   using namespace lstm_tc;
   const long long cells = (long long)B * NN;
   MPGCN_CHECK(ws != nullptr && ws_bytes >= lstm_tc_bwd_workspace_bytes(B, T, NN), "lstm backward: workspace too small (%zu < %zu)",
@@ -705,7 +705,7 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "lstm backward: workspace must be 256-byte aligned");
   float* scale2 = static_cast<float*>(ws);
   __half* scratch = reinterpret_cast<__half*>(static_cast<uint8_t*>(ws) + 1024);
-  if (int e = grad_scale_prepare(d_hT, (size_t)cells * C, scale2, st)) return e;
+  if (int e = grad_scale_prepare(d_hT, (size_t)cells * C, scale2, d_hT_absmax, st)) return e;
   MPGCN_CUDA(cudaMemsetAsync(d_w_ih, 0, sizeof(float) * G4, st));
   MPGCN_CUDA(cudaMemsetAsync(d_w_hh, 0, sizeof(float) * G4 * C, st));
   MPGCN_CUDA(cudaMemsetAsync(d_b_ih, 0, sizeof(float) * G4, st));

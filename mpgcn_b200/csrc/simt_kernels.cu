@@ -266,8 +266,8 @@ __global__ void absmax_kernel(const float* __restrict__ x, size_t n, unsigned in
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, __float_as_uint(m));
 }
-__global__ void make_scale_kernel(float* scale2) {
-  const float amax = __uint_as_float(*reinterpret_cast<unsigned int*>(scale2));
+__global__ void make_scale_kernel(float* scale2, const float* hint) {
+  const float amax = hint ? *hint : __uint_as_float(*reinterpret_cast<unsigned int*>(scale2));
   float S = 1.f;
   if (amax > 0.f && amax < 3.0e38f) {
     int e;
@@ -280,12 +280,14 @@ __global__ void make_scale_kernel(float* scale2) {
   scale2[1] = 1.f / S;
 }
 
-int grad_scale_prepare(const float* d_out, size_t n, float* scale2, cudaStream_t s) {
-  MPGCN_CUDA(cudaMemsetAsync(scale2, 0, 2 * sizeof(float), s));
+int grad_scale_prepare(const float* d_out, size_t n, float* scale2, const float* absmax_hint, cudaStream_t s) {
+  if (absmax_hint == nullptr) {
+    MPGCN_CUDA(cudaMemsetAsync(scale2, 0, 2 * sizeof(float), s));
+    prof_count(PROF_ELEMENTWISE);
+    absmax_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_out, n, reinterpret_cast<unsigned int*>(scale2));
+  }
   prof_count(PROF_ELEMENTWISE);
-  absmax_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_out, n, reinterpret_cast<unsigned int*>(scale2));
-  prof_count(PROF_ELEMENTWISE);
-  make_scale_kernel<<<1, 1, 0, s>>>(scale2);
+  make_scale_kernel<<<1, 1, 0, s>>>(scale2, absmax_hint);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }

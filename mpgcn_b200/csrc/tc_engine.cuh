@@ -44,6 +44,7 @@ struct Epilogue {
   const float* bias;         // [32] or null
   float alpha;
   const float* alpha_dev;    // optional device scalar multiplied into alpha (gradient un-scaling), may be null
+  float* absmax_out;         // optional device scalar (pre-zeroed): receives max |stored value| (bit pattern, atomicMax)
   // optional diagonal correction (forward only): out[z][i][r][:] += sum_seg delta[(zA*corr_nseg + seg)*m_valid + i] *
   // corr_src[zB*cZ + seg*cSeg + i*cI + r*cR + :], the exact remainder of the support diagonal lost by its fp16 rounding
   const __half* corr_src;
@@ -92,7 +93,8 @@ __host__ __device__ inline size_t smem_bytes(int a_stage, int R, int BK, int sta
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void store_chunk(const Epilogue& ep, float alpha, const float* sbias, long long off, uint32_t (&acc)[32]) {
+__device__ __forceinline__ void store_chunk(const Epilogue& ep, float alpha, const float* sbias, long long off, uint32_t (&acc)[32],
+                                            float& amax) {
   float v[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
@@ -100,6 +102,10 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, float alpha, con
     if (ep.bias) x += sbias[c];
     if (ep.relu) x = fmaxf(x, 0.f);
     v[c] = x;
+  }
+  if (ep.absmax_out) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) amax = fmaxf(amax, fabsf(v[c]));
   }
   if (ep.out_f16) {
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out) + off);
@@ -279,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int quarter = warp & 3;     // TMEM lane quarter this warp may access
     const float alpha = p.ep.alpha_dev ? p.ep.alpha * __ldg(p.ep.alpha_dev) : p.ep.alpha;
+    float amax = 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
               }
             }
           }
-          store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs);
+          store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs, amax);
         }
       }
       tc_fence_before();
@@ -338,6 +345,10 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
       if (lane == 0) mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if (p.ep.absmax_out) {
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(p.ep.absmax_out), __float_as_uint(amax));
     }
   }
 
@@ -493,6 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
     // ------------------------------ epilogue (warps 2..5 of both CTAs) ------------------------------
     const int quarter = warp & 3;
     const float alpha = p.ep.alpha_dev ? p.ep.alpha * __ldg(p.ep.alpha_dev) : p.ep.alpha;
+    float amax = 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
@@ -543,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
               }
             }
           }
-          store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs);
+          store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs, amax);
         }
       }
       tc_fence_before();
@@ -551,6 +563,10 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
       if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);    // tell the leader's MMA warp this accumulator is drained
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if (p.ep.absmax_out) {
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(p.ep.absmax_out), __float_as_uint(amax));
     }
   }
 

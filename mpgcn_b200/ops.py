@@ -56,6 +56,27 @@ def _scratch(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+# Gradient-magnitude hand-over between consecutive backward calls of the fp16 path: the kernel that writes a gradient tensor also
+# records max|grad| in a device scalar; the next backward that receives exactly that tensor (same storage, same version) reuses
+# it for its power-of-two scaling instead of re-reading the tensor.  Purely an optimisation -- a missed hint costs one extra pass.
+_ABSMAX_HINTS = {}
+
+
+def _put_hint(t, absmax_scalar):
+    if t is None:
+        return
+    if len(_ABSMAX_HINTS) > 16:
+        _ABSMAX_HINTS.clear()
+    _ABSMAX_HINTS[(t.device.index, t.data_ptr())] = (t._version, t.numel(), absmax_scalar)
+
+
+def _take_hint(t):
+    e = _ABSMAX_HINTS.pop((t.device.index, t.data_ptr()), None)
+    if e is not None and e[0] == t._version and e[1] == t.numel():
+        return e[2]
+    return None
+
+
 class _BDGCNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, G_o, G_d, W, b, dynamic: bool, act: int, precision):
@@ -89,15 +110,20 @@ class _BDGCNFn(torch.autograd.Function):
         if saved.numel() == 0:
             raise RuntimeError("mpgcn_b200.bdgcn: backward called but forward ran without requires_grad inputs")
         d_out = _f32c(d_out)
+        tc = prec == _lib.PREC_FP16_TC
+        hint = _take_hint(d_out) if tc else None
         need_dx = ctx.needs_input_grad[0]
         dX = torch.empty((B, N, N, C), dtype=torch.float32, device=out.device) if need_dx else None
+        dx_absmax = torch.empty(1, dtype=torch.float32, device=out.device) if (need_dx and tc) else None
         dW = torch.empty_like(Wc)
         db = torch.empty(H, dtype=torch.float32, device=out.device) if has_bias else None
         ws = _scratch(lib.mpgcn_bdgcn_bwd_workspace_bytes(B, N, K, C, H, int(dynamic), prec), out.device)
         with torch.cuda.device(out.device):
-            _lib.check(lib.mpgcn_bdgcn_backward(_ptr(d_out), _ptr(out), _ptr(Goc), _ptr(Gdc), int(dynamic), _ptr(Wc), act, _ptr(saved),
-                                                _ptr(dX), _ptr(dW), _ptr(db), _ptr(ws), ws.numel(), B, N, K, C, H, prec, _stream()),
-                       "bdgcn_backward")
+            _lib.check(lib.mpgcn_bdgcn_backward_ex(_ptr(d_out), _ptr(out), _ptr(Goc), _ptr(Gdc), int(dynamic), _ptr(Wc), act, _ptr(saved),
+                                                   _ptr(dX), _ptr(dW), _ptr(db), _ptr(ws), ws.numel(), B, N, K, C, H, prec, _ptr(hint),
+                                                   _ptr(dx_absmax), _stream()), "bdgcn_backward")
+        if dx_absmax is not None:
+            _put_hint(dX, dx_absmax)
         return dX, None, None, dW, db, None, None, None
 
 
@@ -154,15 +180,16 @@ class _LSTMLastFn(torch.autograd.Function):
         xc, w_ih, w_hh, b_ih, b_hh = ctx.saved_tensors
         B, T, NN, C, prec = ctx.dims
         d_hT = _f32c(d_hT)
+        hint = _take_hint(d_hT) if prec == _lib.PREC_FP16_TC else None
         dev = xc.device
         g_wih, g_whh = torch.empty_like(w_ih), torch.empty_like(w_hh)
         g_bih, g_bhh = torch.empty_like(b_ih), torch.empty_like(b_hh)
         d_x = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
         ws = _scratch(lib.mpgcn_lstm_bwd_workspace_bytes(B, T, NN, C, prec), dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.mpgcn_lstm_last_backward(_ptr(xc), _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(d_hT), _ptr(g_wih),
-                                                    _ptr(g_whh), _ptr(g_bih), _ptr(g_bhh), _ptr(d_x), _ptr(ws), ws.numel(), B, T, NN, C,
-                                                    prec, _stream()), "lstm_last_backward")
+            _lib.check(lib.mpgcn_lstm_last_backward_ex(_ptr(xc), _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(d_hT), _ptr(g_wih),
+                                                       _ptr(g_whh), _ptr(g_bih), _ptr(g_bhh), _ptr(d_x), _ptr(ws), ws.numel(), B, T, NN, C,
+                                                       prec, _ptr(hint), _stream()), "lstm_last_backward")
         return d_x, g_wih, g_whh, g_bih, g_bhh, None
 
 
@@ -204,9 +231,12 @@ class _HeadFn(torch.autograd.Function):
         db = torch.empty(M, dtype=torch.float32, device=dy.device)
         ptrs = (ctypes.c_void_p * M)(*[g.data_ptr() for g in gc])
         dptrs = (ctypes.c_void_p * M)(*[(d.data_ptr() if d is not None else None) for d in dgs])
+        amax = torch.empty(M, dtype=torch.float32, device=dy.device)
         with torch.cuda.device(dy.device):
-            _lib.check(lib.mpgcn_head_backward(ptrs, _ptr(wc), _ptr(pre), _ptr(dy), dptrs, _ptr(dw), _ptr(db), cells, C, M, _stream()),
-                       "head_backward")
+            _lib.check(lib.mpgcn_head_backward(ptrs, _ptr(wc), _ptr(pre), _ptr(dy), dptrs, _ptr(dw), _ptr(db), _ptr(amax), cells, C, M,
+                                               _stream()), "head_backward")
+        for m, d in enumerate(dgs):
+            _put_hint(d, amax[m:m + 1])
         return (dw, db) + tuple(dgs)
 
 
