@@ -107,6 +107,21 @@ MPGCN_API int mpgcn_lstm_last_backward_ex(const float* x_seq, const float* w_ih,
                                 size_t workspace_bytes, int B, int T, long long NN, int C, int precision, const float* d_hT_absmax,
                                 void* stream);
 
+/* Training pair for the LSTM (what autograd keeps between nn.LSTM's forward and backward, MPGCN.py:100-104 under
+ * loss.backward(), Model_Trainer.py:114).  The forward additionally writes c_t and h_t of every step (fp16) into `saved`
+ * (mpgcn_lstm_saved_bytes; 0 for precision 0, whose backward recomputes; 16-byte aligned; NULL = plain inference forward);
+ * the backward walks that buffer once in reverse instead of re-running the recurrence.  With saved == NULL the backward is
+ * mpgcn_lstm_last_backward_ex (recompute, workspace from mpgcn_lstm_bwd_workspace_bytes); with saved != NULL the
+ * workspace only needs 1024 bytes. */
+MPGCN_API size_t mpgcn_lstm_saved_bytes(int B, int T, long long NN, int C, int precision);
+MPGCN_API int mpgcn_lstm_last_forward_train(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                  float* hT, void* saved, size_t saved_bytes, int B, int T, long long NN, int C, int precision,
+                                  void* stream);
+MPGCN_API int mpgcn_lstm_last_backward_saved(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                   const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x,
+                                   const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, int B, int T,
+                                   long long NN, int C, int precision, const float* d_hT_absmax, void* stream);
+
 /* FC head + multi-perspective fusion (reference MPGCN.py:74-76,107,110,112), one pass:
  *     y[cell] = (1/M) * sum_m relu( g_m[cell,:] . w[m,:] + bias[m] )      (Linear(C -> 1) + ReLU per branch, mean over the M branches)
  *   g    HOST array of M device pointers, each [cells, C] (cells = B*N*N);  w [M,C], bias [M];  y [cells]

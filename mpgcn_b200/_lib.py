@@ -46,6 +46,11 @@ _SIGS = {
                                                ctypes.c_size_t] + [ctypes.c_int] * 6 + [_c_f, _c_f, ctypes.c_void_p]),
     "mpgcn_lstm_last_backward_ex": (ctypes.c_int, [_c_f] * 12 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
                                                    ctypes.c_int, _c_f, ctypes.c_void_p]),
+    "mpgcn_lstm_saved_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]),
+    "mpgcn_lstm_last_forward_train": (ctypes.c_int, [_c_f] * 7 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
+                                                     ctypes.c_int, ctypes.c_void_p]),
+    "mpgcn_lstm_last_backward_saved": (ctypes.c_int, [_c_f] * 12 + [ctypes.c_size_t, _c_f, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.c_longlong, ctypes.c_int, ctypes.c_int, _c_f, ctypes.c_void_p]),
     "mpgcn_lstm_precision_supported": (ctypes.c_int, [ctypes.c_int] * 3),
     "mpgcn_lstm_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]),
     "mpgcn_lstm_last_forward": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,

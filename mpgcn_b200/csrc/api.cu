@@ -133,40 +133,65 @@ size_t mpgcn_lstm_bwd_workspace_bytes(int B, int T, long long NN, int C, int pre
   return precision == PREC_FP16_TC ? lstm_tc_bwd_workspace_bytes(B, T, NN) : 256;
 }
 
-int mpgcn_lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
-                            int B, int T, long long NN, int C, int precision, void* stream) {
+size_t mpgcn_lstm_saved_bytes(int B, int T, long long NN, int C, int precision) {
+  (void)C;
+  return precision == PREC_FP16_TC ? lstm_tc_saved_bytes(B, T, NN) : 0;
+}
+
+int mpgcn_lstm_last_forward_train(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
+                                  void* saved, size_t saved_bytes, int B, int T, long long NN, int C, int precision, void* stream) {
   MPGCN_CHECK(x_seq && w_ih && w_hh && b_ih && b_hh && hT, "mpgcn_lstm_last_forward: null pointer argument");
   MPGCN_CHECK(B >= 1 && T >= 1 && NN >= 1, "mpgcn_lstm_last_forward: empty input");
   MPGCN_CHECK(mpgcn_lstm_precision_supported(T, C, precision), "lstm: precision %d does not support T=%d, hidden=%d", precision, T, C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (precision == PREC_FP16_TC) return lstm_last_forward_tc(x_seq, w_ih, w_hh, b_ih, b_hh, hT, B, T, NN, st);
+  if (precision == PREC_FP16_TC) {
+    MPGCN_CHECK(saved == nullptr || saved_bytes >= lstm_tc_saved_bytes(B, T, NN), "lstm forward: saved buffer too small (%zu < %zu)",
+                saved_bytes, lstm_tc_saved_bytes(B, T, NN));
+    return lstm_last_forward_tc(x_seq, w_ih, w_hh, b_ih, b_hh, hT, saved, B, T, NN, st);
+  }
   return lstm_last_forward(x_seq, w_ih, w_hh, b_ih, b_hh, hT, B, T, NN, C, st);
 }
 
-int mpgcn_lstm_last_backward_ex(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                                const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
-                                size_t workspace_bytes, int B, int T, long long NN, int C, int precision, const float* d_hT_absmax,
-                                void* stream);
+int mpgcn_lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
+                            int B, int T, long long NN, int C, int precision, void* stream) {
+  return mpgcn_lstm_last_forward_train(x_seq, w_ih, w_hh, b_ih, b_hh, hT, nullptr, 0, B, T, NN, C, precision, stream);
+}
+
+int mpgcn_lstm_last_backward_saved(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                   const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x,
+                                   const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, int B, int T,
+                                   long long NN, int C, int precision, const float* d_hT_absmax, void* stream);
 
 int mpgcn_lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                              const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
                              size_t workspace_bytes, int B, int T, long long NN, int C, int precision, void* stream) {
-  return mpgcn_lstm_last_backward_ex(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, workspace, workspace_bytes,
-                                     B, T, NN, C, precision, nullptr, stream);
+  return mpgcn_lstm_last_backward_saved(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, nullptr, 0, workspace,
+                                        workspace_bytes, B, T, NN, C, precision, nullptr, stream);
 }
 
 int mpgcn_lstm_last_backward_ex(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
                                 const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, void* workspace,
                                 size_t workspace_bytes, int B, int T, long long NN, int C, int precision, const float* d_hT_absmax,
                                 void* stream) {
+  return mpgcn_lstm_last_backward_saved(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, nullptr, 0, workspace,
+                                        workspace_bytes, B, T, NN, C, precision, d_hT_absmax, stream);
+}
+
+int mpgcn_lstm_last_backward_saved(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                   const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x,
+                                   const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, int B, int T,
+                                   long long NN, int C, int precision, const float* d_hT_absmax, void* stream) {
   MPGCN_CHECK(x_seq && w_ih && w_hh && b_ih && b_hh && d_hT && d_w_ih && d_w_hh && d_b_ih && d_b_hh,
               "mpgcn_lstm_last_backward: null pointer argument");
   MPGCN_CHECK(B >= 1 && T >= 1 && NN >= 1, "mpgcn_lstm_last_backward: empty input");
   MPGCN_CHECK(mpgcn_lstm_precision_supported(T, C, precision), "lstm: precision %d does not support T=%d, hidden=%d", precision, T, C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (precision == PREC_FP16_TC)
-    return lstm_last_backward_tc(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, B, T, NN, workspace,
+  if (precision == PREC_FP16_TC) {
+    MPGCN_CHECK(saved == nullptr || saved_bytes >= lstm_tc_saved_bytes(B, T, NN), "lstm backward: saved buffer too small (%zu < %zu)",
+                saved_bytes, lstm_tc_saved_bytes(B, T, NN));
+    return lstm_last_backward_tc(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, saved, B, T, NN, workspace,
                                  workspace_bytes, d_hT_absmax, st);
+  }
   return lstm_last_backward(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_b_hh, d_x, B, T, NN, C, st);
 }
 

@@ -77,11 +77,13 @@ int adj_process(const float* flow, float* supports, int B, int N, int kernel_typ
 // tcgen05 LSTM (lstm_tc.cu): hidden size 32 only
 bool lstm_tc_supported(int T, int C);
 size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN);
+size_t lstm_tc_saved_bytes(int B, int T, long long NN);
+// saved (nullable): training state c_t, h_t written by the forward; the backward walks it instead of recomputing the forward
 int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
-                         int B, int T, long long NN, cudaStream_t s);
+                         void* saved, int B, int T, long long NN, cudaStream_t s);
 int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                          const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, int B, int T,
-                          long long NN, void* ws, size_t ws_bytes, const float* d_hT_absmax, cudaStream_t s);
+                          const float* d_hT, float* d_w_ih, float* d_w_hh, float* d_b_ih, float* d_b_hh, float* d_x, const void* saved,
+                          int B, int T, long long NN, void* ws, size_t ws_bytes, const float* d_hT_absmax, cudaStream_t s);
 
 // ---- BDGCN layer orchestration ---------------------------------------------------------------
 struct BdgcnShape {

@@ -167,10 +167,14 @@ class _LSTMLastFn(torch.autograd.Function):
         xc = _f32c(x_seq)
         ws = [_f32c(t) for t in (w_ih, w_hh, b_ih, b_hh)]
         hT = torch.empty((B * NN, C), dtype=torch.float32, device=x_seq.device)
+        # training: the forward keeps c_t / h_t of every step (fp16) so that the backward is one reverse walk
+        nsave = lib.mpgcn_lstm_saved_bytes(B, T, NN, C, prec) if any(ctx.needs_input_grad[:5]) else 0
+        saved = torch.empty(nsave, dtype=torch.uint8, device=x_seq.device) if nsave else None
         with torch.cuda.device(x_seq.device):
-            _lib.check(lib.mpgcn_lstm_last_forward(_ptr(xc), *[_ptr(t) for t in ws], _ptr(hT), B, T, NN, C, prec, _stream()),
-                       "lstm_last_forward")
+            _lib.check(lib.mpgcn_lstm_last_forward_train(_ptr(xc), *[_ptr(t) for t in ws], _ptr(hT), _ptr(saved), nsave, B, T, NN, C, prec,
+                                                         _stream()), "lstm_last_forward")
         ctx.dims = (B, T, NN, C, prec)
+        ctx.lstm_saved = saved
         ctx.save_for_backward(xc, *ws)
         return hT
 
@@ -185,11 +189,14 @@ class _LSTMLastFn(torch.autograd.Function):
         g_wih, g_whh = torch.empty_like(w_ih), torch.empty_like(w_hh)
         g_bih, g_bhh = torch.empty_like(b_ih), torch.empty_like(b_hh)
         d_x = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
-        ws = _scratch(lib.mpgcn_lstm_bwd_workspace_bytes(B, T, NN, C, prec), dev)
+        saved = ctx.lstm_saved
+        ws = _scratch(1024 if saved is not None else lib.mpgcn_lstm_bwd_workspace_bytes(B, T, NN, C, prec), dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.mpgcn_lstm_last_backward_ex(_ptr(xc), _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(d_hT), _ptr(g_wih),
-                                                       _ptr(g_whh), _ptr(g_bih), _ptr(g_bhh), _ptr(d_x), _ptr(ws), ws.numel(), B, T, NN, C,
-                                                       prec, _ptr(hint), _stream()), "lstm_last_backward")
+            _lib.check(lib.mpgcn_lstm_last_backward_saved(_ptr(xc), _ptr(w_ih), _ptr(w_hh), _ptr(b_ih), _ptr(b_hh), _ptr(d_hT), _ptr(g_wih),
+                                                          _ptr(g_whh), _ptr(g_bih), _ptr(g_bhh), _ptr(d_x), _ptr(saved),
+                                                          saved.numel() if saved is not None else 0, _ptr(ws), ws.numel(), B, T, NN, C,
+                                                          prec, _ptr(hint), _stream()), "lstm_last_backward")
+        ctx.lstm_saved = None
         return d_x, g_wih, g_whh, g_bih, g_bhh, None
 
 

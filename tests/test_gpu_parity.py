@@ -128,6 +128,48 @@ def test_lstm_tensor_path_agrees_with_fp32_path(S, T, gmag, cuda_device):
         _check(a, r.cpu().numpy(), 1e-3 if n == "hT" else 2e-3, f"S={S} T={T} {n}")
 
 
+@pytest.mark.parametrize("S,T", [(700, 12), (130, 2), (64, 1)])
+def test_lstm_saved_state_backward_agrees_with_recompute_backward(S, T, cuda_device):
+    """The two C-ABI backward flavours of the tcgen05 LSTM: (a) forward_train keeps c_t/h_t and backward_saved walks them,
+    (b) plain forward + backward_ex recomputes the recurrence.  Same hT bits; gradients within the fp16-stash noise."""
+    from mpgcn_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(7 * S + T)
+    B, C, prec = 2, 32, _lib.PREC_FP16_TC
+    lstm = nn.LSTM(1, C, 1, batch_first=True).to(cuda_device)
+    ws = [w.detach().contiguous() for w in (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)]
+    x = (torch.rand(B, T, S, device=cuda_device) * 6).contiguous()
+    d_h = torch.randn(B * S, C, device=cuda_device)
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: None if t is None else t.data_ptr()
+    h_a, h_b = torch.empty(B * S, C, device=cuda_device), torch.empty(B * S, C, device=cuda_device)
+    nsave = lib.mpgcn_lstm_saved_bytes(B, T, S, C, prec)
+    assert nsave == ((B * S + 127) // 128) * T * 128 * 128
+    saved = torch.empty(nsave, dtype=torch.uint8, device=cuda_device)
+    _lib.check(lib.mpgcn_lstm_last_forward_train(p(x), *[p(w) for w in ws], p(h_a), p(saved), nsave, B, T, S, C, prec, st), "fwd_train")
+    _lib.check(lib.mpgcn_lstm_last_forward(p(x), *[p(w) for w in ws], p(h_b), B, T, S, C, prec, st), "fwd")
+    assert torch.equal(h_a, h_b)
+    outs = []
+    for flavour in ("saved", "recompute"):
+        g = [torch.empty_like(w) for w in ws]
+        dx = torch.empty_like(x)
+        if flavour == "saved":
+            wsb = torch.empty(1024, dtype=torch.uint8, device=cuda_device)
+            _lib.check(lib.mpgcn_lstm_last_backward_saved(p(x), *[p(w) for w in ws], p(d_h), *[p(t) for t in g], p(dx), p(saved), nsave,
+                                                          p(wsb), wsb.numel(), B, T, S, C, prec, None, st), "bwd_saved")
+        else:
+            wsb = torch.empty(lib.mpgcn_lstm_bwd_workspace_bytes(B, T, S, C, prec), dtype=torch.uint8, device=cuda_device)
+            _lib.check(lib.mpgcn_lstm_last_backward_ex(p(x), *[p(w) for w in ws], p(d_h), *[p(t) for t in g], p(dx), p(wsb), wsb.numel(),
+                                                       B, T, S, C, prec, None, st), "bwd_recompute")
+        torch.cuda.synchronize()
+        outs.append(g + [dx])
+    for a, r, n in zip(outs[0], outs[1], ("dw_ih", "dw_hh", "db_ih", "db_hh", "dx")):
+        _check(a, r.cpu().numpy(), 2e-3, f"S={S} T={T} saved-vs-recompute {n}")
+    # a too-small saved buffer is refused
+    rc = lib.mpgcn_lstm_last_forward_train(p(x), *[p(w) for w in ws], p(h_a), p(saved), nsave - 1, B, T, S, C, prec, st)
+    assert rc != 0 and b"saved buffer too small" in lib.mpgcn_last_error()
+
+
 @pytest.mark.parametrize("name", golden_names("adj_"))
 def test_adj_processor_matches_reference_fixture(name, cuda_device):
     """GPU support-matrix builder vs fixtures produced by the reference's Adj_Processor (fp32: summation-order noise only)."""
