@@ -694,11 +694,16 @@ __device__ void load_weights_ext(uint8_t* sWx, const float* w_ih, const float* w
   }
 }
 
-__global__ void __maxnreg__(112)
+constexpr int BWD_THREADS = 256;    // 8 warps, all of them epilogue warps; warp 0 also issues the MMAs (see kernel comment)
+
+__global__ void __launch_bounds__(BWD_THREADS, 2)
 lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                          const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ d_hT,
                          float* __restrict__ d_w_ih, float* __restrict__ d_w_hh, float* __restrict__ d_b, float* __restrict__ d_x,
                          const __half* __restrict__ saved, const float* __restrict__ scale2, long long cells, int T, long long NN) {
+  // No dedicated MMA warp: with 9 warps per CTA the register file only holds ONE CTA per SM at > 102 registers per thread
+  // (18 warps -> 5 on one scheduler partition); 8 warps x 2 CTAs x 128 registers fills it exactly.  Every step ends in one
+  // CTA-wide barrier, after which lane 0 of warp 0 issues the step's three MMA groups while everybody moves on.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sDA = smem;                               // 32 KB
@@ -707,13 +712,9 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
   uint8_t* sW = sWx + WX_BYTES;                      // 8 KB
   float* s_bias = reinterpret_cast<float*>(sW + 8192);
   float* s_wih = s_bias + G4;
-  uint64_t* h_ready = reinterpret_cast<uint64_t*>(s_wih + G4);
-  uint64_t* g_ready = h_ready + 1;
-  uint64_t* da_ready = g_ready + 1;
-  uint64_t* da_free = da_ready + 1;
-  uint64_t* dh_ready = da_free + 1;
-  uint64_t* acc_done = dh_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
+  uint64_t* mma_ready = reinterpret_cast<uint64_t*>(s_wih + G4);     // dh_t and the ex2 arguments of step t are in TMEM
+  uint64_t* mma_free = mma_ready + 1;                                  // the weight-gradient MMA has retired: sDA / hx reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   load_weights(sW, s_bias, s_wih, w_ih, w_hh, b_ih, b_hh);
@@ -724,12 +725,11 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
     *reinterpret_cast<uint4*>(sHX + buf * HX_BYTES + sw128_off(r, ch)) = make_uint4(0u, 0u, 0u, 0u);
   }
   if (threadIdx.x == 0) {
-    mbar_init(h_ready, EPI); mbar_init(g_ready, 1);
-    mbar_init(da_ready, EPI); mbar_init(da_free, 1);
-    mbar_init(dh_ready, 1); mbar_init(acc_done, 1);
+    mbar_init(mma_ready, 1);
+    mbar_init(mma_free, 1);
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -739,222 +739,210 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
   const long long tiles = (cells + CELLS - 1) / CELLS;
   const float S = scale2[0], invS = scale2[1];
 
-  if (warp == MMA_WARP) {
-    const uint32_t id_gates = umma_idesc_f16(128, G4, 0, 0);
-    const uint32_t id_dh = umma_idesc_f16(128, 32, 0, 1);
-    const uint32_t id_dw = umma_idesc_f16(128, 64, 1, 1);
-    const uint64_t hi64 = umma_desc_hi(512, 4u), hi128 = umma_desc_hi(1024, 2u);
-    const uint32_t w_addr = smem_u32(sW), wx_addr = smem_u32(sWx);
-    const uint32_t da_addr = smem_u32(sDA), hx_addr = smem_u32(sHX);
-    uint32_t ph_h = 0, ph_da = 0;
-    bool first_dw = true;
-    auto issue_gates = [&](int t) {                // ex2 arguments of step t from hx_t (48 of its 64 columns are live)
-      mbar_wait(h_ready, ph_h);
-      ph_h ^= 1u;
+  const uint32_t id_gates = umma_idesc_f16(128, G4, 0, 0);
+  const uint32_t id_dh = umma_idesc_f16(128, 32, 0, 1);
+  const uint32_t id_dw = umma_idesc_f16(128, 64, 1, 1);
+  const uint64_t hi64 = umma_desc_hi(512, 4u), hi128 = umma_desc_hi(1024, 2u);
+  const uint32_t w_addr = smem_u32(sW), wx_addr = smem_u32(sWx);
+  const uint32_t da_addr = smem_u32(sDA), hx_addr = smem_u32(sHX);
+  bool first_dw = true;               // meaningful in the issuing thread only
+
+  const int hh = warp >> 2;
+  const int row = (warp & 3) * 32 + lane;
+  const int u0 = UN * hh;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t t_g = TM_GATES + lane_base + u0, t_dh = TM_DH + lane_base + u0, t_dc = TM_DC + lane_base + u0;
+  uint32_t ph_ready = 0, ph_free = 0;
+  bool mma2_pending = false;          // a weight-gradient MMA that reads sDA / an hx buffer may still be in flight
+
+  // stage hx_t: this thread's 16 units of h_{t-1} (or zeros at t = 0) and, from unit half 0, the x / 1 columns
+  auto stage_hx = [&](const __half* my_save, int t, float xt) {
+    uint8_t* buf = sHX + (t & 1) * HX_BYTES;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint8_t* dst = buf + sw128_off(row, 2 * hh + q);
+      if (t > 0) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(save_at(my_save, t - 1, 4 + q)) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    if (hh == 0) {
+      const float x_hi = __half2float(__float2half_rn(xt));
+      *reinterpret_cast<uint4*>(buf + sw128_off(row, 4)) = make_uint4(pack2(x_hi, 1.f), pack2(xt - x_hi, x_hi), pack2(1.f, 0.f), 0u);
+    }
+  };
+  // ex2 arguments of step t from hx_t (48 of its 64 columns are live)
+  auto issue_gates = [&](int t) {
+    const uint32_t a = hx_addr + (uint32_t)(t & 1) * HX_BYTES;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      umma_f16(TM_GATES, umma_desc(hi128, a + k * 32, 16), umma_desc(hi128, wx_addr + k * 32, 16), id_gates, k > 0 ? 1u : 0u);
+  };
+
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long cell = tile * CELLS + row;
+    const bool live = cell < cells;
+    const size_t xb = live ? x_base(cell, T, NN) : 0;
+    const __half* my_save = saved + (size_t)tile * T * (SAVE_CHUNKS * CELLS * 8) + (size_t)(2 * hh) * CELLS * 8 + (size_t)row * 8;
+    if (mma2_pending) {                // last step of the previous tile
+      mbar_wait(mma_free, ph_free);
+      ph_free ^= 1u;
+      mma2_pending = false;
+    }
+    stage_hx(my_save, T - 1, live ? x_seq[xb + (size_t)(T - 1) * NN] : 0.f);
+    float x_stage = (live && T > 1) ? x_seq[xb + (size_t)(T - 2) * NN] : 0.f;      // x of the hx tile the next step stages
+    // seed dh (scaled d_hT) and dc (0) in TMEM
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint32_t r[8];
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) v = *reinterpret_cast<const float4*>(d_hT + (size_t)cell * C + u0 + 8 * q + e);
+        r[e] = __float_as_uint(v.x * S); r[e + 1] = __float_as_uint(v.y * S);
+        r[e + 2] = __float_as_uint(v.z * S); r[e + 3] = __float_as_uint(v.w * S);
+      }
+      tmem_st_32x8(t_dh + 8 * q, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = 0u;
+      tmem_st_32x8(t_dc + 8 * q, r);
+    }
+    tmem_st_wait();
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a = hx_addr + (uint32_t)(t & 1) * HX_BYTES;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          umma_f16(TM_GATES, umma_desc(hi128, a + k * 32, 16), umma_desc(hi128, wx_addr + k * 32, 16), id_gates, k > 0 ? 1u : 0u);
-        umma_commit(g_ready);
+        issue_gates(T - 1);
+        umma_commit(mma_ready);
       }
       __syncwarp();
-    };
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      issue_gates(T - 1);
-      for (int t = T - 1; t >= 0; --t) {
-        if (t > 0) issue_gates(t - 1);             // overlaps the epilogue's math of step t
-        mbar_wait(da_ready, ph_da);
-        ph_da ^= 1u;
+    }
+    uint4 vc[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) vc[q] = *save_at(my_save, T - 1, q);
+    for (int t = T - 1; t >= 0; --t) {
+      uint4 vcp[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        vcp[q] = make_uint4(0, 0, 0, 0);
+        if (t > 0) vcp[q] = *save_at(my_save, t - 1, q);
+      }
+      const float x_cur = x_stage;
+      x_stage = (live && t > 1) ? x_seq[xb + (size_t)(t - 2) * NN] : 0.f;
+      mbar_wait(mma_ready, ph_ready);    // ex2 arguments of this step and (t < T-1) dh_t
+      ph_ready ^= 1u;
+      tc_fence_after();
+      if (mma2_pending) {                // MMA2 of step t+1 retired: sDA and hx buffer (t+1) & 1 == (t-1) & 1 are free
+        mbar_wait(mma_free, ph_free);
+        ph_free ^= 1u;
+        mma2_pending = false;
+      }
+      if (t > 0) stage_hx(my_save, t - 1, x_cur);
+      float dx_acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t ri[8], rf[8], rg[8], ro[8], rdh[8], rdc[8];
+        tmem_ld_32x8(t_g + 0 * C + 8 * q, ri);
+        tmem_ld_32x8(t_g + 1 * C + 8 * q, rf);
+        tmem_ld_32x8(t_g + 2 * C + 8 * q, rg);
+        tmem_ld_32x8(t_g + 3 * C + 8 * q, ro);
+        tmem_ld_32x8(t_dh + 8 * q, rdh);
+        tmem_ld_32x8(t_dc + 8 * q, rdc);
+        tmem_ld_wait();
+        float fc[8], fcp[8];
+        unpack8(vc[q], fc); unpack8(vcp[q], fcp);
+        float di[8], df[8], dg[8], d_o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          // accumulators are -log2e * pre (i, f, o) and -2 log2e * pre (g); clamp from above only (ex2(-big) = 0 is fine),
+          // which keeps the product of two (1 + 2^arg) terms below 1e26
+          const float ai = 1.f + ex2_(fminf(__uint_as_float(ri[e]), 43.280851f));
+          const float ag = 1.f + ex2_(fminf(__uint_as_float(rg[e]), 43.280851f));
+          const float af = 1.f + ex2_(fminf(__uint_as_float(rf[e]), 43.280851f));
+          const float ao = 1.f + ex2_(fminf(__uint_as_float(ro[e]), 43.280851f));
+          const float r1 = rcp_(ai * ag), r2 = rcp_(af * ao);
+          const float gi = r1 * ag, gg = fmaf(r1 + r1, ai, -1.f);
+          const float gf = r2 * ao, go = r2 * af;
+          const float tcv = tanh_(fc[e]);
+          const float dhv = __uint_as_float(rdh[e]);
+          const float dcv = fmaf(dhv * go, fmaf(-tcv, tcv, 1.f), __uint_as_float(rdc[e]));
+          d_o[e] = (dhv * tcv) * fmaf(-go, go, go);
+          di[e] = (dcv * gg) * fmaf(-gi, gi, gi);
+          df[e] = (dcv * fcp[e]) * fmaf(-gf, gf, gf);
+          dg[e] = (dcv * gi) * fmaf(-gg, gg, 1.f);
+          rdc[e] = __float_as_uint(dcv * gf);
+          if (d_x != nullptr) {
+            const int u = u0 + 8 * q + e;
+            dx_acc += di[e] * s_wih[u] + df[e] * s_wih[C + u] + dg[e] * s_wih[2 * C + u] + d_o[e] * s_wih[3 * C + u];
+          }
+        }
+#define MPGCN_ST_DA(blk, arr)                                                                              \
+  *reinterpret_cast<uint4*>(sDA + (((blk) * 32 + u0 + 8 * q) >> 6) * 16384 +                               \
+                            sw128_off(row, (((blk) * 32 + u0 + 8 * q) & 63) >> 3)) = pack8(arr)
+        MPGCN_ST_DA(0, di);
+        MPGCN_ST_DA(1, df);
+        MPGCN_ST_DA(2, dg);
+        MPGCN_ST_DA(3, d_o);
+#undef MPGCN_ST_DA
+        tmem_st_32x8(t_dc + 8 * q, rdc);
+      }
+      if (d_x != nullptr && live) atomicAdd(&d_x[xb + (size_t)t * NN], dx_acc * invS);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) vc[q] = vcp[q];
+      tmem_st_wait();
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();                   // da_t, hx_{t-1} and dc are in place; every read of this step's gates / dh is done
+      if (warp == 0) {
         tc_fence_after();
         if (lane == 0) {
           const uint32_t hx = hx_addr + (uint32_t)(t & 1) * HX_BYTES;
           if (t > 0) {
+            // dh_{t-1} = da (K-major, two 64-gate sub-tiles of [128 cells][128 B]) x W_hh (rows j, K step = 16 rows x 64 B)
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               umma_f16(TM_DH, umma_desc(hi128, da_addr + (k >> 2) * 16384 + (k & 3) * 32, 16), umma_desc(hi64, w_addr + k * 1024, 2048),
                        id_dh, k > 0 ? 1u : 0u);
-            umma_commit(dh_ready);
+            issue_gates(t - 1);
+            umma_commit(mma_ready);
           }
+          // dWext += da^T (MN-major: k rows = cells, 2 m-chunks of 64 gates 16 KB apart) x hx_t (k rows = cells, 128 B)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_f16(TM_DW, umma_desc(hi128, da_addr + k * 2048, 16384), umma_desc(hi128, hx + k * 2048, 16384), id_dw,
                      (first_dw && k == 0) ? 0u : 1u);
           first_dw = false;
-          umma_commit(da_free);
+          umma_commit(mma_free);
         }
         __syncwarp();
       }
+      mma2_pending = true;
     }
-    if (lane == 0) umma_commit(acc_done);
-    __syncwarp();
-  } else {
-    const int hh = warp >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const int u0 = UN * hh;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t t_g = TM_GATES + lane_base + u0, t_dh = TM_DH + lane_base + u0, t_dc = TM_DC + lane_base + u0;
-    uint32_t ph_g = 0, ph_dh = 0, ph_free = 0;
-    bool mma2_pending = false;           // a weight-gradient MMA that reads sDA / an hx buffer may still be in flight
-    // stage hx_t: this thread's 16 units of h_{t-1} (or zeros at t = 0) and, from unit half 0, the x / 1 columns
-    auto stage_hx = [&](const __half* my_save, int t, float xt) {
-      uint8_t* buf = sHX + (t & 1) * HX_BYTES;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint8_t* dst = buf + sw128_off(row, 2 * hh + q);
-        if (t > 0) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(save_at(my_save, t - 1, 4 + q)) : "memory");
-        } else {
-          *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-      if (hh == 0) {
-        const float x_hi = __half2float(__float2half_rn(xt));
-        *reinterpret_cast<uint4*>(buf + sw128_off(row, 4)) = make_uint4(pack2(x_hi, 1.f), pack2(xt - x_hi, x_hi), pack2(1.f, 0.f), 0u);
-      }
-    };
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const long long cell = tile * CELLS + row;
-      const bool live = cell < cells;
-      const size_t xb = live ? x_base(cell, T, NN) : 0;
-      const __half* my_save = saved + (size_t)tile * T * (SAVE_CHUNKS * CELLS * 8) + (size_t)(2 * hh) * CELLS * 8 + (size_t)row * 8;
-      if (mma2_pending) {                // last step of the previous tile
-        mbar_wait(da_free, ph_free);
-        ph_free ^= 1u;
-        mma2_pending = false;
-      }
-      float xv = live ? x_seq[xb + (size_t)(T - 1) * NN] : 0.f;
-      stage_hx(my_save, T - 1, xv);
-      // seed dh (scaled d_hT) and dc (0) in TMEM
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint32_t r[8];
-#pragma unroll
-        for (int e = 0; e < 8; e += 4) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live) v = *reinterpret_cast<const float4*>(d_hT + (size_t)cell * C + u0 + 8 * q + e);
-          r[e] = __float_as_uint(v.x * S); r[e + 1] = __float_as_uint(v.y * S);
-          r[e + 2] = __float_as_uint(v.z * S); r[e + 3] = __float_as_uint(v.w * S);
-        }
-        tmem_st_32x8(t_dh + 8 * q, r);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) r[e] = 0u;
-        tmem_st_32x8(t_dc + 8 * q, r);
-      }
-      tmem_st_wait();
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(h_ready);
-      uint4 vc[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) vc[q] = *save_at(my_save, T - 1, q);
-      for (int t = T - 1; t >= 0; --t) {
-        uint4 vcp[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          vcp[q] = make_uint4(0, 0, 0, 0);
-          if (t > 0) vcp[q] = *save_at(my_save, t - 1, q);
-        }
-        const float xp = (live && t > 0) ? x_seq[xb + (size_t)(t - 1) * NN] : 0.f;
-        mbar_wait(g_ready, ph_g);          // ex2 arguments of this step (issued one step ago)
-        ph_g ^= 1u;
-        tc_fence_after();
-        if (mma2_pending) {                // MMA2 of step t+1 retired: sDA and hx buffer (t+1) & 1 == (t-1) & 1 are free
-          mbar_wait(da_free, ph_free);
-          ph_free ^= 1u;
-          mma2_pending = false;
-        }
-        if (t > 0) stage_hx(my_save, t - 1, xp);
-        float dx_acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint32_t ri[8], rf[8], rg[8], ro[8], rdh[8], rdc[8];
-          tmem_ld_32x8(t_g + 0 * C + 8 * q, ri);
-          tmem_ld_32x8(t_g + 1 * C + 8 * q, rf);
-          tmem_ld_32x8(t_g + 2 * C + 8 * q, rg);
-          tmem_ld_32x8(t_g + 3 * C + 8 * q, ro);
-          tmem_ld_32x8(t_dh + 8 * q, rdh);
-          tmem_ld_32x8(t_dc + 8 * q, rdc);
-          tmem_ld_wait();
-          if (q == 1 && t > 0) {           // every gate read of this step is done and hx_{t-1} is staged: release MMA0(t-1)
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(h_ready);
-          }
-          float fc[8], fcp[8];
-          unpack8(vc[q], fc); unpack8(vcp[q], fcp);
-          float di[8], df[8], dg[8], d_o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            // accumulators are -log2e * pre (i, f, o) and -2 log2e * pre (g); clamp from above only (ex2(-big) = 0 is fine),
-            // which keeps the product of two (1 + 2^arg) terms below 1e26
-            const float ai = 1.f + ex2_(fminf(__uint_as_float(ri[e]), 43.280851f));
-            const float ag = 1.f + ex2_(fminf(__uint_as_float(rg[e]), 43.280851f));
-            const float af = 1.f + ex2_(fminf(__uint_as_float(rf[e]), 43.280851f));
-            const float ao = 1.f + ex2_(fminf(__uint_as_float(ro[e]), 43.280851f));
-            const float r1 = rcp_(ai * ag), r2 = rcp_(af * ao);
-            const float gi = r1 * ag, gg = fmaf(r1 + r1, ai, -1.f);
-            const float gf = r2 * ao, go = r2 * af;
-            const float tcv = tanh_(fc[e]);
-            const float dhv = __uint_as_float(rdh[e]);
-            const float dcv = fmaf(dhv * go, fmaf(-tcv, tcv, 1.f), __uint_as_float(rdc[e]));
-            d_o[e] = (dhv * tcv) * fmaf(-go, go, go);
-            di[e] = (dcv * gg) * fmaf(-gi, gi, gi);
-            df[e] = (dcv * fcp[e]) * fmaf(-gf, gf, gf);
-            dg[e] = (dcv * gi) * fmaf(-gg, gg, 1.f);
-            rdc[e] = __float_as_uint(dcv * gf);
-            if (d_x != nullptr) {
-              const int u = u0 + 8 * q + e;
-              dx_acc += di[e] * s_wih[u] + df[e] * s_wih[C + u] + dg[e] * s_wih[2 * C + u] + d_o[e] * s_wih[3 * C + u];
-            }
-          }
-#define MPGCN_ST_DA(blk, arr)                                                                              \
-  *reinterpret_cast<uint4*>(sDA + (((blk) * 32 + u0 + 8 * q) >> 6) * 16384 +                               \
-                            sw128_off(row, (((blk) * 32 + u0 + 8 * q) & 63) >> 3)) = pack8(arr)
-          MPGCN_ST_DA(0, di);
-          MPGCN_ST_DA(1, df);
-          MPGCN_ST_DA(2, dg);
-          MPGCN_ST_DA(3, d_o);
-#undef MPGCN_ST_DA
-          tmem_st_32x8(t_dc + 8 * q, rdc);
-        }
-        if (d_x != nullptr && live) atomicAdd(&d_x[xb + (size_t)t * NN], dx_acc * invS);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) vc[q] = vcp[q];
-        tmem_st_wait();
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(da_ready);
-        mma2_pending = true;
-        if (t > 0) {
-          mbar_wait(dh_ready, ph_dh);
-          ph_dh ^= 1u;
-          tc_fence_after();
-        }
-      }
-    }
-    mbar_wait(acc_done, 0);
+  }
+  // ---- flush the weight-gradient accumulator: TMEM lane = gate row j, this thread's 16 columns ----
+  if (mma2_pending) {
+    mbar_wait(mma_free, ph_free);
     tc_fence_after();
-    if (tiles > (long long)blockIdx.x) {
-      uint32_t r[UN];
-      tmem_ld_32x16(TM_DW + lane_base + u0, r);
-      tmem_ld_wait();
+    uint32_t r[UN];
+    tmem_ld_32x16(TM_DW + lane_base + u0, r);
+    tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < UN; ++k) atomicAdd(&d_w_hh[row * C + u0 + k], __uint_as_float(r[k]) * invS);
-      if (hh == 0) {
-        tmem_ld_32x16(TM_DW + lane_base + 32, r);
-        tmem_ld_wait();
-        atomicAdd(&d_w_ih[row], (__uint_as_float(r[0]) + __uint_as_float(r[2])) * invS);
-        atomicAdd(&d_b[row], __uint_as_float(r[1]) * invS);
-      }
+    for (int k = 0; k < UN; ++k) atomicAdd(&d_w_hh[row * C + u0 + k], __uint_as_float(r[k]) * invS);
+    if (hh == 0) {
+      tmem_ld_32x16(TM_DW + lane_base + 32, r);
+      tmem_ld_wait();
+      atomicAdd(&d_w_ih[row], (__uint_as_float(r[0]) + __uint_as_float(r[2])) * invS);
+      atomicAdd(&d_b[row], __uint_as_float(r[1]) * invS);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
 __global__ void copy_vec_kernel(const float* src, float* dst, int n) {
@@ -989,7 +977,7 @@ size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN) {
 // whose TMEM allocations -- 2 x 128 / 2 x 256 columns -- always fit); the rest of the 228 KB stays L1
 static const int kLstmFwdSmem = 24 * 1024;
 static const int kLstmSmem = 72 * 1024;
-static const int kLstmSavedSmem = 96 * 1024;     // saved-state backward: + second hx buffer + extended weight tile
+static const int kLstmSavedSmem = 94 * 1024;     // saved-state backward: + second hx buffer + extended weight tile
 
 size_t lstm_tc_saved_bytes(int B, int T, long long NN) {
   const long long tiles = ((long long)B * NN + lstm_tc::CELLS - 1) / lstm_tc::CELLS;
@@ -1047,7 +1035,7 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   if (saved) {
     prof_begin(PROF_LSTM_BWD, 12.0 * C * (C + 1) * (double)cells * T, st);
     static_assert(1024 + DA_BYTES + 2 * HX_BYTES + WX_BYTES + 8192 + 2 * G4 * sizeof(float) + 256 <= (size_t)kLstmSavedSmem, "smem");
-    lstm_bwd_saved_tc_kernel<<<lstm_grid(cells), THREADS, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
+    lstm_bwd_saved_tc_kernel<<<lstm_grid(cells), BWD_THREADS, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
                                                                            static_cast<const __half*>(saved), scale2, cells, T, NN);
   } else {
     prof_begin(PROF_LSTM_BWD, 16.0 * C * (C + 1) * (double)cells * T, st);
