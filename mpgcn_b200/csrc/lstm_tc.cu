@@ -35,6 +35,9 @@ constexpr int STASH = 6 * C;    // halves per cell-step: i f g o c h
 constexpr int THREADS = 288;    // 8 epilogue warps + 1 MMA warp
 constexpr int EPI = 256;
 constexpr int MMA_WARP = 8;
+constexpr int DA_BYTES = 32768;     // [128 cells][128 gates] fp16 as two [128][64] SW128 sub-tiles
+constexpr int HX_BYTES = 16384;     // [128 cells][64] fp16, SW128
+constexpr int WX_BYTES = 16384;     // [128 gates][64] fp16, SW128
 
 __device__ __forceinline__ uint32_t sw64_off(int row, int chunk) { return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4); }
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
@@ -288,116 +291,153 @@ __device__ __forceinline__ void write_h_tile(uint8_t* sH, int row, int hh, const
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
+// Per 128-cell tile and step ONE MMA produces the ex2 arguments of all four gates, affine part included:
+//     hx_t[cell] = [ h_{t-1} (32) | x_hi  1  x_lo  x_hi  1  0 0 0 | 0 .. ]                    (fp16, 64 columns, SWIZZLE_128B)
+//     Wx[j]      = s_j * [ W_hh[j,:] | wih_hi  b_hi  wih_hi  wih_lo  b_lo  0 0 0 | 0 .. ]      s_j = -log2 e (i, f, o), -2 log2 e (g)
+//     acc[cell][j] = hx_t . Wx[j] = s_j * (W_hh h_{t-1} + w_ih x_t + b)_j
+// x, w_ih and b are split into fp16 hi + lo parts, so the affine part keeps ~22 bits; h_{t-1} is rounded to fp16 (the only
+// reduced-precision operand).  Eight warps, two threads per cell (16 hidden units each); no dedicated MMA warp (see the
+// register-file note at lstm_bwd_saved_tc_kernel): a step ends in one CTA barrier, then lane 0 of warp 0 issues the MMA.
+
+__device__ void load_weights_ext(uint8_t* sWx, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh) {
+  for (int e = threadIdx.x; e < G4 * 8; e += blockDim.x) {
+    const int j = e >> 3, ch = e & 7;
+    const float sc = ((j >> 5) == 2) ? -2.8853900817779268f : -1.4426950408889634f;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ch < 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = sc * w_hh[j * C + ch * 8 + i];
+    } else if (ch == 4) {
+      const float wi = sc * w_ih[j], bb = sc * (b_ih[j] + b_hh[j]);
+      const float wi_hi = __half2float(__float2half_rn(wi)), b_hi = __half2float(__float2half_rn(bb));
+      v[0] = wi_hi; v[1] = b_hi; v[2] = wi_hi; v[3] = wi - wi_hi; v[4] = bb - b_hi;
+    }
+    *reinterpret_cast<uint4*>(sWx + sw128_off(j, ch)) = pack8(v);
+  }
+}
+
+
+constexpr int FWD_THREADS = 256;
+
 template <bool SAVE>
-#if MPGCN_LSTM_FWD_LB == 1
-__global__ void __launch_bounds__(THREADS, 2)
-#elif MPGCN_LSTM_FWD_LB == 2
-__global__ void __launch_bounds__(THREADS)          // with -maxrregcount=112 for this file
-#else
-__global__ void __maxnreg__(112)
-#endif
+__global__ void __launch_bounds__(FWD_THREADS, 2)
 lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ hT, __half* __restrict__ saved,
                    long long cells, int T, long long NN) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW = smem;                      // 8 KB
-  uint8_t* sH = smem + 8192;               // 8 KB
-  float* s_bias = reinterpret_cast<float*>(smem + 2 * 8192);
-  float* s_wih = s_bias + G4;
-  uint64_t* h_ready = reinterpret_cast<uint64_t*>(s_wih + G4);
-  uint64_t* g_ready = h_ready + 1;
+  uint8_t* sWx = smem;                     // 16 KB
+  uint8_t* sHX = smem + WX_BYTES;          // 16 KB
+  uint64_t* g_ready = reinterpret_cast<uint64_t*>(sHX + HX_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  load_weights(sW, s_bias, s_wih, w_ih, w_hh, b_ih, b_hh);
+  load_weights_ext(sWx, w_ih, w_hh, b_ih, b_hh);
+  for (int e = threadIdx.x; e < CELLS * 3; e += blockDim.x)      // constant zero columns 40..63 (chunks 5, 6, 7)
+    *reinterpret_cast<uint4*>(sHX + sw128_off(e / 3, 5 + e % 3)) = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
-    mbar_init(h_ready, EPI);
     mbar_init(g_ready, 1);
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
-  fence_proxy_async_smem();       // weight tile was written with generic stores, will be read by the tensor core
+  if (warp == 0) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const long long tiles = (cells + CELLS - 1) / CELLS;
+  const uint32_t idesc = umma_idesc_f16(128, G4, 0, 0);
+  const uint64_t hi128 = umma_desc_hi(1024, 2u);
+  const uint32_t a_addr = smem_u32(sHX), b_addr = smem_u32(sWx);
 
-  if (warp == MMA_WARP) {
-    const uint32_t idesc = umma_idesc_f16(128, G4, 0, 0);
-    const uint64_t hi = umma_desc_hi(512, 4u);
-    const uint32_t a_addr = smem_u32(sH), b_addr = smem_u32(sW);
-    uint32_t ph = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      for (int t = 1; t < T; ++t) {
-        mbar_wait(h_ready, ph);
-        ph ^= 1u;
+  const int hh = warp >> 2;
+  const int row = (warp & 3) * 32 + lane;
+  const int u0 = UN * hh;
+  const uint32_t t_col = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)u0;
+  uint32_t ph = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long cell = tile * CELLS + row;
+    const bool live = cell < cells;
+    float c[UN], h[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) { c[u] = 0.f; h[u] = 0.f; }
+    const size_t xb = live ? x_base(cell, T, NN) : 0;
+    float xv = live ? x_seq[xb] : 0.f;
+    __half* my_save = SAVE ? saved + (size_t)tile * T * (SAVE_CHUNKS * CELLS * 8) + (size_t)(2 * hh) * CELLS * 8 + (size_t)row * 8 : nullptr;
+    for (int t = 0; t < T; ++t) {
+      // hx_t = [h_{t-1} | x_t ...]: the tile is free (the MMA of step t-1 was waited for before h_{t-1} was computed)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) *reinterpret_cast<uint4*>(sHX + sw128_off(row, 2 * hh + q)) = pack8(h + 8 * q);
+      if (hh == 0) {
+        const float x_hi = __half2float(__float2half_rn(xv));
+        *reinterpret_cast<uint4*>(sHX + sw128_off(row, 4)) = make_uint4(pack2(x_hi, 1.f), pack2(xv - x_hi, x_hi), pack2(1.f, 0.f), 0u);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();                 // also orders this thread's TMEM reads of step t-1 before the MMA that overwrites them
+      __syncthreads();
+      if (warp == 0) {
         tc_fence_after();
         if (lane == 0) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_f16(tmem_base, umma_desc(hi, a_addr + k * 32, 16), umma_desc(hi, b_addr + k * 32, 16), idesc, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 3; ++k)
+            umma_f16(tmem_base, umma_desc(hi128, a_addr + k * 32, 16), umma_desc(hi128, b_addr + k * 32, 16), idesc, k > 0 ? 1u : 0u);
           umma_commit(g_ready);
         }
         __syncwarp();
       }
+      xv = (live && t + 1 < T) ? x_seq[xb + (size_t)(t + 1) * NN] : 0.f;     // next step's input, requested under the MMA
+      mbar_wait(g_ready, ph);
+      ph ^= 1u;
+      tc_fence_after();
+      {
+        uint32_t ra[UN], rb[UN];
+        float ig[UN];
+        tmem_ld_32x16(t_col + 0 * C, ra);
+        tmem_ld_32x16(t_col + 2 * C, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          // accumulators are -log2e * pre (i, f, o) and -2 log2e * pre (g); clamp from above only (ex2(-big) = 0 is fine),
+          // which keeps the product of two (1 + 2^arg) terms below 1e26
+          const float ai = 1.f + ex2_(fminf(__uint_as_float(ra[u]), 43.280851f));
+          const float ag = 1.f + ex2_(fminf(__uint_as_float(rb[u]), 43.280851f));
+          const float r = rcp_(ai * ag);
+          ig[u] = (r * ag) * fmaf(r + r, ai, -1.f);          // sigmoid(i) * tanh(g)
+        }
+        tmem_ld_32x16(t_col + 1 * C, ra);
+        tmem_ld_32x16(t_col + 3 * C, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const float af = 1.f + ex2_(fminf(__uint_as_float(ra[u]), 43.280851f));
+          const float ao = 1.f + ex2_(fminf(__uint_as_float(rb[u]), 43.280851f));
+          const float r = rcp_(af * ao);
+          c[u] = fmaf(r * ao, c[u], ig[u]);
+          h[u] = (r * af) * tanh_(c[u]);
+        }
+      }
+      if (SAVE) {                     // training: c_t and h_t (fp16) for the backward kernel, see save_at()
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          *save_at(my_save, t, q) = pack8(c + 8 * q);
+          *save_at(my_save, t, 4 + q) = pack8(h + 8 * q);
+        }
+      }
     }
-  } else {
-    const int hh = warp >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const int u0 = UN * hh;
-    const uint32_t t_col = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)u0;
-    uint32_t ph = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const long long cell = tile * CELLS + row;
-      const bool live = cell < cells;
-      float c[UN], h[UN];
+    if (live) {
+      float4* dst = reinterpret_cast<float4*>(hT + (size_t)cell * C + u0);
 #pragma unroll
-      for (int u = 0; u < UN; ++u) c[u] = 0.f;
-      const size_t xb = live ? x_base(cell, T, NN) : 0;
-      float xv = live ? x_seq[xb] : 0.f;
-      __half* my_save = SAVE ? saved + (size_t)tile * T * (SAVE_CHUNKS * CELLS * 8) + (size_t)(2 * hh) * CELLS * 8 + (size_t)row * 8 : nullptr;
-      for (int t = 0; t < T; ++t) {
-        const float xn = (live && t + 1 < T) ? x_seq[xb + (size_t)(t + 1) * NN] : 0.f;   // prefetch next step's input
-        if (t > 0) {
-          mbar_wait(g_ready, ph);
-          ph ^= 1u;
-          tc_fence_after();
-        }
-        cell_step<false, (MPGCN_LSTM_FWD_PAIRED != 0)>(t_col, t > 0, xv, s_bias, s_wih, u0, c, h, nullptr, 0, hh);
-        if (SAVE) {                     // training: c_t and h_t (fp16) for the backward kernel, see save_at()
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            *save_at(my_save, t, q) = pack8(c + 8 * q);
-            *save_at(my_save, t, 4 + q) = pack8(h + 8 * q);
-          }
-        }
-        if (t + 1 < T) {
-          write_h_tile(sH, row, hh, h);
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(h_ready);
-        }
-        xv = xn;
-      }
-      if (live) {
-        float4* dst = reinterpret_cast<float4*>(hT + (size_t)cell * C + u0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-      }
+      for (int q = 0; q < 4; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
 // ---------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------
-constexpr int DA_BYTES = 32768;     // [128 cells][128 gates] fp16 as two [128][64] SW128 sub-tiles
-constexpr int HX_BYTES = 16384;     // [128 cells][64] fp16, SW128
 
 #ifndef MPGCN_LSTM_BWD_LB
 #define MPGCN_LSTM_BWD_LB 0
@@ -675,25 +715,6 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
 //     MMA1: dh_{t-1}     = da_t (K-major) x W_hh
 //     MMA2: dWext       += da_t^T (MN-major) x hx_t              (cols 0..31 dW_hh, 32 + 34 dW_ih, 33 db)
 // TMEM: gates 0..127 | dh 128..159 | dWext 160..223 | dc 224..255.
-constexpr int WX_BYTES = 16384;     // [128 gates][64] fp16, SW128
-
-__device__ void load_weights_ext(uint8_t* sWx, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh) {
-  for (int e = threadIdx.x; e < G4 * 8; e += blockDim.x) {
-    const int j = e >> 3, ch = e & 7;
-    const float sc = ((j >> 5) == 2) ? -2.8853900817779268f : -1.4426950408889634f;
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (ch < 4) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = sc * w_hh[j * C + ch * 8 + i];
-    } else if (ch == 4) {
-      const float wi = sc * w_ih[j], bb = sc * (b_ih[j] + b_hh[j]);
-      const float wi_hi = __half2float(__float2half_rn(wi)), b_hi = __half2float(__float2half_rn(bb));
-      v[0] = wi_hi; v[1] = b_hi; v[2] = wi_hi; v[3] = wi - wi_hi; v[4] = bb - b_hi;
-    }
-    *reinterpret_cast<uint4*>(sWx + sw128_off(j, ch)) = pack8(v);
-  }
-}
-
 constexpr int BWD_THREADS = 256;    // 8 warps, all of them epilogue warps; warp 0 also issues the MMAs (see kernel comment)
 
 __global__ void __launch_bounds__(BWD_THREADS, 2)
@@ -975,7 +996,7 @@ size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN) {
 
 // dynamic shared memory requests: just what the kernels carve (registers already limit residency to two CTAs per SM,
 // whose TMEM allocations -- 2 x 128 / 2 x 256 columns -- always fit); the rest of the 228 KB stays L1
-static const int kLstmFwdSmem = 24 * 1024;
+static const int kLstmFwdSmem = 34 * 1024;
 static const int kLstmSmem = 72 * 1024;
 static const int kLstmSavedSmem = 94 * 1024;     // saved-state backward: + second hx buffer + extended weight tile
 
@@ -999,10 +1020,10 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
   }
   prof_begin(PROF_LSTM_FWD, 8.0 * C * (C + 1) * (double)cells * T, st);
   if (saved)
-    lstm_fwd_tc_kernel<true><<<lstm_grid(cells), THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, static_cast<__half*>(saved),
+    lstm_fwd_tc_kernel<true><<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, static_cast<__half*>(saved),
                                                                           cells, T, NN);
   else
-    lstm_fwd_tc_kernel<false><<<lstm_grid(cells), THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, nullptr, cells, T, NN);
+    lstm_fwd_tc_kernel<false><<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, nullptr, cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
