@@ -390,30 +390,40 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
       ph ^= 1u;
       tc_fence_after();
       {
+        // Seven SFU operations per hidden unit and step (5 ex2 + 2 rcp): i, g, f share one reciprocal of the product of their
+        // three (1 + 2^arg) terms, o and tanh(c) share another.  The accumulators are -log2e * pre (i, f, o) and -2 log2e * pre
+        // (g); arguments are clamped from above at 40 (ex2(-big) = 0 is fine), so a triple product stays below 1.4e36; the
+        // clamp moves sigmoid / tanh by < 1e-12.
         uint32_t ra[UN], rb[UN];
-        float ig[UN];
+        float p[UN];                      // a_i * a_g, later o's (1 + 2^arg) term
         tmem_ld_32x16(t_col + 0 * C, ra);
         tmem_ld_32x16(t_col + 2 * C, rb);
         tmem_ld_wait();
+        float ai[UN], ag[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-          // accumulators are -log2e * pre (i, f, o) and -2 log2e * pre (g); clamp from above only (ex2(-big) = 0 is fine),
-          // which keeps the product of two (1 + 2^arg) terms below 1e26
-          const float ai = 1.f + ex2_(fminf(__uint_as_float(ra[u]), 43.280851f));
-          const float ag = 1.f + ex2_(fminf(__uint_as_float(rb[u]), 43.280851f));
-          const float r = rcp_(ai * ag);
-          ig[u] = (r * ag) * fmaf(r + r, ai, -1.f);          // sigmoid(i) * tanh(g)
+          ai[u] = 1.f + ex2_(fminf(__uint_as_float(ra[u]), 40.f));
+          ag[u] = 1.f + ex2_(fminf(__uint_as_float(rb[u]), 40.f));
         }
         tmem_ld_32x16(t_col + 1 * C, ra);
         tmem_ld_32x16(t_col + 3 * C, rb);
         tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-          const float af = 1.f + ex2_(fminf(__uint_as_float(ra[u]), 43.280851f));
-          const float ao = 1.f + ex2_(fminf(__uint_as_float(rb[u]), 43.280851f));
-          const float r = rcp_(af * ao);
-          c[u] = fmaf(r * ao, c[u], ig[u]);
-          h[u] = (r * af) * tanh_(c[u]);
+          const float af = 1.f + ex2_(fminf(__uint_as_float(ra[u]), 40.f));
+          const float pig = ai[u] * ag[u];
+          const float r = rcp_(pig * af);
+          const float gi = r * (ag[u] * af);                    // sigmoid(i)
+          const float gg = fmaf(r + r, ai[u] * af, -1.f);       // tanh(g)
+          const float gf = r * pig;                             // sigmoid(f)
+          c[u] = fmaf(gf, c[u], gi * gg);
+          p[u] = 1.f + ex2_(fminf(__uint_as_float(rb[u]), 40.f));
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const float ac = 1.f + ex2_(fminf(-2.8853900817779268f * c[u], 40.f));
+          const float r = rcp_(p[u] * ac);
+          h[u] = (r * ac) * fmaf(r + r, p[u], -1.f);            // sigmoid(o) * tanh(c)
         }
       }
       if (SAVE) {                     // training: c_t and h_t (fp16) for the backward kernel, see save_at()
@@ -880,15 +890,16 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           // accumulators are -log2e * pre (i, f, o) and -2 log2e * pre (g); clamp from above only (ex2(-big) = 0 is fine),
-          // which keeps the product of two (1 + 2^arg) terms below 1e26
-          const float ai = 1.f + ex2_(fminf(__uint_as_float(ri[e]), 43.280851f));
-          const float ag = 1.f + ex2_(fminf(__uint_as_float(rg[e]), 43.280851f));
-          const float af = 1.f + ex2_(fminf(__uint_as_float(rf[e]), 43.280851f));
-          const float ao = 1.f + ex2_(fminf(__uint_as_float(ro[e]), 43.280851f));
-          const float r1 = rcp_(ai * ag), r2 = rcp_(af * ao);
-          const float gi = r1 * ag, gg = fmaf(r1 + r1, ai, -1.f);
-          const float gf = r2 * ao, go = r2 * af;
-          const float tcv = tanh_(fc[e]);
+          // which keeps the product of three (1 + 2^arg) terms below 1.4e36
+          const float ai = 1.f + ex2_(fminf(__uint_as_float(ri[e]), 40.f));
+          const float ag = 1.f + ex2_(fminf(__uint_as_float(rg[e]), 40.f));
+          const float af = 1.f + ex2_(fminf(__uint_as_float(rf[e]), 40.f));
+          const float ao = 1.f + ex2_(fminf(__uint_as_float(ro[e]), 40.f));
+          const float ac = 1.f + ex2_(fminf(-2.8853900817779268f * fc[e], 40.f));
+          const float pig = ai * ag;
+          const float r1 = rcp_(pig * af), r2 = rcp_(ao * ac);      // 7 SFU ops per unit: see the forward kernel
+          const float gi = r1 * (ag * af), gg = fmaf(r1 + r1, ai * af, -1.f), gf = r1 * pig;
+          const float go = r2 * ac, tcv = fmaf(r2 + r2, ao, -1.f);
           const float dhv = __uint_as_float(rdh[e]);
           const float dcv = fmaf(dhv * go, fmaf(-tcv, tcv, 1.f), __uint_as_float(rdc[e]));
           d_o[e] = (dhv * tcv) * fmaf(-go, go, go);
