@@ -73,10 +73,10 @@ int map_flat(CUtensorMap* m, const __half* t, long long cols, long long k_rows, 
   return make_tmap_f16(m, t, 4, dims, str, box, TMAP_SW64);
 }
 // K-major plane tensor T[plane][rows][32]: dims (k=32, row, plane, 1), box (32, 128)
-int map_planes(CUtensorMap* m, const __half* t, long long rows, long long planes) {
+int map_planes(CUtensorMap* m, const __half* t, long long rows, long long planes, int box_planes = 1) {
   const uint64_t dims[4] = {32, (uint64_t)rows, (uint64_t)planes, 1};
   const uint64_t str[3] = {64, (uint64_t)rows * 64, (uint64_t)rows * 64 * (uint64_t)planes};
-  const uint32_t box[4] = {32, 128, 1, 1};
+  const uint32_t box[4] = {32, 128, (uint32_t)box_planes, 1};
   return make_tmap_f16(m, t, 4, dims, str, box, TMAP_SW64);
 }
 }  // namespace
@@ -218,18 +218,34 @@ static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, in
   const long long NN = (long long)s.N * s.N;
   GemmParams p;
   init_params(p);
-  if (int e = map_planes(&p.a_map, a16, NN, (long long)s.B * K)) return e;
-  if (int e = map_chunks(&p.b_map, w16, (long long)K * 32, 32, K, (long long)K * 32 * 32, w_halves, (long long)K * K * 32 * 32, 32, K)) return e;
-  // segment s: plane = b*K + (s % K); weight rows (s % K)*32 of half s / K  (half 0 = fp16(W), half 1 = fp16(W - half 0))
-  p.am = omap(1, kBig, K, 1, 0, K, 0);
-  p.bm = omap(1, 1, 0, 0, 32, K, 1);
+  static int mode = -1;     // A/B knob: 0 default, 1 = W streams with A (one plane per k-block), 2 = W resident, one plane per k-block
+  if (mode < 0) { const char* e = getenv("MPGCN_B200_MIX_MODE"); mode = e ? atoi(e) : 0; }
+  const size_t w_bytes = (size_t)K * w_halves * K * 32 * 64;      // K * w_halves tiles of K chunks x [32 k][64 B]
+  int bk = 32;
+  if (mode == 0 && (K == 2 || K == 3)) {
+    // One k-block per tile: a single TMA box brings the K planes of a 128-cell tile (the single-thread producer / MMA loops
+    // cost ~0.3 us per k-block, which bounded the per-plane version at a third of the HBM rate), W resident in shared memory
+    bk = 32 * K;
+    if (int e = map_planes(&p.a_map, a16, NN, (long long)s.B * K, K)) return e;
+    if (int e = map_chunks(&p.b_map, w16, (long long)K * 32, 32, K, (long long)K * 32 * 32, w_halves, (long long)K * K * 32 * 32, bk, K)) return e;
+    p.am = omap(1, kBig, K, 0, 0);                 // z = b -> first plane b*K
+    p.bm = omap(1, 1, 0, 1, 0);                    // resident tile index = weight half
+    p.kb_total = 1; p.kb_per_seg = 1; p.b_res_reps = w_halves;
+  } else {
+    if (int e = map_planes(&p.a_map, a16, NN, (long long)s.B * K)) return e;
+    if (int e = map_chunks(&p.b_map, w16, (long long)K * 32, 32, K, (long long)K * 32 * 32, w_halves, (long long)K * K * 32 * 32, 32, K)) return e;
+    // segment s: plane = b*K + (s % K); weight rows (s % K)*32 of half s / K  (half 0 = fp16(W), half 1 = fp16(W - half 0))
+    p.am = omap(1, kBig, K, 1, 0, K, 0);
+    p.bm = omap(1, 1, 0, 0, 32, K, 1);
+    if (mode == 1 || w_bytes > 160 * 1024) { p.kb_total = K * w_halves; p.kb_per_seg = 1; }      // large K: W streams with A
+    else { p.kb_total = K; p.kb_per_seg = 1; p.b_res_reps = w_halves; }                           // W resident, A plane by plane
+  }
   p.MT = ceil_div(NN, 128); p.NT = 1; p.Z = s.B; p.R = K;
-  p.kb_total = K * w_halves; p.kb_per_seg = 1;
   p.ep.out = d16; p.ep.out_f16 = 1;
   p.ep.sZ = (long long)K * NN * 32; p.ep.sI = 32; p.ep.sR = NN * 32;
   p.ep.m_valid = (int)NN; p.ep.r_valid = K;
   prof_set_next(tag, 2.0 * s.B * (double)K * K * NN * 32 * 32);   // algorithmic flops (the fp16 hi/lo weight split doubles the executed MMAs)
-  return tc::launch_contract(tc::A_K64, 32, p, st);
+  return tc::launch_contract(tc::A_K64, bk, p, st);
 }
 
 // FWD_B: out[b][m][e][h] = act( sum_{(o,n)} Gflat[(o,n)][m] U16[b][(o,n)][e][h] + bias[h] )

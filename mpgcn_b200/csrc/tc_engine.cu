@@ -166,14 +166,24 @@ static int launch_impl(GemmParams& p, cudaStream_t stream) {
   }
   MPGCN_CHECK(p.R >= 1 && p.R <= 8, "R=%d out of range", p.R);
   // N of the UMMA must be a multiple of 16 for M=128: R odd -> N=32R is still a multiple of 32. ok.
-  const size_t stage_bytes = (size_t)C::A_STAGE + (size_t)p.R * BK * 64;
-  int stages = (int)((kMaxSmem - 1024 - 512) / stage_bytes);
-  if (stages > 8) stages = 8;
+  const size_t b_stage = (size_t)p.R * BK * 64;
+  const int nres = p.b_res_reps * p.kb_total;
+  int stages;
+  if (nres) {
+    MPGCN_CHECK(p.NT == 1 && p.kb_per_seg == 1 && !p.split_k && !p.b_flat && p.bm.z_mul == 0, "resident B needs a tile-independent B operand");
+    MPGCN_CHECK((size_t)nres * b_stage + 2 * (size_t)C::A_STAGE + 1536 <= (size_t)kMaxSmem, "resident B operand does not fit in shared memory");
+    stages = (int)((kMaxSmem - 1024 - 512 - (size_t)nres * b_stage) / (size_t)C::A_STAGE);
+  } else {
+    stages = (int)((kMaxSmem - 1024 - 512) / ((size_t)C::A_STAGE + b_stage));
+  }
+  // small stages (channel mixes, 8 KB of A per k-block) are HBM-latency bound: keep >= 128 KB of loads in flight per SM
+  const int max_stages = ((size_t)C::A_STAGE + (nres ? 0 : b_stage) <= 16384) ? 16 : 8;
+  if (stages > max_stages) stages = max_stages;
   MPGCN_CHECK(stages >= 2, "tile does not fit in shared memory");
   p.stages = stages;
   // always request the full opt-in budget: exactly one CTA per SM, so the 512-column TMEM allocation never contends
   const size_t smem = kMaxSmem;
-  MPGCN_CHECK(smem_bytes(C::A_STAGE, p.R, BK, stages) <= smem, "internal: smem budget");
+  MPGCN_CHECK(smem_bytes(C::A_STAGE, p.R, BK, stages, nres) <= smem, "internal: smem budget");
   const long long tiles = (long long)p.MT * p.NT * p.Z;
   MPGCN_CHECK(tiles > 0 && tiles < (1ll << 31), "bad tile count %lld", tiles);
   MPGCN_CHECK(p.kb_total > 0 && p.kb_per_seg > 0, "empty contraction");
@@ -183,7 +193,7 @@ static int launch_impl(GemmParams& p, cudaStream_t stream) {
   g_prof.next_tag = -1;
   g_prof.next_flops = 0;
   prof_begin(tag, fl, stream);
-  contract_kernel<AK, BK><<<grid, kThreads, smem, stream>>>(p);
+  contract_kernel<AK, BK><<<grid, kThreads1, smem, stream>>>(p);
   prof_end(stream);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
@@ -262,6 +272,8 @@ int launch_contract(int ak, int bk, GemmParams& p, cudaStream_t stream) {
   if (ak == A_MN128 && bk == 64) return launch_impl<A_MN128, 64>(p, stream);
   if (ak == A_K128 && bk == 64) return launch_impl<A_K128, 64>(p, stream);
   if (ak == A_K64 && bk == 32) return launch_impl<A_K64, 32>(p, stream);
+  if (ak == A_K64 && bk == 64) return launch_impl<A_K64, 64>(p, stream);
+  if (ak == A_K64 && bk == 96) return launch_impl<A_K64, 96>(p, stream);
   if (ak == A_MN64 && bk == 64) return launch_impl<A_MN64, 64>(p, stream);
   set_error("no contraction kernel for A kind %d, BK %d", ak, bk);
   return 1;

@@ -13,7 +13,7 @@
 //     A_MN64  : A is [k][chunk][32]            (Z for the weight gradient dW = Z^T V)
 //     B       : always [k][chunk r][32 ch], 64-byte rows, SWIZZLE_64B, MN-major
 // * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-//   warps 2..5 = epilogue (TMEM -> registers -> global).  Two TMEM accumulators
+//   warps 2..9 = epilogue (TMEM -> registers -> global; 2..5 in the 2-CTA kernel).  Two TMEM accumulators
 //   (2 x 256 columns) let the epilogue of tile t overlap the MMAs of tile t+1.
 //
 // Reference math being evaluated: BDGCN.forward, /root/reference/MPGCN.py:24-50, in the
@@ -63,17 +63,26 @@ struct alignas(64) GemmParams {
   int kb_total, kb_per_seg;  // k-blocks over all segments / per segment
   int split_k, kb_per_slice; // split-K: z is a k-slice [z*kb_per_slice, ...)
   int stages;
+  // resident B (channel mixes): the whole B operand -- b_res_reps * kb_total tiles, index rep * kb_total + kb -- is loaded
+  // once per CTA and every A k-block is multiplied by its b_res_reps tiles (the fp16 hi / lo halves of W); 0 = B streams
+  // through the ring with A.  Needs NT == 1, kb_per_seg == 1, no split-K, a z-independent B map.
+  int b_res_reps;
   int nt_fastest;            // tile order: 0 = m-tiles vary fastest (default), 1 = n-tiles vary fastest
   Epilogue ep;
 };
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;        // 2-CTA kernel: producer, MMA, 4 epilogue warps
+constexpr int kEpiWarps1 = 8;        // 1-CTA kernel: 8 epilogue warps (two per TMEM lane quarter, alternating chunks): with one warp per
+                                     // scheduler the TMEM -> convert -> store chain of the channel mixes (short MMAs, 3 chunks per
+                                     // tile) ran at ~0.3 IPC and bounded the kernel at half the HBM rate
+constexpr int kThreads1 = 64 + 32 * kEpiWarps1;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
 
 template <int AK, int BK>
 struct Cfg {
-  static constexpr int A_STAGE = (AK == A_MN128) ? BK * 256 : (AK == A_K128) ? 128 * 128 : (AK == A_K64) ? 128 * 64 : 4 * BK * 64;
+  // A_K64 with BK = 32 P: P planes per k-block, one [128 m][64 B] slab each (a single TMA box over the plane dimension)
+  static constexpr int A_STAGE = (AK == A_MN128) ? BK * 256 : (AK == A_K128) ? 128 * 128 : (AK == A_K64) ? 128 * 64 * (BK / 32) : 4 * BK * 64;
   static constexpr bool A_MN = (AK == A_MN128) || (AK == A_MN64);
   // byte advance of the A descriptor start address per UMMA (K = 16)
   static constexpr uint32_t A_KSTEP = (AK == A_MN128) ? 16 * 128 : (AK == A_MN64) ? 16 * 64 : 32;
@@ -84,12 +93,18 @@ struct Cfg {
   static constexpr uint32_t B_LBO = BK * 64;
   static constexpr uint32_t B_SBO = 512;
   static_assert(AK != A_K128 || BK == 64, "K-major SW128 rows hold exactly 64 halves");
-  static_assert(AK != A_K64 || BK == 32, "K-major SW64 rows hold exactly 32 halves");
+  static_assert(AK != A_K64 || BK % 32 == 0, "K-major SW64 rows hold exactly 32 halves: BK counts whole planes");
+  // byte offset of the A descriptor for the k-th UMMA (K = 16) of a k-block
+  __host__ __device__ static constexpr uint32_t a_koff(int k) {
+    return (AK == A_K64) ? (uint32_t)(k >> 1) * 8192u + (uint32_t)(k & 1) * 32u : (uint32_t)k * A_KSTEP;
+  }
   static_assert(BK % 16 == 0, "UMMA K is 16 for fp16");
 };
 
-__host__ __device__ inline size_t smem_bytes(int a_stage, int R, int BK, int stages) {
-  return 1024 /*align slack*/ + (size_t)stages * (a_stage + (size_t)R * BK * 64) + 512 /*barriers, tmem slot, bias*/;
+__host__ __device__ inline size_t smem_bytes(int a_stage, int R, int BK, int stages, int b_resident_tiles = 0) {
+  const size_t b_stage = (size_t)R * BK * 64;
+  return 1024 /*align slack*/ + (size_t)stages * a_stage + (size_t)(b_resident_tiles ? b_resident_tiles : stages) * b_stage +
+         512 /*barriers, tmem slot, bias*/;
 }
 
 #ifdef __CUDACC__
@@ -146,7 +161,7 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, float alpha, con
 }
 
 template <int AK, int BK>
-__global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kThreads1, 1) contract_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<AK, BK>;
   constexpr int A_STAGE = C::A_STAGE;
   const int R = p.R;
@@ -155,13 +170,15 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int NRES = p.b_res_reps * p.kb_total;       // resident B tiles (0: B goes through the ring)
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)S * A_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)S * B_STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)(NRES ? NRES : S) * B_STAGE);
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bres_full = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
   float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -176,8 +193,9 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], kEpiWarps1);
     }
+    mbar_init(bres_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -197,6 +215,13 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (NRES && (int)blockIdx.x < num_tiles) {      // the whole B operand, once
+        mbar_arrive_expect_tx(bres_full, (uint32_t)(NRES * B_STAGE));
+        for (int sg = 0; sg < NRES; ++sg) {
+          const int lo = sg % p.bm.seg_mod, hi = sg / p.bm.seg_mod;
+          tma_load_4d(sB + (size_t)sg * B_STAGE, &p.b_map, bres_full, 0, lo * p.bm.k_seg, 0, lo * p.bm.seg_mul + hi * p.bm.seg_hi_mul);
+        }
+      }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int mt = t % p.MT;
         const int rest = t / p.MT;
@@ -214,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
         int sb_lo = seg % p.bm.seg_mod, sb_hi = seg / p.bm.seg_mod;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)(A_STAGE + B_STAGE));
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(A_STAGE + (NRES ? 0 : B_STAGE)));
           const int zA = zA0 + sa_lo * p.am.seg_mul + sa_hi * p.am.seg_hi_mul;
           const int zB = zB0 + sb_lo * p.bm.seg_mul + sb_hi * p.bm.seg_hi_mul;
           const int kA = kk * BK + sa_lo * p.am.k_seg;
@@ -229,7 +254,9 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
           } else {                      // A_MN64: dims (ch, k, chunk, z), 4 chunks per tile
             tma_load_4d(a_dst, &p.a_map, &full[stage], 0, kA, mt * 4, zA);
           }
-          if (!p.b_flat) {              // dims (ch, k, r, z)
+          if (NRES) {
+            // B is resident
+          } else if (!p.b_flat) {       // dims (ch, k, r, z)
             tma_load_4d(b_dst, &p.b_map, &full[stage], 0, kB, nt * R, zB);
           } else {                      // dims (col, k, z, 1): one 32-column box per chunk
             for (int j = 0; j < R; ++j)
@@ -253,6 +280,10 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
     const uint32_t idesc = umma_idesc_f16(128, 32 * R, C::A_MN ? 1 : 0, 1);
     const uint64_t a_hi = umma_desc_hi(C::A_SBO, C::A_LAYOUT);
     const uint64_t b_hi = umma_desc_hi(C::B_SBO, 4u);
+    if (NRES && (int)blockIdx.x < num_tiles) {
+      mbar_wait(bres_full, 0);
+      tc_fence_after();
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int z = (t / p.MT) / p.NT;
       const int kb0 = p.split_k ? z * p.kb_per_slice : 0;
@@ -265,12 +296,15 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE);
-          const uint32_t b_addr = smem_u32(sB + (size_t)stage * B_STAGE);
+          const int reps = NRES ? p.b_res_reps : 1;
+          for (int rep = 0; rep < reps; ++rep) {
+            const uint32_t b_addr = smem_u32(sB + (size_t)(NRES ? rep * p.kb_total + kb : stage) * B_STAGE);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = umma_desc(a_hi, a_addr + k * C::A_KSTEP, C::A_LBO);
-            const uint64_t bd = umma_desc(b_hi, b_addr + k * C::B_KSTEP, C::B_LBO);
-            umma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = umma_desc(a_hi, a_addr + C::a_koff(k), C::A_LBO);
+              const uint64_t bd = umma_desc(b_hi, b_addr + k * C::B_KSTEP, C::B_LBO);
+              umma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0 || rep > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);                 // frees this smem stage when the MMAs retire
           if (kb == kb1 - 1) umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
@@ -282,8 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
       if (acc == 0) acc_phase ^= 1u;
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    // ------------------------------ epilogue (warps 2..9) ------------------------------
     const int quarter = warp & 3;     // TMEM lane quarter this warp may access
+    const int jpar = (warp - 2) >> 2;  // which of the two warps of this quarter: takes chunks jpar, jpar + 2, ...
     const float alpha = p.ep.alpha_dev ? p.ep.alpha * __ldg(p.ep.alpha_dev) : p.ep.alpha;
     float amax = 0.f;
     int acc = 0;
@@ -312,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract_kernel(const __grid_cons
           any_corr |= (dl[sgi] != 0.f);
         }
       }
-      for (int j = 0; j < R; ++j) {
+      for (int j = jpar; j < R; j += kEpiWarps1 / 4) {
         uint32_t regs[32];
         tmem_ld_32x32(t_row + (uint32_t)j * 32, regs);
         tmem_ld_wait();
@@ -379,13 +414,15 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int NRES = p.b_res_reps * p.kb_total;       // resident B tiles (0: B goes through the ring)
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)S * A_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)S * B_STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)(NRES ? NRES : S) * B_STAGE);
   uint64_t* empty = full + S;
   uint64_t* tfull = empty + S;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bres_full = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
   float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5;
