@@ -17,24 +17,49 @@ __global__ void head_fwd_kernel(HeadPtrs p, const float* __restrict__ w /*[M][C]
                                 float* __restrict__ y, float* __restrict__ pre /*[M][cells] or null*/, long long cells, int C, int M) {
   const int sub = threadIdx.x & 7;
   const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
-  for (long long cell = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); cell < cells; cell += stride) {
-    float acc = 0.f;
+  constexpr int U = 4;               // cells per thread and iteration: U x M independent 16-byte loads in flight
+  for (long long cell0 = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); cell0 < cells; cell0 += U * stride) {
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.f;
     for (int m = 0; m < M; ++m) {
-      const float* g = p.g[m] + cell * C;
-      float s = 0.f;
-      for (int l = sub * 4; l < C; l += 32) {
-        const float4 v = *reinterpret_cast<const float4*>(g + l);
-        const float4 ww = *reinterpret_cast<const float4*>(w + m * C + l);
-        s += v.x * ww.x + v.y * ww.y + v.z * ww.z + v.w * ww.w;
+      float s[U];
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {          // issue every load of the iteration first (C <= 32: one float4 per thread and cell)
+        const long long cell = cell0 + u * stride;
+        v[u] = (cell < cells && sub * 4 < C) ? *reinterpret_cast<const float4*>(p.g[m] + cell * C + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      s += bias[m];
-      if (pre != nullptr && sub == 0) pre[(long long)m * cells + cell] = s;
-      acc += fmaxf(s, 0.f);
+      const float4 w0 = (sub * 4 < C) ? *reinterpret_cast<const float4*>(w + m * C + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        s[u] = v[u].x * w0.x + v[u].y * w0.y + v[u].z * w0.z + v[u].w * w0.w;
+        const long long cell = cell0 + u * stride;
+        if (C > 32 && cell < cells) {
+          const float* g = p.g[m] + cell * C;
+          for (int l = sub * 4 + 32; l < C; l += 32) {
+            const float4 vv = *reinterpret_cast<const float4*>(g + l);
+            const float4 ww = *reinterpret_cast<const float4*>(w + m * C + l);
+            s[u] += vv.x * ww.x + vv.y * ww.y + vv.z * ww.z + vv.w * ww.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        s[u] += __shfl_xor_sync(0xffffffffu, s[u], 1);
+        s[u] += __shfl_xor_sync(0xffffffffu, s[u], 2);
+        s[u] += __shfl_xor_sync(0xffffffffu, s[u], 4);
+        s[u] += bias[m];
+        const long long cell = cell0 + u * stride;
+        if (pre != nullptr && sub == 0 && cell < cells) pre[(long long)m * cells + cell] = s[u];
+        acc[u] += fmaxf(s[u], 0.f);
+      }
     }
-    if (sub == 0) y[cell] = acc / (float)M;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long cell = cell0 + u * stride;
+      if (sub == 0 && cell < cells) y[cell] = acc[u] / (float)M;
+    }
   }
 }
 
@@ -52,26 +77,40 @@ __global__ void head_bwd_kernel(HeadPtrs p, const float* __restrict__ w, const f
   for (int m = 0; m < M; ++m) {
     float wacc[4] = {0.f, 0.f, 0.f, 0.f}, bacc = 0.f;     // C <= 32 fast path; larger C falls through to smem atomics below
     float amax = 0.f;
-    for (long long cell = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); cell < cells; cell += stride) {
-      const float d = (pre[(long long)m * cells + cell] > 0.f) ? dy[cell] * inv_m : 0.f;
-      const float* g = p.g[m] + cell * C;
-      float* dg = p.dg[m] ? p.dg[m] + cell * C : nullptr;
-      for (int l = sub * 4; l < C; l += 32) {
-        const float4 v = *reinterpret_cast<const float4*>(g + l);
-        const float4 ww = *reinterpret_cast<const float4*>(w + m * C + l);
-        if (dg) {
-          const float4 o = make_float4(d * ww.x, d * ww.y, d * ww.z, d * ww.w);
-          *reinterpret_cast<float4*>(dg + l) = o;
-          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-        }
-        if (l < 32) {
-          wacc[0] += d * v.x; wacc[1] += d * v.y; wacc[2] += d * v.z; wacc[3] += d * v.w;
-        } else {
-          atomicAdd(&s_acc[m * (C + 1) + l], d * v.x); atomicAdd(&s_acc[m * (C + 1) + l + 1], d * v.y);
-          atomicAdd(&s_acc[m * (C + 1) + l + 2], d * v.z); atomicAdd(&s_acc[m * (C + 1) + l + 3], d * v.w);
-        }
+    constexpr int U = 4;             // cells per thread and iteration
+    for (long long cell0 = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); cell0 < cells; cell0 += U * stride) {
+      float d[U];
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {          // issue every load of the iteration first (C <= 32: one float4 per thread and cell)
+        const long long cell = cell0 + u * stride;
+        const bool ok = cell < cells;
+        d[u] = (ok && pre[(long long)m * cells + cell] > 0.f) ? dy[cell] * inv_m : 0.f;
+        v[u] = (ok && sub * 4 < C) ? *reinterpret_cast<const float4*>(p.g[m] + cell * C + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (sub == 0) bacc += d;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long cell = cell0 + u * stride;
+        if (cell >= cells) continue;
+        const float* g = p.g[m] + cell * C;
+        float* dg = p.dg[m] ? p.dg[m] + cell * C : nullptr;
+        for (int l = sub * 4; l < C; l += 32) {
+          const float4 vv = (l < 32) ? v[u] : *reinterpret_cast<const float4*>(g + l);
+          const float4 ww = *reinterpret_cast<const float4*>(w + m * C + l);
+          if (dg) {
+            const float4 o = make_float4(d[u] * ww.x, d[u] * ww.y, d[u] * ww.z, d[u] * ww.w);
+            *reinterpret_cast<float4*>(dg + l) = o;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          }
+          if (l < 32) {
+            wacc[0] += d[u] * vv.x; wacc[1] += d[u] * vv.y; wacc[2] += d[u] * vv.z; wacc[3] += d[u] * vv.w;
+          } else {
+            atomicAdd(&s_acc[m * (C + 1) + l], d[u] * vv.x); atomicAdd(&s_acc[m * (C + 1) + l + 1], d[u] * vv.y);
+            atomicAdd(&s_acc[m * (C + 1) + l + 2], d[u] * vv.z); atomicAdd(&s_acc[m * (C + 1) + l + 3], d[u] * vv.w);
+          }
+        }
+        if (sub == 0) bacc += d[u];
+      }
     }
     if (sub * 4 < C) {
 #pragma unroll
