@@ -725,21 +725,41 @@ lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
 //     MMA1: dh_{t-1}     = da_t (K-major) x W_hh
 //     MMA2: dWext       += da_t^T (MN-major) x hx_t              (cols 0..31 dW_hh, 32 + 34 dW_ih, 33 db)
 // TMEM: gates 0..127 | dh 128..159 | dWext 160..223 | dc 224..255.
-constexpr int BWD_THREADS = 256;    // 8 warps, all of them epilogue warps; warp 0 also issues the MMAs (see kernel comment)
+// x4 TMEM load / store (32 lanes x 4 columns)
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+template <int W> __device__ __forceinline__ void tmem_ld_w(uint32_t taddr, uint32_t (&r)[W]);
+template <> __device__ __forceinline__ void tmem_ld_w<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld_32x8(taddr, r); }
+template <> __device__ __forceinline__ void tmem_ld_w<4>(uint32_t taddr, uint32_t (&r)[4]) { tmem_ld_32x4(taddr, r); }
+template <int W> __device__ __forceinline__ void tmem_st_w(uint32_t taddr, const uint32_t (&r)[W]);
+template <> __device__ __forceinline__ void tmem_st_w<8>(uint32_t taddr, const uint32_t (&r)[8]) { tmem_st_32x8(taddr, r); }
+template <> __device__ __forceinline__ void tmem_st_w<4>(uint32_t taddr, const uint32_t (&r)[4]) { tmem_st_32x4(taddr, r); }
 
-__global__ void __launch_bounds__(BWD_THREADS, 2)
+// TPC = threads per cell: 2 (8 warps, 16 hidden units per thread, <= 128 registers) is what is launched; 4 (16 warps, 8 units per
+// thread, <= 64 registers) was measured 12-18 % slower on B200 (5.4 vs 6.0-6.4 ms) and is not instantiated.  Two CTAs are
+// resident per SM and a thread makes two passes of PW = UNT / 2 units per step.
+// No dedicated MMA warp: with 9 warps per CTA the register file only holds ONE CTA per SM at > 102 registers per thread
+// (18 warps -> 5 on one scheduler partition).  Every step ends in one CTA-wide barrier, after which lane 0 of warp 0 issues
+// the step's three MMA groups while everybody moves on.
+template <int TPC>
+__global__ void __launch_bounds__(128 * TPC, 2)
 lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                          const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ d_hT,
                          float* __restrict__ d_w_ih, float* __restrict__ d_w_hh, float* __restrict__ d_b, float* __restrict__ d_x,
                          const __half* __restrict__ saved, const float* __restrict__ scale2, long long cells, int T, long long NN) {
-  // No dedicated MMA warp: with 9 warps per CTA the register file only holds ONE CTA per SM at > 102 registers per thread
-  // (18 warps -> 5 on one scheduler partition); 8 warps x 2 CTAs x 128 registers fills it exactly.  Every step ends in one
-  // CTA-wide barrier, after which lane 0 of warp 0 issues the step's three MMA groups while everybody moves on.
+  constexpr int UNT = C / TPC;          // hidden units per thread
+  constexpr int PW = UNT / 2;           // units per pass
+  constexpr int NCH = UNT / 8;          // 16-byte chunks of c / h per thread and step
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sDA = smem;                               // 32 KB
-  uint8_t* sHX = smem + DA_BYTES;                    // 2 x 16 KB: hx_t in buffer t & 1
-  uint8_t* sWx = sHX + 2 * HX_BYTES;                 // 16 KB
+  uint8_t* sHX = smem + DA_BYTES;                    // 3 x 16 KB: hx_t in buffer t % 3 (staged while the MMAs of step t+2 may still read theirs)
+  uint8_t* sWx = sHX + 3 * HX_BYTES;                 // 16 KB
   uint8_t* sW = sWx + WX_BYTES;                      // 8 KB
   float* s_bias = reinterpret_cast<float*>(sW + 8192);
   float* s_wih = s_bias + G4;
@@ -750,8 +770,8 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   load_weights(sW, s_bias, s_wih, w_ih, w_hh, b_ih, b_hh);
   load_weights_ext(sWx, w_ih, w_hh, b_ih, b_hh);
-  // constant zero columns 40..63 of both hx buffers (chunks 5, 6, 7); chunks 0..4 are rewritten every step
-  for (int e = threadIdx.x; e < 2 * CELLS * 3; e += blockDim.x) {
+  // constant zero columns 40..63 of the hx buffers (chunks 5, 6, 7); chunks 0..4 are rewritten every step
+  for (int e = threadIdx.x; e < 3 * CELLS * 3; e += blockDim.x) {
     const int buf = e / (CELLS * 3), r = (e / 3) % CELLS, ch = 5 + e % 3;
     *reinterpret_cast<uint4*>(sHX + buf * HX_BYTES + sw128_off(r, ch)) = make_uint4(0u, 0u, 0u, 0u);
   }
@@ -778,34 +798,35 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
   const uint32_t da_addr = smem_u32(sDA), hx_addr = smem_u32(sHX);
   bool first_dw = true;               // meaningful in the issuing thread only
 
-  const int hh = warp >> 2;
+  const int us = warp >> 2;           // unit slice of this thread: units u0 .. u0 + UNT - 1
   const int row = (warp & 3) * 32 + lane;
-  const int u0 = UN * hh;
+  const int u0 = UNT * us;
+  const int ch0 = u0 >> 3;            // first 16-byte chunk of this thread's units
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t t_g = TM_GATES + lane_base + u0, t_dh = TM_DH + lane_base + u0, t_dc = TM_DC + lane_base + u0;
   uint32_t ph_ready = 0, ph_free = 0;
   bool mma2_pending = false;          // a weight-gradient MMA that reads sDA / an hx buffer may still be in flight
 
-  // stage hx_t: this thread's 16 units of h_{t-1} (or zeros at t = 0) and, from unit half 0, the x / 1 columns
+  // stage hx_t: this thread's units of h_{t-1} (or zeros at t = 0) and, from unit slice 0, the x / 1 columns
   auto stage_hx = [&](const __half* my_save, int t, float xt) {
-    uint8_t* buf = sHX + (t & 1) * HX_BYTES;
+    uint8_t* buf = sHX + (t % 3) * HX_BYTES;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint8_t* dst = buf + sw128_off(row, 2 * hh + q);
+    for (int q = 0; q < NCH; ++q) {
+      uint8_t* dst = buf + sw128_off(row, ch0 + q);
       if (t > 0) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(save_at(my_save, t - 1, 4 + q)) : "memory");
       } else {
         *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
       }
     }
-    if (hh == 0) {
+    if (us == 0) {
       const float x_hi = __half2float(__float2half_rn(xt));
       *reinterpret_cast<uint4*>(buf + sw128_off(row, 4)) = make_uint4(pack2(x_hi, 1.f), pack2(xt - x_hi, x_hi), pack2(1.f, 0.f), 0u);
     }
   };
   // ex2 arguments of step t from hx_t (48 of its 64 columns are live)
   auto issue_gates = [&](int t) {
-    const uint32_t a = hx_addr + (uint32_t)(t & 1) * HX_BYTES;
+    const uint32_t a = hx_addr + (uint32_t)(t % 3) * HX_BYTES;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
       umma_f16(TM_GATES, umma_desc(hi128, a + k * 32, 16), umma_desc(hi128, wx_addr + k * 32, 16), id_gates, k > 0 ? 1u : 0u);
@@ -815,7 +836,8 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
     const long long cell = tile * CELLS + row;
     const bool live = cell < cells;
     const size_t xb = live ? x_base(cell, T, NN) : 0;
-    const __half* my_save = saved + (size_t)tile * T * (SAVE_CHUNKS * CELLS * 8) + (size_t)(2 * hh) * CELLS * 8 + (size_t)row * 8;
+    // save_at(my_save, t, q) = chunk q of this thread's c_t units, save_at(my_save, t, 4 + q) = of its h_t units
+    const __half* my_save = saved + (size_t)tile * T * (SAVE_CHUNKS * CELLS * 8) + (size_t)ch0 * CELLS * 8 + (size_t)row * 8;
     if (mma2_pending) {                // last step of the previous tile
       mbar_wait(mma_free, ph_free);
       ph_free ^= 1u;
@@ -826,18 +848,18 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
     // seed dh (scaled d_hT) and dc (0) in TMEM
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      uint32_t r[8];
+      uint32_t r[PW];
 #pragma unroll
-      for (int e = 0; e < 8; e += 4) {
+      for (int e = 0; e < PW; e += 4) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) v = *reinterpret_cast<const float4*>(d_hT + (size_t)cell * C + u0 + 8 * q + e);
+        if (live) v = *reinterpret_cast<const float4*>(d_hT + (size_t)cell * C + u0 + PW * q + e);
         r[e] = __float_as_uint(v.x * S); r[e + 1] = __float_as_uint(v.y * S);
         r[e + 2] = __float_as_uint(v.z * S); r[e + 3] = __float_as_uint(v.w * S);
       }
-      tmem_st_32x8(t_dh + 8 * q, r);
+      tmem_st_w<PW>(t_dh + PW * q, r);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) r[e] = 0u;
-      tmem_st_32x8(t_dc + 8 * q, r);
+      for (int e = 0; e < PW; ++e) r[e] = 0u;
+      tmem_st_w<PW>(t_dc + PW * q, r);
     }
     tmem_st_wait();
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -852,13 +874,13 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
       }
       __syncwarp();
     }
-    uint4 vc[2];
+    uint4 vc[NCH];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) vc[q] = *save_at(my_save, T - 1, q);
+    for (int q = 0; q < NCH; ++q) vc[q] = *save_at(my_save, T - 1, q);
     for (int t = T - 1; t >= 0; --t) {
-      uint4 vcp[2];
+      uint4 vcp[NCH];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < NCH; ++q) {
         vcp[q] = make_uint4(0, 0, 0, 0);
         if (t > 0) vcp[q] = *save_at(my_save, t - 1, q);
       }
@@ -867,28 +889,32 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
       mbar_wait(mma_ready, ph_ready);    // ex2 arguments of this step and (t < T-1) dh_t
       ph_ready ^= 1u;
       tc_fence_after();
-      if (mma2_pending) {                // MMA2 of step t+1 retired: sDA and hx buffer (t+1) & 1 == (t-1) & 1 are free
-        mbar_wait(mma_free, ph_free);
-        ph_free ^= 1u;
-        mma2_pending = false;
-      }
-      if (t > 0) stage_hx(my_save, t - 1, x_cur);
+      if (t > 0) stage_hx(my_save, t - 1, x_cur);      // buffer (t-1) % 3: last read by the MMAs of step t+2, long retired
       float dx_acc = 0.f;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        uint32_t ri[8], rf[8], rg[8], ro[8], rdh[8], rdc[8];
-        tmem_ld_32x8(t_g + 0 * C + 8 * q, ri);
-        tmem_ld_32x8(t_g + 1 * C + 8 * q, rf);
-        tmem_ld_32x8(t_g + 2 * C + 8 * q, rg);
-        tmem_ld_32x8(t_g + 3 * C + 8 * q, ro);
-        tmem_ld_32x8(t_dh + 8 * q, rdh);
-        tmem_ld_32x8(t_dc + 8 * q, rdc);
+        uint32_t ri[PW], rf[PW], rg[PW], ro[PW], rdh[PW], rdc[PW];
+        tmem_ld_w<PW>(t_g + 0 * C + PW * q, ri);
+        tmem_ld_w<PW>(t_g + 1 * C + PW * q, rf);
+        tmem_ld_w<PW>(t_g + 2 * C + PW * q, rg);
+        tmem_ld_w<PW>(t_g + 3 * C + PW * q, ro);
+        tmem_ld_w<PW>(t_dh + PW * q, rdh);
+        tmem_ld_w<PW>(t_dc + PW * q, rdc);
         tmem_ld_wait();
-        float fc[8], fcp[8];
-        unpack8(vc[q], fc); unpack8(vcp[q], fcp);
-        float di[8], df[8], dg[8], d_o[8];
+        float fc[PW], fcp[PW];
+        if (PW == 8) {
+          unpack8(vc[q % NCH], fc); unpack8(vcp[q % NCH], fcp);
+        } else {                         // one chunk holds both passes: halves 4q .. 4q+3
+          const uint32_t c0 = q ? vc[0].z : vc[0].x, c1 = q ? vc[0].w : vc[0].y;
+          const uint32_t p0 = q ? vcp[0].z : vcp[0].x, p1 = q ? vcp[0].w : vcp[0].y;
+          const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&c0)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&c1));
+          const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&p0)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&p1));
+          fc[0] = a0.x; fc[1] = a0.y; fc[2] = a1.x; fc[3] = a1.y;
+          fcp[0] = b0.x; fcp[1] = b0.y; fcp[2] = b1.x; fcp[3] = b1.y;
+        }
+        float di[PW], df[PW], dg[PW], d_o[PW];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < PW; ++e) {
           // accumulators are -log2e * pre (i, f, o) and -2 log2e * pre (g); clamp from above only (ex2(-big) = 0 is fine),
           // which keeps the product of three (1 + 2^arg) terms below 1.4e36
           const float ai = 1.f + ex2_(fminf(__uint_as_float(ri[e]), 40.f));
@@ -908,23 +934,29 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
           dg[e] = (dcv * gi) * fmaf(-gg, gg, 1.f);
           rdc[e] = __float_as_uint(dcv * gf);
           if (d_x != nullptr) {
-            const int u = u0 + 8 * q + e;
+            const int u = u0 + PW * q + e;
             dx_acc += di[e] * s_wih[u] + df[e] * s_wih[C + u] + dg[e] * s_wih[2 * C + u] + d_o[e] * s_wih[3 * C + u];
           }
         }
-#define MPGCN_ST_DA(blk, arr)                                                                              \
-  *reinterpret_cast<uint4*>(sDA + (((blk) * 32 + u0 + 8 * q) >> 6) * 16384 +                               \
-                            sw128_off(row, (((blk) * 32 + u0 + 8 * q) & 63) >> 3)) = pack8(arr)
-        MPGCN_ST_DA(0, di);
-        MPGCN_ST_DA(1, df);
-        MPGCN_ST_DA(2, dg);
-        MPGCN_ST_DA(3, d_o);
-#undef MPGCN_ST_DA
-        tmem_st_32x8(t_dc + 8 * q, rdc);
+        if (q == 0 && mma2_pending) {    // MMA2 of step t+1 must have retired before sDA is overwritten; by now it has
+          mbar_wait(mma_free, ph_free);
+          ph_free ^= 1u;
+          mma2_pending = false;
+        }
+        // gate j = blk*32 + u0 + PW*q .. : sub-tile (j >> 6), 16-byte chunk ((j & 63) >> 3), byte (j & 7) * 2 inside the chunk
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+          const float* arr = blk == 0 ? di : blk == 1 ? df : blk == 2 ? dg : d_o;
+          const int j0 = blk * 32 + u0 + PW * q;
+          uint8_t* dst = sDA + (j0 >> 6) * 16384 + sw128_off(row, (j0 & 63) >> 3) + (j0 & 7) * 2;
+          if (PW == 8) *reinterpret_cast<uint4*>(dst) = pack8(arr);
+          else *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(arr[0], arr[1]), pack2(arr[2], arr[3]));
+        }
+        tmem_st_w<PW>(t_dc + PW * q, rdc);
       }
       if (d_x != nullptr && live) atomicAdd(&d_x[xb + (size_t)t * NN], dx_acc * invS);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) vc[q] = vcp[q];
+      for (int q = 0; q < NCH; ++q) vc[q] = vcp[q];
       tmem_st_wait();
       asm volatile("cp.async.wait_all;" ::: "memory");
       fence_proxy_async_smem();
@@ -933,7 +965,7 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
       if (warp == 0) {
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t hx = hx_addr + (uint32_t)(t & 1) * HX_BYTES;
+          const uint32_t hx = hx_addr + (uint32_t)(t % 3) * HX_BYTES;
           if (t > 0) {
             // dh_{t-1} = da (K-major, two 64-gate sub-tiles of [128 cells][128 B]) x W_hh (rows j, K step = 16 rows x 64 B)
 #pragma unroll
@@ -956,17 +988,21 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
       mma2_pending = true;
     }
   }
-  // ---- flush the weight-gradient accumulator: TMEM lane = gate row j, this thread's 16 columns ----
+  // ---- flush the weight-gradient accumulator: TMEM lane = gate row j, this thread's UNT columns ----
   if (mma2_pending) {
     mbar_wait(mma_free, ph_free);
     tc_fence_after();
-    uint32_t r[UN];
-    tmem_ld_32x16(TM_DW + lane_base + u0, r);
-    tmem_ld_wait();
 #pragma unroll
-    for (int k = 0; k < UN; ++k) atomicAdd(&d_w_hh[row * C + u0 + k], __uint_as_float(r[k]) * invS);
-    if (hh == 0) {
-      tmem_ld_32x16(TM_DW + lane_base + 32, r);
+    for (int q = 0; q < 2; ++q) {
+      uint32_t r[PW];
+      tmem_ld_w<PW>(TM_DW + lane_base + u0 + PW * q, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < PW; ++k) atomicAdd(&d_w_hh[row * C + u0 + PW * q + k], __uint_as_float(r[k]) * invS);
+    }
+    if (us == 0) {
+      uint32_t r[4];
+      tmem_ld_32x4(TM_DW + lane_base + 32, r);
       tmem_ld_wait();
       atomicAdd(&d_w_ih[row], (__uint_as_float(r[0]) + __uint_as_float(r[2])) * invS);
       atomicAdd(&d_b[row], __uint_as_float(r[1]) * invS);
@@ -1009,7 +1045,7 @@ size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN) {
 // whose TMEM allocations -- 2 x 128 / 2 x 256 columns -- always fit); the rest of the 228 KB stays L1
 static const int kLstmFwdSmem = 34 * 1024;
 static const int kLstmSmem = 72 * 1024;
-static const int kLstmSavedSmem = 94 * 1024;     // saved-state backward: + second hx buffer + extended weight tile
+static const int kLstmSavedSmem = 107 * 1024;     // saved-state backward: + second hx buffer + extended weight tile
 
 size_t lstm_tc_saved_bytes(int B, int T, long long NN) {
   const long long tiles = ((long long)B * NN + lstm_tc::CELLS - 1) / lstm_tc::CELLS;
@@ -1060,15 +1096,15 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   static bool attr = false;
   if (!attr) {
     MPGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmSmem));
-    MPGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_saved_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmSavedSmem));
+    MPGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_saved_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmSavedSmem));
     attr = true;
   }
   MPGCN_CHECK(smem <= (size_t)kLstmSmem, "internal: lstm backward smem");
   if (saved) {
     prof_begin(PROF_LSTM_BWD, 12.0 * C * (C + 1) * (double)cells * T, st);
-    static_assert(1024 + DA_BYTES + 2 * HX_BYTES + WX_BYTES + 8192 + 2 * G4 * sizeof(float) + 256 <= (size_t)kLstmSavedSmem, "smem");
-    lstm_bwd_saved_tc_kernel<<<lstm_grid(cells), BWD_THREADS, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
-                                                                           static_cast<const __half*>(saved), scale2, cells, T, NN);
+    static_assert(1024 + DA_BYTES + 3 * HX_BYTES + WX_BYTES + 8192 + 2 * G4 * sizeof(float) + 256 <= (size_t)kLstmSavedSmem, "smem");
+    lstm_bwd_saved_tc_kernel<2><<<lstm_grid(cells), 256, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
+                                                                               static_cast<const __half*>(saved), scale2, cells, T, NN);
   } else {
     prof_begin(PROF_LSTM_BWD, 16.0 * C * (C + 1) * (double)cells * T, st);
     lstm_bwd_tc_kernel<<<lstm_grid(cells), THREADS, kLstmSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x, scratch,
