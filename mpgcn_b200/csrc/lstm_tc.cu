@@ -3,23 +3,15 @@
 // Reference semantics: nn.LSTM(1, 32, 1, batch_first=True) over B*N*N independent cells with zero
 // initial state, last hidden state only (/root/reference/MPGCN.py:69,80-87,100-104); gate order i,f,g,o.
 //
-// Forward, per tile of 128 cells (TMEM lane = cell):
-//     gates[128 x 128] = H_{t-1}[128 x 32] (fp16, smem, K-major SW64)  x  W_hh^T (fp16, smem)   -> TMEM fp32
-//     epilogue: + b + w_ih*x_t, sigmoid/tanh (ex2/rcp on the SFU), c in registers (fp32), h -> fp16 -> smem
-// The recurrence rounds h to fp16 only as the MMA operand; c, the gate pre-activations and the returned h_T
-// stay fp32.
-//
-// Backward, per tile: (1) recompute the forward, stashing i,f,g,o,c,h (fp16) per step in a per-CTA scratch
-// ring (coalesced chunk-major layout); (2) walk back in time: da (fp16, power-of-two scaled) is written once to
-// shared memory and read by two MMAs through two different descriptors over the same bytes:
-//     dh_{t-1}[128 x 32]  = da[128 cells x 128 gates] (K-major)  x  W_hh[128 x 32]          -> TMEM, read back
-//     dWext[128 x 64]    += da^T (MN-major) x [h_{t-1} | x_t | 1 | 0..][128 cells x 64]     -> TMEM, accumulated
-// over every step and every tile of the CTA; columns 0..31 of dWext are dW_hh, column 32 dW_ih, column 33 db.
-//
-// Thread mapping: TWO threads per cell, each owning 16 of the 32 hidden units (8 epilogue warps per tile: warp w
-// serves TMEM lane quarter w % 4 and unit half w / 4), one MMA warp, two CTAs per SM.  The kernels are bound by
-// SFU throughput and by the latency of the per-step round trip through the tensor core, so the design maximises
-// resident warps (18 per SM) and keeps the per-thread state small enough to issue a whole step's loads at once.
+// Three kernels (details at each):
+//   lstm_fwd_tc_kernel<SAVE>       forward; SAVE additionally stores c_t, h_t (fp16) of every step for training
+//   lstm_bwd_saved_tc_kernel<2>    backward from that saved state: one reverse walk, gate MMA prefetched a step ahead
+//   lstm_bwd_tc_kernel             backward for callers without saved state: recomputes the forward per tile into a stash
+// Tile = 128 cells = the 128 TMEM lanes.  The gate GEMM of a step, affine part and ex2 scaling included, is ONE MMA
+// [128 cells x 48] . [48 x 128 gates] whose fp32 accumulator is the exponent argument of the activation; activations
+// cost 7 SFU operations per hidden unit and step.  The recurrence rounds h to fp16 only as MMA operand; c, the gate
+// arguments and the returned h_T stay fp32.  The first two kernels use 8-warp CTAs without a dedicated MMA warp so that
+// two CTAs stay resident per SM at 128 registers per thread (see lstm_bwd_saved_tc_kernel).
 #include "kernels.h"
 
 #include <stdlib.h>
