@@ -81,7 +81,8 @@ MPGCN_API int mpgcn_bdgcn_backward_ex(const float* d_out, const float* out, cons
  *   w_ih [4C,1], w_hh [4C,C], b_ih [4C], b_hh [4C]   (gate order i,f,g,o)
  *   hT   [B*NN, C]
  * precision 0: fp32 CUDA-core kernels (C <= 64); precision 1: tcgen05 gate GEMM with the recurrent h rounded to
- * fp16 as MMA operand, state and activations in fp32 (C == 32). */
+ * fp16 as MMA operand, state and activations in fp32 (C == 32); x enters that GEMM as an fp16 hi + lo pair, exact to
+ * ~22 bits for |x| < 65504 and saturating beyond. */
 MPGCN_API int mpgcn_lstm_precision_supported(int T, int C, int precision);
 MPGCN_API size_t mpgcn_lstm_bwd_workspace_bytes(int B, int T, long long NN, int C, int precision);
 MPGCN_API int mpgcn_lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,

@@ -41,6 +41,11 @@ __device__ __forceinline__ float rcp_(float x) { float y; asm("rcp.approx.ftz.f3
 __device__ __forceinline__ float sigm(float x) { return rcp_(1.f + ex2_(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_(float x) { return fmaf(2.f, rcp_(1.f + ex2_(-2.8853900817779268f * x)), -1.f); }
 
+// x enters the gate MMA as fp16 hi + lo (exact to ~22 bits for |x| < 65504); both parts saturate instead of overflowing to inf,
+// so larger inputs give finite (saturated-gate) results rather than NaN
+__device__ __forceinline__ float x_split_hi(float x) { return __half2float(__float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f))); }
+__device__ __forceinline__ float x_split_lo(float x, float hi) { return fminf(fmaxf(x - hi, -65504.f), 65504.f); }
+
 // x_seq is [B][T][NN]: element (cell, t) = x_base(cell) + t * NN; the 64-bit division is done once per tile
 __device__ __forceinline__ size_t x_base(long long cell, int T, long long NN) {
   const long long b = cell / NN;
@@ -361,8 +366,8 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
 #pragma unroll
       for (int q = 0; q < 2; ++q) *reinterpret_cast<uint4*>(sHX + sw128_off(row, 2 * hh + q)) = pack8(h + 8 * q);
       if (hh == 0) {
-        const float x_hi = __half2float(__float2half_rn(xv));
-        *reinterpret_cast<uint4*>(sHX + sw128_off(row, 4)) = make_uint4(pack2(x_hi, 1.f), pack2(xv - x_hi, x_hi), pack2(1.f, 0.f), 0u);
+        const float x_hi = x_split_hi(xv);
+        *reinterpret_cast<uint4*>(sHX + sw128_off(row, 4)) = make_uint4(pack2(x_hi, 1.f), pack2(x_split_lo(xv, x_hi), x_hi), pack2(1.f, 0.f), 0u);
       }
       fence_proxy_async_smem();
       tc_fence_before();                 // also orders this thread's TMEM reads of step t-1 before the MMA that overwrites them
@@ -812,8 +817,8 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
       }
     }
     if (us == 0) {
-      const float x_hi = __half2float(__float2half_rn(xt));
-      *reinterpret_cast<uint4*>(buf + sw128_off(row, 4)) = make_uint4(pack2(x_hi, 1.f), pack2(xt - x_hi, x_hi), pack2(1.f, 0.f), 0u);
+      const float x_hi = x_split_hi(xt);
+      *reinterpret_cast<uint4*>(buf + sw128_off(row, 4)) = make_uint4(pack2(x_hi, 1.f), pack2(x_split_lo(xt, x_hi), x_hi), pack2(1.f, 0.f), 0u);
     }
   };
   // ex2 arguments of step t from hx_t (48 of its 64 columns are live)

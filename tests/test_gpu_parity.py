@@ -108,13 +108,15 @@ def test_lstm_last_matches_reference_fixture(name, cuda_device):
         _check(x.grad[0].T, g["dx"][:, :, 0], tb, f"{prec}/dx")
 
 
-@pytest.mark.parametrize("S,T,gmag", [(1000, 12, 1.0), (300, 7, 1e-7), (129, 1, 1.0), (4097, 3, 1e3)])
-def test_lstm_tensor_path_agrees_with_fp32_path(S, T, gmag, cuda_device):
-    """Ragged tile counts, T = 1, tiny / huge gradient magnitudes: tcgen05 LSTM vs the fp32 CUDA-core LSTM."""
+@pytest.mark.parametrize("S,T,gmag,xmag", [(1000, 12, 1.0, 8.0), (300, 7, 1e-7, 8.0), (129, 1, 1.0, 8.0), (4097, 3, 1e3, 8.0),
+                                            (500, 6, 1.0, 3000.0), (256, 4, 1.0, 0.01)])
+def test_lstm_tensor_path_agrees_with_fp32_path(S, T, gmag, xmag, cuda_device):
+    """Ragged tile counts, T = 1, tiny / huge gradient magnitudes, un-normalised (|x| ~ 3000, saturated gates) and tiny
+    inputs (x rides in the gate MMA as an fp16 hi + lo pair): tcgen05 LSTM vs the fp32 CUDA-core LSTM."""
     torch.manual_seed(S + T)
     lstm = nn.LSTM(1, 32, 1, batch_first=True).to(cuda_device)
     ws0 = [lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0]
-    x0 = torch.rand(2, T, S, 1, 1, device=cuda_device) * 8
+    x0 = torch.rand(2, T, S, 1, 1, device=cuda_device) * xmag
     d_h = torch.randn(2 * S, 32, device=cuda_device) * gmag
     res = {}
     for prec in ("fp32", "fp16"):
@@ -352,7 +354,7 @@ def test_inference_mode_needs_no_stash_and_trainer_call_pattern(cuda_device):
             opt.zero_grad()
             loss.backward()
             opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
     model.eval()
     with torch.no_grad():
