@@ -7,6 +7,8 @@
 // the fp16 tensor path).  It is NOT a CPU fallback: everything here runs on the GPU.
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace mpgcn {
 
 // ---------------------------------------------------------------------------------------
@@ -180,19 +182,41 @@ int cvt_f32_to_f16_hilo(const float* src, __half* hi, __half* lo, size_t n, cuda
   return 0;
 }
 
-__global__ void diag_delta_kernel(const float* __restrict__ G, float* __restrict__ delta, size_t planes, int N) {
-  const size_t total = planes * (size_t)N;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const size_t p = t / N;
-    const int i = (int)(t - p * N);
-    const float g = G[(p * N + i) * (size_t)N + i];
-    delta[t] = g - __half2float(f2h_sat(g));
+// delta[p][i] = G_p[i,i] - fp16(G_p[i,i]) where the diagonal entry DOMINATES its column (G_ii^2 > tau * sum_{c != i} G_ci^2),
+// else 0.  The contraction epilogues add delta * (the diagonal operand row) back, which removes the one rounding error that
+// matters when a support is close to the identity (Chebyshev / random-walk T_k of a sparse graph); for a dense support the
+// diagonal is one of N comparable terms, the remainder is noise-level, and a zero delta lets the epilogue skip the re-read
+// of the operand tensor altogether.
+__global__ void diag_delta_kernel(const float* __restrict__ G, float* __restrict__ delta, size_t planes, int N, float tau) {
+  // block = 32 columns x 32 row groups of one plane; blockIdx.x enumerates (plane, column block)
+  __shared__ float s_sq[32][33];
+  const int cblocks = (N + 31) / 32;
+  const size_t p = blockIdx.x / cblocks;
+  const int i = (int)(blockIdx.x % cblocks) * 32 + (threadIdx.x & 31);
+  const int rg = threadIdx.x >> 5;
+  const float* plane = G + p * (size_t)N * N;
+  float sq = 0.f;
+  if (i < N && tau >= 0.f)
+    for (int c = rg; c < N; c += 32) { const float v = plane[(size_t)c * N + i]; sq = fmaf(v, v, sq); }   // 128-byte rows per warp
+  s_sq[rg][threadIdx.x & 31] = sq;
+  __syncthreads();
+  if (rg == 0 && i < N) {
+    float col = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) col += s_sq[r][threadIdx.x];
+    const float g = plane[(size_t)i * N + i];
+    float d = g - __half2float(f2h_sat(g));
+    if (tau >= 0.f && !(g * g > tau * (col - g * g))) d = 0.f;
+    delta[p * N + i] = d;
   }
 }
 int support_diag_delta(const float* G, float* delta, size_t planes, int N, cudaStream_t s) {
+  static float tau = -2.f;
+  if (tau == -2.f) { const char* e = getenv("MPGCN_B200_DIAG_TAU"); tau = e ? (float)atof(e) : 0.0625f; }   // < 0: always correct
   prof_count(PROF_ELEMENTWISE);
-  diag_delta_kernel<<<grid_for(planes * N, 256), 256, 0, s>>>(G, delta, planes, N);
+  const size_t blocks = planes * (size_t)((N + 31) / 32);
+  MPGCN_CHECK(blocks < (1ull << 31), "support_diag_delta: too many planes");
+  diag_delta_kernel<<<(unsigned)blocks, 1024, 0, s>>>(G, delta, planes, N, tau);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -306,6 +306,35 @@ def test_baseline_config_sizes_forward_and_backward(N, K, B, dyn, cuda_device):
         _check(a, r.cpu().numpy(), 2e-3, f"cfg N={N} K={K} {what}")
 
 
+@pytest.mark.parametrize("N,K,T,B", [(200, 3, 8, 4), (500, 3, 12, 1)])
+def test_full_model_at_baseline_config_shapes(N, K, T, B, cuda_device):
+    """BASELINE.json configs[1] / [2] model shapes (N=200,K=3,T=8 and N=500,K=3,T=12; batch reduced): the whole MPGCN forward +
+    backward (LSTM -> 3 x BDGCN -> fused head, two branches, static + dynamic supports) on the tensor-core kernels against
+    the same model on the exact fp32 kernels.  Forward within 1e-3; parameter gradients see the ReLU-mask flips of a
+    reduced-precision forward, hence the rel_L2 bound."""
+    torch.manual_seed(N + T)
+    model = shim.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=32, lstm_num_layers=1, gcn_hidden_dim=32, gcn_num_layers=3,
+                       num_nodes=N, user_bias=True, activation=nn.ReLU).to(cuda_device)
+    x = torch.rand(B, T, N, N, 1, device=cuda_device) * 4
+    G = torch.randn(K, N, N, device=cuda_device) / N ** 0.5
+    dyn = (torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5, torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5)
+    d_y = torch.randn(B, 1, N, N, 1, device=cuda_device) / (B * N * N)
+    res = {}
+    for prec in ("fp32", "fp16"):
+        model.lstm_precision = prec
+        for mod in model.modules():
+            if isinstance(mod, shim.BDGCN):
+                mod.precision = prec
+        model.zero_grad(set_to_none=True)
+        y = model(x_seq=x, G_list=[G, dyn])
+        y.backward(d_y)
+        torch.cuda.synchronize()
+        res[prec] = (y.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+    _check(res["fp16"][0], res["fp32"][0].cpu().numpy(), 1e-3, f"model N={N} K={K} T={T} y")
+    for k, gref in res["fp32"][1].items():
+        _check(res["fp16"][1][k], gref.cpu().numpy(), 8e-2, f"model N={N} grad:{k}", l2_only=True)
+
+
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
 def test_size_independent_properties(prec, cuda_device):
     """Linearity in X (no activation), identity supports, static == broadcast dynamic; N = 300."""
