@@ -318,7 +318,6 @@ def test_full_model_at_baseline_config_shapes(N, K, T, B, cuda_device):
     x = torch.rand(B, T, N, N, 1, device=cuda_device) * 4
     G = torch.randn(K, N, N, device=cuda_device) / N ** 0.5
     dyn = (torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5, torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5)
-    d_y = torch.randn(B, 1, N, N, 1, device=cuda_device) / (B * N * N)
     res = {}
     for prec in ("fp32", "fp16"):
         model.lstm_precision = prec
@@ -327,7 +326,11 @@ def test_full_model_at_baseline_config_shapes(N, K, T, B, cuda_device):
                 mod.precision = prec
         model.zero_grad(set_to_none=True)
         y = model(x_seq=x, G_list=[G, dyn])
-        y.backward(d_y)
+        # the trainer's loss (nn.MSELoss, Model_Trainer.py:64,108) against a zero target: a coherent d_y.  (An i.i.d. random d_y
+        # makes every parameter gradient a noise-dominated sum of random-sign terms, in which the ~3e-4 ReLU-mask flips of the
+        # reduced-precision forward show up as 10 % relative differences.)
+        loss = (y ** 2).mean()
+        loss.backward()
         torch.cuda.synchronize()
         res[prec] = (y.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters()})
     _check(res["fp16"][0], res["fp32"][0].cpu().numpy(), 1e-3, f"model N={N} K={K} T={T} y")
