@@ -123,6 +123,18 @@ MPGCN_API int mpgcn_lstm_last_backward_saved(const float* x_seq, const float* w_
                                    const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes, int B, int T,
                                    long long NN, int C, int precision, const float* d_hT_absmax, void* stream);
 
+/* Dynamic origin / destination graphs from the OD history = DataInput.construct_dyn_G (reference Data_Container_OD.py:39-59).
+ *   od_history [periods * P, N, N]  the first periods*P days of the (un-normalised) OD tensor, P = perceived period (7)
+ *   o_graph, d_graph [P, N, N]      slot t: A_t = mean_k od_history[t + k P];
+ *       o_graph[t][i][j] = cosine_distance(A_t[i,:], A_t[j,:])            (:50-52)
+ *       d_graph[t][i][j] = cosine_distance(A_t[:,i], A_t[j,:])            (:54-56: column i against ROW j, as the reference does)
+ *   cosine_distance = clip(1 - u.v / sqrt(u.u v.v), 0, 2) (scipy), NaN for a zero vector.  fp32 on the device (the reference
+ *   is float64 on the host): absolute error ~1e-6.  The reference stacks the slots on the LAST axis ([N,N,P]); the Python
+ *   mirror mpgcn_b200.dyn_graph.construct_dyn_G returns that layout. */
+MPGCN_API size_t mpgcn_dyn_graph_workspace_bytes(int P, int N);
+MPGCN_API int mpgcn_dyn_graph_build(const float* od_history, int periods, float* o_graph, float* d_graph, int P, int N, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* FC head + multi-perspective fusion (reference MPGCN.py:74-76,107,110,112), one pass:
  *     y[cell] = (1/M) * sum_m relu( g_m[cell,:] . w[m,:] + bias[m] )      (Linear(C -> 1) + ReLU per branch, mean over the M branches)
  *   g    HOST array of M device pointers, each [cells, C] (cells = B*N*N);  w [M,C], bias [M];  y [cells]

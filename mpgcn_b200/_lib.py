@@ -46,6 +46,8 @@ _SIGS = {
                                                ctypes.c_size_t] + [ctypes.c_int] * 6 + [_c_f, _c_f, ctypes.c_void_p]),
     "mpgcn_lstm_last_backward_ex": (ctypes.c_int, [_c_f] * 12 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
                                                    ctypes.c_int, _c_f, ctypes.c_void_p]),
+    "mpgcn_dyn_graph_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "mpgcn_dyn_graph_build": (ctypes.c_int, [_c_f, ctypes.c_int, _c_f, _c_f, ctypes.c_int, ctypes.c_int, _c_f, ctypes.c_size_t, ctypes.c_void_p]),
     "mpgcn_lstm_saved_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]),
     "mpgcn_lstm_last_forward_train": (ctypes.c_int, [_c_f] * 7 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
                                                      ctypes.c_int, ctypes.c_void_p]),

@@ -122,6 +122,14 @@ long long mpgcn_debug_tc_workspace_offset(int which, int B, int N, int K, int dy
   return tc_debug_offset(mk(B, N, K, 32, 32, dynamic, 0), which);
 }
 
+size_t mpgcn_dyn_graph_workspace_bytes(int P, int N) { return (P >= 1 && N >= 1) ? dyn_graph_workspace_bytes(P, N) : 0; }
+
+int mpgcn_dyn_graph_build(const float* od_history, int periods, float* o_graph, float* d_graph, int P, int N, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  MPGCN_CHECK(od_history && o_graph && d_graph, "mpgcn_dyn_graph_build: null pointer argument");
+  return dyn_graph_build(od_history, periods, o_graph, d_graph, P, N, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int mpgcn_lstm_precision_supported(int T, int C, int precision) {
   if (precision == PREC_FP32_SIMT) return (T >= 1 && C >= 1 && C <= 64) ? 1 : 0;
   if (precision == PREC_FP16_TC) return lstm_tc_supported(T, C) ? 1 : 0;

@@ -74,6 +74,10 @@ int adj_num_supports(int kernel_type, int K);
 size_t adj_workspace_bytes(int B, int N, int kernel_type, int K);
 int adj_process(const float* flow, float* supports, int B, int N, int kernel_type, int K, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// dynamic O / D graphs from the OD history (dyn_graph_kernels.cu)
+size_t dyn_graph_workspace_bytes(int P, int N);
+int dyn_graph_build(const float* od_hist, int periods, float* o_g, float* d_g, int P, int N, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // tcgen05 LSTM (lstm_tc.cu): hidden size 32 only
 bool lstm_tc_supported(int T, int C);
 size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN);

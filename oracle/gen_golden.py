@@ -189,6 +189,32 @@ def gen_adj(ref_gcn):
         print("wrote", name, sup.shape)
 
 
+DYN_CASES = [
+    # name, N, days, split_ratio, zero_row
+    ("dyn_n12_d70", 12, 70, [6.4, 1.6, 2], False),
+    ("dyn_n20_d45", 20, 45, [6.4, 1.6, 2], False),      # 45 days -> train_len 28 -> 4 periods
+    ("dyn_n9_d30_zero", 9, 30, [7, 1, 2], True),        # an all-zero origin row: NaN entries, as scipy produces
+]
+
+
+def gen_dyn(ref_data):
+    """DataInput.construct_dyn_G of the unmodified reference (Data_Container_OD.py:39-59; scipy distance.cosine per pair)."""
+    import warnings
+    for idx, (name, N, days, split, zero_row) in enumerate(DYN_CASES):
+        rng = np.random.default_rng(5000 + idx)
+        od = rng.poisson(6.0, size=(days, N, N, 1)).astype(np.float64)
+        od[:, :, 2, :] *= 0.25                                     # make the graphs less uniform
+        if zero_row:
+            od[:, 4, :, :] = 0
+        di = ref_data.DataInput({"split_ratio": split})
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o_g, d_g = di.construct_dyn_G(od)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), od=od.astype(np.float32), split_ratio=np.asarray(split, dtype=np.float64),
+                            O_dyn_G=o_g, D_dyn_G=d_g)
+        print("wrote", name, o_g.shape, "nan:", int(np.isnan(o_g).sum()), int(np.isnan(d_g).sum()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -200,6 +226,7 @@ def main():
     gen_lstm()
     gen_model(ref_mpgcn, ref_gcn)
     gen_adj(ref_gcn)
+    gen_dyn(_load_ref("Data_Container_OD"))
 
 
 if __name__ == "__main__":

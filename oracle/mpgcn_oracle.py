@@ -373,3 +373,26 @@ def adj_process(flow, kernel_type, K):
             raise ValueError("Invalid kernel_type. Must be one of [chebyshev, localpool, random_walk_diffusion, dual_random_walk_diffusion].")
         out.append(np.stack(ks, axis=0))
     return np.stack(out, axis=0)
+
+
+def construct_dyn_g(OD_data, split_ratio, perceived_period=7):
+    """DataInput.construct_dyn_G (Data_Container_OD.py:39-59), vectorised in float64.
+    OD_data [days, N, N, 1] -> (O_dyn_G, D_dyn_G) [N, N, P];  O[i,j,t] = cos_dist(A_t[i,:], A_t[j,:]),
+    D[i,j,t] = cos_dist(A_t[:,i], A_t[j,:]) -- column i against ROW j, the reference's own eq.-(7) indexing at :56 --
+    with scipy's cosine distance clip(1 - u.v / sqrt(u.u v.v), 0, 2) (NaN for a zero vector)."""
+    OD_data = np.asarray(OD_data, dtype=np.float64)
+    train_len = int(OD_data.shape[0] * split_ratio[0] / sum(split_ratio))               # :40
+    periods = train_len // perceived_period                                               # :41
+    hist = OD_data[:periods * perceived_period]                                           # :42
+    Os, Ds = [], []
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for t in range(perceived_period):
+            A = hist[t::perceived_period].mean(axis=0)[..., 0]                            # :45
+            rr = (A * A).sum(axis=1)          # |row i|^2
+            cc = (A * A).sum(axis=0)          # |col i|^2
+            O = 1.0 - (A @ A.T) / np.sqrt(rr[:, None] * rr[None, :])                      # :50-52
+            D = 1.0 - (A.T @ A.T) / np.sqrt(cc[:, None] * rr[None, :])                    # :54-56  (col i . row j)
+            Os.append(np.clip(O, 0.0, 2.0))
+            Ds.append(np.clip(D, 0.0, 2.0))
+    return np.stack(Os, axis=-1), np.stack(Ds, axis=-1)                                   # :59
+

@@ -193,6 +193,41 @@ def test_adj_processor_at_size_vs_oracle(kind, K, N, B, cuda_device):
     _check(sup, orc.adj_process(flow.astype(np.float64), kind, K), 2e-5, f"adj {kind} N={N}")
 
 
+@pytest.mark.parametrize("name", golden_names("dyn_"))
+def test_dyn_graphs_match_reference_fixture(name, cuda_device):
+    """GPU construct_dyn_G vs fixtures produced by the reference's DataInput.construct_dyn_G (float64, per-pair scipy calls):
+    fp32 arithmetic on the device -> 5e-6 absolute; identical NaN pattern (zero vectors)."""
+    from mpgcn_b200 import dyn_graph
+    g = load_golden(name)
+    O, D = dyn_graph.construct_dyn_G(g["od"], list(g["split_ratio"]), device=cuda_device)
+    for a, ref, what in ((O, g["O_dyn_G"], "O"), (D, g["D_dyn_G"], "D")):
+        assert a.shape == ref.shape and a.dtype == np.float64
+        assert np.array_equal(np.isnan(a), np.isnan(ref)), f"{name}/{what}: NaN pattern"
+        err = float(np.nanmax(np.abs(a - ref)))
+        record_parity(f"{name}/{what} (abs)", err, err, 5e-6)
+        assert err <= 5e-6, f"{name}/{what}: max abs err {err:.2e}"
+
+
+def test_dyn_graphs_at_size_and_drop_in_method(cuda_device):
+    """N = 300 (1.26 M scipy calls in the reference) against the float64 oracle, through the drop-in replacement of the
+    reference's method (same signature: self, OD_data, perceived_period=7)."""
+    from mpgcn_b200 import dyn_graph
+    rng = np.random.default_rng(11)
+    N, days = 300, 64
+    od = rng.poisson(3.0, size=(days, N, N, 1)).astype(np.float32)
+    class DataInput:                      # the reference class's relevant surface (Data_Container_OD.py:10-12,39)
+        def __init__(self, params):
+            self.params = params
+    dyn_graph.install(DataInput)
+    O, D = DataInput({"split_ratio": [6.4, 1.6, 2]}).construct_dyn_G(od)
+    Oref, Dref = orc.construct_dyn_g(od.astype(np.float64), [6.4, 1.6, 2])
+    assert O.shape == (N, N, 7) and D.shape == (N, N, 7)
+    for a, ref, what in ((O, Oref, "O"), (D, Dref, "D")):
+        err = float(np.max(np.abs(a - ref)))
+        record_parity(f"dyn N={N}/{what} (abs)", err, err, 5e-6)
+        assert err <= 5e-6, f"{what}: max abs err {err:.2e}"
+
+
 @pytest.mark.parametrize("M,C,cells", [(2, 32, 1000), (1, 8, 77), (3, 64, 4099)])
 def test_fused_head_matches_oracle(M, C, cells, cuda_device):
     """Linear(C->1)+ReLU per branch and branch mean in one kernel (reference MPGCN.py:74-76,107,110) vs the numpy oracle."""

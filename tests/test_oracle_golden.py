@@ -108,3 +108,18 @@ def test_adj_process_matches_reference(name):
     sup = orc.adj_process(g["flow"], str(g["kernel_type"]), int(g["K"]))
     assert sup.shape == g["supports"].shape
     _check(sup, g["supports"], tol=2e-5, what="supports")
+
+
+@pytest.mark.parametrize("name", golden_names("dyn_"))
+def test_construct_dyn_g_matches_reference(name):
+    """Vectorised restatement vs DataInput.construct_dyn_G of the unmodified reference (per-pair scipy distance.cosine),
+    including the NaN pattern of an all-zero origin row and the column-vs-row indexing of the D graph."""
+    g = load_golden(name)
+    O, D = orc.construct_dyn_g(g["od"].astype(np.float64), list(g["split_ratio"]))
+    for a, ref, what in ((O, g["O_dyn_G"], "O"), (D, g["D_dyn_G"], "D")):
+        assert a.shape == ref.shape and a.dtype == np.float64
+        assert np.array_equal(np.isnan(a), np.isnan(ref)), f"{name}/{what}: NaN pattern"
+        assert np.nanmax(np.abs(a - ref)) <= 1e-12, f"{name}/{what}"
+    if "zero" not in name:
+        assert not np.allclose(D, np.transpose(D, (1, 0, 2))), "D graph must keep the reference's asymmetric (column i, row j) form"
+
