@@ -57,24 +57,41 @@ def _scratch(nbytes: int, device) -> torch.Tensor:
 
 
 # Gradient-magnitude hand-over between consecutive backward calls of the fp16 path: the kernel that writes a gradient tensor also
-# records max|grad| in a device scalar; the next backward that receives exactly that tensor (same storage, same version) reuses
-# it for its power-of-two scaling instead of re-reading the tensor.  Purely an optimisation -- a missed hint costs one extra pass.
-_ABSMAX_HINTS = {}
+# records max|grad| in a device scalar, and the backward that receives that tensor reuses it for its power-of-two scaling
+# instead of re-reading the tensor.  The hand-over follows the autograd graph, not memory addresses: at forward time a consumer
+# (BDGCN layer, FC head) notes which of OUR autograd nodes produced its input (looking through pure view nodes only); at
+# backward time it leaves (data_ptr, version, numel, scalar) of the gradient it wrote ON that node, and the node's backward
+# accepts the hint only if the gradient it receives is that very memory, unmodified (gradient accumulation from a second
+# consumer arrives in a different buffer or with a bumped version).  Purely an optimisation: a missed hint costs one pass.
+_VIEW_NODES = ("ViewBackward", "UnsafeViewBackward", "ReshapeAliasBackward", "AliasBackward")
+_OUR_NODES = ("_BDGCNFnBackward", "_LSTMLastFnBackward")
 
 
-def _put_hint(t, absmax_scalar):
-    if t is None:
-        return
-    if len(_ABSMAX_HINTS) > 16:
-        _ABSMAX_HINTS.clear()
-    _ABSMAX_HINTS[(t.device.index, t.data_ptr())] = (t._version, t.numel(), absmax_scalar)
-
-
-def _take_hint(t):
-    e = _ABSMAX_HINTS.pop((t.device.index, t.data_ptr()), None)
-    if e is not None and e[0] == t._version and e[1] == t.numel():
-        return e[2]
+def _producer_node(t):
+    node = getattr(t, "grad_fn", None)
+    for _ in range(8):
+        if node is None:
+            return None
+        name = type(node).__name__
+        if name in _OUR_NODES:
+            return node
+        if not name.startswith(_VIEW_NODES) or len(node.next_functions) != 1:
+            return None
+        node = node.next_functions[0][0]
     return None
+
+
+def _put_hint(node, grad, absmax_scalar):
+    if node is not None and grad is not None and absmax_scalar is not None:
+        node._mpgcn_hint = (grad.data_ptr(), grad._version, grad.numel(), absmax_scalar)
+
+
+def _take_hint(node, grad):
+    e = getattr(node, "_mpgcn_hint", None)
+    if e is None:
+        return None
+    node._mpgcn_hint = None
+    return e[3] if (e[0] == grad.data_ptr() and e[1] == grad._version and e[2] == grad.numel()) else None
 
 
 class _BDGCNFn(torch.autograd.Function):
@@ -98,6 +115,7 @@ class _BDGCNFn(torch.autograd.Function):
                                                _ptr(saved), _ptr(ws), ws.numel(), B, N, K, C, H, prec, _stream()), "bdgcn_forward")
         ctx.shape = (B, N, K, C, H)
         ctx.meta = (bool(dynamic), act, prec, b is not None)
+        ctx.x_producer = _producer_node(X) if need_grad else None
         ctx.save_for_backward(out, Goc, Gdc, Wc, saved if saved is not None else torch.empty(0, device=X.device))
         return out
 
@@ -109,9 +127,9 @@ class _BDGCNFn(torch.autograd.Function):
         dynamic, act, prec, has_bias = ctx.meta
         if saved.numel() == 0:
             raise RuntimeError("mpgcn_b200.bdgcn: backward called but forward ran without requires_grad inputs")
-        d_out = _f32c(d_out)
         tc = prec == _lib.PREC_FP16_TC
-        hint = _take_hint(d_out) if tc else None
+        hint = _take_hint(ctx, d_out) if (tc and d_out.dtype == torch.float32 and d_out.is_contiguous()) else None
+        d_out = _f32c(d_out)
         need_dx = ctx.needs_input_grad[0]
         dX = torch.empty((B, N, N, C), dtype=torch.float32, device=out.device) if need_dx else None
         dx_absmax = torch.empty(1, dtype=torch.float32, device=out.device) if (need_dx and tc) else None
@@ -122,8 +140,7 @@ class _BDGCNFn(torch.autograd.Function):
             _lib.check(lib.mpgcn_bdgcn_backward_ex(_ptr(d_out), _ptr(out), _ptr(Goc), _ptr(Gdc), int(dynamic), _ptr(Wc), act, _ptr(saved),
                                                    _ptr(dX), _ptr(dW), _ptr(db), _ptr(ws), ws.numel(), B, N, K, C, H, prec, _ptr(hint),
                                                    _ptr(dx_absmax), _stream()), "bdgcn_backward")
-        if dx_absmax is not None:
-            _put_hint(dX, dx_absmax)
+        _put_hint(ctx.x_producer, dX, dx_absmax)
         return dX, None, None, dW, db, None, None, None
 
 
@@ -183,8 +200,8 @@ class _LSTMLastFn(torch.autograd.Function):
         lib = _lib.load()
         xc, w_ih, w_hh, b_ih, b_hh = ctx.saved_tensors
         B, T, NN, C, prec = ctx.dims
+        hint = _take_hint(ctx, d_hT) if (prec == _lib.PREC_FP16_TC and d_hT.dtype == torch.float32 and d_hT.is_contiguous()) else None
         d_hT = _f32c(d_hT)
-        hint = _take_hint(d_hT) if prec == _lib.PREC_FP16_TC else None
         dev = xc.device
         g_wih, g_whh = torch.empty_like(w_ih), torch.empty_like(w_hh)
         g_bih, g_bhh = torch.empty_like(b_ih), torch.empty_like(b_hh)
@@ -223,6 +240,7 @@ class _HeadFn(torch.autograd.Function):
         with torch.cuda.device(y.device):
             _lib.check(lib.mpgcn_head_forward(ptrs, _ptr(wc), _ptr(bc), _ptr(y), _ptr(pre), cells, C, M, _stream()), "head_forward")
         ctx.dims = (M, C, cells)
+        ctx.g_producers = [_producer_node(g) for g in gs] if need else None
         ctx.save_for_backward(wc, pre if pre is not None else torch.empty(0, device=y.device), *gc)
         return y
 
@@ -243,7 +261,7 @@ class _HeadFn(torch.autograd.Function):
             _lib.check(lib.mpgcn_head_backward(ptrs, _ptr(wc), _ptr(pre), _ptr(dy), dptrs, _ptr(dw), _ptr(db), _ptr(amax), cells, C, M,
                                                _stream()), "head_backward")
         for m, d in enumerate(dgs):
-            _put_hint(d, amax[m:m + 1])
+            _put_hint(ctx.g_producers[m], d, amax[m:m + 1])
         return (dw, db) + tuple(dgs)
 
 

@@ -438,6 +438,58 @@ def test_inference_mode_needs_no_stash_and_trainer_call_pattern(cuda_device):
         assert torch.equal(model2(x_seq=x, G_list=[G, dyn]), model(x_seq=x, G_list=[G, dyn]))
 
 
+def test_gradient_magnitude_hints_follow_the_autograd_graph(cuda_device, monkeypatch):
+    """max|grad| hand-over (ops._put_hint / _take_hint): in the model every fp16 backward receives its scale from the kernel
+    that wrote its incoming gradient (8 hand-overs: head -> layer 3 -> 2 -> 1 -> LSTM on two branches), results are
+    the same with and without the hand-over, and a gradient that is not the producer's own buffer (here: a second
+    consumer of the LSTM output, so autograd accumulates) is not trusted."""
+    torch.manual_seed(3)
+    N, K, B, T = 40, 2, 2, 3
+    model = shim.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=32, lstm_num_layers=1, gcn_hidden_dim=32, gcn_num_layers=3,
+                       num_nodes=N, user_bias=True, activation=nn.ReLU).to(cuda_device)
+    x = torch.rand(B, T, N, N, 1, device=cuda_device) * 4
+    G = torch.randn(K, N, N, device=cuda_device) / N ** 0.5
+    lib = _lib.load()
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        lib.mpgcn_profile_reset()
+        (model(x_seq=x, G_list=[G, G]) ** 2).mean().backward()
+        torch.cuda.synchronize()
+        return _lib.profile_read()["ELEMENTWISE"]["launches"], [p.grad.clone() for p in model.parameters()]
+
+    n_with, g_with = run()
+    monkeypatch.setattr(ops, "_producer_node", lambda t: None)
+    n_without, g_without = run()
+    monkeypatch.undo()
+    assert n_without - n_with == 8, (n_with, n_without)          # one absmax pass saved per hand-over
+    for a, b in zip(g_with, g_without):      # same scales either way; only the atomic summation order differs run to run
+        _check(a, b.cpu().numpy(), 1e-5, "gradients with vs without the hand-over", l2_only=True)
+    # second consumer of h_T: the LSTM node receives an accumulated gradient -> its hint must be rejected, result still right
+    lstm = model.branch_models[0]['temporal']
+    layer = model.branch_models[0]['spatial'][0]
+    ws = [lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0]
+    def two_consumers(scale_side):
+        for w in ws:
+            w.grad = None
+        h = ops.lstm_last(x, *ws, precision="fp16")
+        out = layer(h.reshape(B, N, N, 32), G)
+        (out.sum() * 1e-3 + scale_side * (h ** 2).sum()).backward()
+        torch.cuda.synchronize()
+        return [w.grad.clone() for w in ws]
+    ref = two_consumers(0.0)
+    big = two_consumers(50.0)         # the side branch dominates max|grad|: a stale scale would saturate fp16
+    assert all(torch.isfinite(g).all() for g in big)
+    assert not torch.allclose(big[1], ref[1])
+    for w in ws:
+        w.grad = None
+    h = ops.lstm_last(x, *ws, precision="fp32")
+    out = layer(h.reshape(B, N, N, 32), G)
+    (out.sum() * 1e-3 + 50.0 * (h ** 2).sum()).backward()
+    for a, w in zip(big, ws):
+        _check(a, w.grad.cpu().numpy(), 5e-3, "two consumers of h_T: accumulated gradient", l2_only=True)
+
+
 def test_cuda_graph_rollout_equals_eager_loop(cuda_device):
     """Model_Trainer.test's autoregressive loop (Model_Trainer.py:157-165): CUDA-graph replay vs the eager loop, N = 47."""
     from mpgcn_b200 import rollout
