@@ -111,8 +111,8 @@ MPGCN_API int mpgcn_lstm_last_backward_ex(const float* x_seq, const float* w_ih,
 /* Training pair for the LSTM (what autograd keeps between nn.LSTM's forward and backward, MPGCN.py:100-104 under
  * loss.backward(), Model_Trainer.py:114).  The forward additionally writes c_t and h_t of every step (fp16) into `saved`
  * (mpgcn_lstm_saved_bytes; 0 for precision 0, whose backward recomputes; 16-byte aligned; NULL = plain inference forward);
- * the backward walks that buffer once in reverse instead of re-running the recurrence.  With saved == NULL the backward is
- * mpgcn_lstm_last_backward_ex (recompute, workspace from mpgcn_lstm_bwd_workspace_bytes); with saved != NULL the
+ * the backward walks that buffer once in reverse.  With saved == NULL the backward is mpgcn_lstm_last_backward_ex: it first
+ * rebuilds that state in its workspace (mpgcn_lstm_bwd_workspace_bytes = 1 KB + the saved size); with saved != NULL the
  * workspace only needs 1024 bytes. */
 MPGCN_API size_t mpgcn_lstm_saved_bytes(int B, int T, long long NN, int C, int precision);
 MPGCN_API int mpgcn_lstm_last_forward_train(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,

@@ -3,14 +3,14 @@
 // Reference semantics: nn.LSTM(1, 32, 1, batch_first=True) over B*N*N independent cells with zero
 // initial state, last hidden state only (/root/reference/MPGCN.py:69,80-87,100-104); gate order i,f,g,o.
 //
-// Three kernels (details at each):
+// Two kernels (details at each):
 //   lstm_fwd_tc_kernel<SAVE>       forward; SAVE additionally stores c_t, h_t (fp16) of every step for training
 //   lstm_bwd_saved_tc_kernel<2>    backward from that saved state: one reverse walk, gate MMA prefetched a step ahead
-//   lstm_bwd_tc_kernel             backward for callers without saved state: recomputes the forward per tile into a stash
+// (a backward call that comes without saved state first re-runs the SAVE forward into its workspace)
 // Tile = 128 cells = the 128 TMEM lanes.  The gate GEMM of a step, affine part and ex2 scaling included, is ONE MMA
 // [128 cells x 48] . [48 x 128 gates] whose fp32 accumulator is the exponent argument of the activation; activations
 // cost 7 SFU operations per hidden unit and step.  The recurrence rounds h to fp16 only as MMA operand; c, the gate
-// arguments and the returned h_T stay fp32.  The first two kernels use 8-warp CTAs without a dedicated MMA warp so that
+// arguments and the returned h_T stay fp32.  Both kernels use 8-warp CTAs without a dedicated MMA warp so that
 // two CTAs stay resident per SM at 128 registers per thread (see lstm_bwd_saved_tc_kernel).
 #include "kernels.h"
 
@@ -23,10 +23,6 @@ constexpr int C = 32;
 constexpr int UN = 16;          // hidden units per thread
 constexpr int G4 = 128;
 constexpr int CELLS = 128;
-constexpr int STASH = 6 * C;    // halves per cell-step: i f g o c h
-constexpr int THREADS = 288;    // 8 epilogue warps + 1 MMA warp
-constexpr int EPI = 256;
-constexpr int MMA_WARP = 8;
 constexpr int DA_BYTES = 32768;     // [128 cells][128 gates] fp16 as two [128][64] SW128 sub-tiles
 constexpr int HX_BYTES = 16384;     // [128 cells][64] fp16, SW128
 constexpr int WX_BYTES = 16384;     // [128 gates][64] fp16, SW128
@@ -34,12 +30,9 @@ constexpr int WX_BYTES = 16384;     // [128 gates][64] fp16, SW128
 __device__ __forceinline__ uint32_t sw64_off(int row, int chunk) { return (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4); }
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
 
-// sigmoid / tanh on the SFU: one ex2.approx + one rcp.approx each (2 ulp), no range fix-ups: for |x| large ex2 saturates to
-// 0 or +inf and rcp(1 + inf) = 0, which are the correct limits.
+// SFU primitives (2 ulp each); ex2 saturates to 0 / +inf and rcp(inf) = 0, which are the limits the activations need.
 __device__ __forceinline__ float ex2_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sigm(float x) { return rcp_(1.f + ex2_(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float tanh_(float x) { return fmaf(2.f, rcp_(1.f + ex2_(-2.8853900817779268f * x)), -1.f); }
 
 // x enters the gate MMA as fp16 hi + lo (exact to ~22 bits for |x| < 65504); both parts saturate instead of overflowing to inf,
 // so larger inputs give finite (saturated-gate) results rather than NaN
@@ -106,13 +99,6 @@ __device__ void load_weights(uint8_t* sW, float* s_bias, float* s_wih, const flo
   }
 }
 
-// Stash layout (per CTA): [t][24 chunks = 6 blocks (i f g o c h) x 4][128 cells][8 halves]: the 32 lanes of a warp
-// touch 32 consecutive 16-byte chunks, i.e. every stash load / store is fully coalesced.
-constexpr int STASH_CHUNKS = 24;
-__device__ __forceinline__ uint4* stash_at(__half* base, int t, int chunk) {
-  return reinterpret_cast<uint4*>(base + (size_t)t * (STASH_CHUNKS * CELLS * 8)) + chunk * CELLS;   // chunk is a compile-time constant at every call site
-}
-
 // Training state written by the forward kernel and read by lstm_bwd_saved_tc_kernel, per 128-cell tile:
 // [t][8 chunks = c (4) then h (4)][128 cells][8 halves], again one 16-byte chunk per lane.  A thread's base pointer already
 // includes its row and its unit half, so chunk q (0/1) addresses its c units and chunk 4+q its h units.
@@ -122,167 +108,6 @@ __device__ __forceinline__ uint4* save_at(__half* base, int t, int chunk) {
 }
 __device__ __forceinline__ const uint4* save_at(const __half* base, int t, int chunk) {
   return reinterpret_cast<const uint4*>(base + (size_t)t * (SAVE_CHUNKS * CELLS * 8)) + chunk * CELLS;
-}
-
-// Two activations with ONE reciprocal: 1/a and 1/b from r = 1/(a*b).  The SFU is the bottleneck of the forward pass
-// (10 transcendental ops per hidden unit and step: 5 ex2 + 5 rcp); pairing (i,g) and (f,o) removes two of the five rcp.
-// Exponent arguments are clamped to +-43.28 (= 30 * log2 e) so that a*b <= (1 + e^30)^2 ~ 1e26 cannot overflow; the clamp is
-// lossless in fp32 (sigmoid(30) = 1 - 9e-14, tanh(15) = 1 - 2e-13).
-__device__ __forceinline__ float exp_arg(float x, float scale) { return fminf(fmaxf(x * scale, -43.280851f), 43.280851f); }
-// returns sigmoid(xa) and tanh(xb)
-__device__ __forceinline__ void sig_tanh_pair(float xa, float xb, float& sa, float& tb) {
-  const float a = 1.f + ex2_(exp_arg(xa, -1.4426950408889634f));
-  const float b = 1.f + ex2_(exp_arg(xb, -2.8853900817779268f));
-  const float r = rcp_(a * b);
-  sa = r * b;
-  tb = fmaf(2.f * r, a, -1.f);
-}
-// returns sigmoid(xa) and sigmoid(xb)
-__device__ __forceinline__ void sig_sig_pair(float xa, float xb, float& sa, float& sb) {
-  const float a = 1.f + ex2_(exp_arg(xa, -1.4426950408889634f));
-  const float b = 1.f + ex2_(exp_arg(xb, -1.4426950408889634f));
-  const float r = rcp_(a * b);
-  sa = r * b;
-  sb = r * a;
-}
-
-// One LSTM step for 16 hidden units of one cell.  t_col = TMEM address of (lane quarter, column 16*hh) of the gate
-// accumulator; u0 = 16*hh.  Updates c[], returns h[]; optionally stashes gates, c and h.
-// tuning switches (measured on B200, N=1000, B=4, T=12)
-#ifndef MPGCN_LSTM_BWD_PAIRED
-#define MPGCN_LSTM_BWD_PAIRED 0
-#endif
-#ifndef MPGCN_LSTM_FWD_PAIRED
-#define MPGCN_LSTM_FWD_PAIRED 1
-#endif
-#ifndef MPGCN_LSTM_FWD_LB
-#define MPGCN_LSTM_FWD_LB 1
-#endif
-
-template <bool STASH_OUT, bool PAIRED = true>
-__device__ __forceinline__ void cell_step(uint32_t t_col, bool has_mma, float xv, const float* s_bias, const float* s_wih, int u0,
-                                          float (&c)[UN], float (&h)[UN], __half* stash, int t_stash, int hh) {
-  if (!PAIRED) {      // one gate block at a time (lower register pressure, 10 SFU ops per unit)
-    uint32_t r[UN];
-    float ig[UN];
-    if (has_mma) { tmem_ld_32x16(t_col + 0 * C, r); tmem_ld_wait(); }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) ig[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[u0 + u], xv, s_bias[u0 + u]));
-    if (STASH_OUT) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 0 * 4 + q) = pack8(ig + 8 * q);
-    }
-    if (has_mma) { tmem_ld_32x16(t_col + 2 * C, r); tmem_ld_wait(); }
-    {
-      float g[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) g[u] = tanh_((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[2 * C + u0 + u], xv, s_bias[2 * C + u0 + u]));
-      if (STASH_OUT) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 2 * 4 + q) = pack8(g + 8 * q);
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) ig[u] *= g[u];
-    }
-    if (has_mma) { tmem_ld_32x16(t_col + 1 * C, r); tmem_ld_wait(); }
-    {
-      float f[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) f[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[C + u0 + u], xv, s_bias[C + u0 + u]));
-      if (STASH_OUT) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 1 * 4 + q) = pack8(f + 8 * q);
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) c[u] = fmaf(f[u], c[u], ig[u]);
-    }
-    if (STASH_OUT) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 4 * 4 + q) = pack8(c + 8 * q);
-    }
-    if (has_mma) { tmem_ld_32x16(t_col + 3 * C, r); tmem_ld_wait(); }
-    {
-      float o[UN];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) o[u] = sigm((has_mma ? __uint_as_float(r[u]) : 0.f) + fmaf(s_wih[3 * C + u0 + u], xv, s_bias[3 * C + u0 + u]));
-      if (STASH_OUT) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 3 * 4 + q) = pack8(o + 8 * q);
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) h[u] = o[u] * tanh_(c[u]);
-    }
-    if (STASH_OUT) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) *stash_at(stash, t_stash, 5 * 4 + q) = pack8(h + 8 * q);
-    }
-    return;
-  }
-  uint32_t ra[UN], rb[UN];
-  float ig[UN];
-  // ---- input gate and cell candidate ----
-  if (has_mma) {
-    tmem_ld_32x16(t_col + 0 * C, ra);
-    tmem_ld_32x16(t_col + 2 * C, rb);
-    tmem_ld_wait();
-  }
-  {
-    float g[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const float ai = (has_mma ? __uint_as_float(ra[u]) : 0.f) + fmaf(s_wih[u0 + u], xv, s_bias[u0 + u]);
-      const float ag = (has_mma ? __uint_as_float(rb[u]) : 0.f) + fmaf(s_wih[2 * C + u0 + u], xv, s_bias[2 * C + u0 + u]);
-      sig_tanh_pair(ai, ag, ig[u], g[u]);
-    }
-    if (STASH_OUT) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        *stash_at(stash, t_stash, 0 * 4 + q) = pack8(ig + 8 * q);
-        *stash_at(stash, t_stash, 2 * 4 + q) = pack8(g + 8 * q);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) ig[u] *= g[u];
-  }
-  // ---- forget and output gates ----
-  if (has_mma) {
-    tmem_ld_32x16(t_col + 1 * C, ra);
-    tmem_ld_32x16(t_col + 3 * C, rb);
-    tmem_ld_wait();
-  }
-  {
-    float f[UN], o[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const float af = (has_mma ? __uint_as_float(ra[u]) : 0.f) + fmaf(s_wih[C + u0 + u], xv, s_bias[C + u0 + u]);
-      const float ao = (has_mma ? __uint_as_float(rb[u]) : 0.f) + fmaf(s_wih[3 * C + u0 + u], xv, s_bias[3 * C + u0 + u]);
-      sig_sig_pair(af, ao, f[u], o[u]);
-    }
-    if (STASH_OUT) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        *stash_at(stash, t_stash, 1 * 4 + q) = pack8(f + 8 * q);
-        *stash_at(stash, t_stash, 3 * 4 + q) = pack8(o + 8 * q);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      c[u] = fmaf(f[u], c[u], ig[u]);
-      h[u] = o[u] * tanh_(c[u]);
-    }
-  }
-  if (STASH_OUT) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      *stash_at(stash, t_stash, 4 * 4 + q) = pack8(c + 8 * q);
-      *stash_at(stash, t_stash, 5 * 4 + q) = pack8(h + 8 * q);
-    }
-  }
-}
-
-__device__ __forceinline__ void write_h_tile(uint8_t* sH, int row, int hh, const float (&h)[UN]) {
-#pragma unroll
-  for (int q = 0; q < 2; ++q) *reinterpret_cast<uint4*>(sH + sw64_off(row, 2 * hh + q)) = pack8(h + 8 * q);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -431,7 +256,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
         }
       }
     }
-    if (live) {
+    if (live && hT != nullptr) {
       float4* dst = reinterpret_cast<float4*>(hT + (size_t)cell * C + u0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
@@ -440,271 +265,6 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
-}
-
-// ---------------------------------------------------------------------------------------
-// backward
-// ---------------------------------------------------------------------------------------
-
-#ifndef MPGCN_LSTM_BWD_LB
-#define MPGCN_LSTM_BWD_LB 0
-#endif
-#if MPGCN_LSTM_BWD_LB == 2
-__global__ void __launch_bounds__(THREADS)          // with -maxrregcount=112 for this file
-#else
-__global__ void __maxnreg__(112)
-#endif
-lstm_bwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
-                   const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ d_hT,
-                   float* __restrict__ d_w_ih, float* __restrict__ d_w_hh, float* __restrict__ d_b, float* __restrict__ d_x,
-                   __half* __restrict__ scratch, const float* __restrict__ scale2, long long cells, int T, long long NN) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sDA = smem;                               // 32 KB (single buffer: MMA2 of step t retires long before step t-1's math ends)
-  uint8_t* sHX = smem + DA_BYTES;                    // 16 KB
-  uint8_t* sW = sHX + HX_BYTES;                      // 8 KB
-  uint8_t* sH = sW + 8192;                           // 8 KB
-  float* s_bias = reinterpret_cast<float*>(sH + 8192);
-  float* s_wih = s_bias + G4;
-  uint64_t* h_ready = reinterpret_cast<uint64_t*>(s_wih + G4);
-  uint64_t* g_ready = h_ready + 1;
-  uint64_t* da_ready = g_ready + 1;
-  uint64_t* da_free = da_ready + 1;
-  uint64_t* dh_ready = da_free + 1;
-  uint64_t* acc_done = dh_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_done + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  load_weights(sW, s_bias, s_wih, w_ih, w_hh, b_ih, b_hh);
-  if (threadIdx.x == 0) {
-    mbar_init(h_ready, EPI); mbar_init(g_ready, 1);
-    mbar_init(da_ready, EPI); mbar_init(da_free, 1);
-    mbar_init(dh_ready, 1); mbar_init(acc_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t TM_GATES = tmem_base, TM_DH = tmem_base + 128, TM_DW = tmem_base + 160;
-  const long long tiles = (cells + CELLS - 1) / CELLS;
-  const float S = scale2[0], invS = scale2[1];
-
-  if (warp == MMA_WARP) {
-    // ---------------- MMA warp ----------------
-    const uint32_t id_gates = umma_idesc_f16(128, G4, 0, 0);
-    const uint32_t id_dh = umma_idesc_f16(128, 32, 0, 1);      // A = da K-major, B = W_hh MN-major
-    const uint32_t id_dw = umma_idesc_f16(128, 64, 1, 1);      // A = da MN-major, B = [h|x|1] MN-major
-    const uint64_t hi64 = umma_desc_hi(512, 4u), hi128 = umma_desc_hi(1024, 2u);
-    const uint32_t w_addr = smem_u32(sW), h_addr = smem_u32(sH);
-    const uint32_t da_addr = smem_u32(sDA), hx_addr = smem_u32(sHX);
-    uint32_t ph_h = 0, ph_da = 0;
-    bool first_dw = true;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      for (int t = 1; t < T; ++t) {           // forward recompute
-        mbar_wait(h_ready, ph_h);
-        ph_h ^= 1u;
-        tc_fence_after();
-        if (lane == 0) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_f16(TM_GATES, umma_desc(hi64, h_addr + k * 32, 16), umma_desc(hi64, w_addr + k * 32, 16), id_gates, k > 0 ? 1u : 0u);
-          umma_commit(g_ready);
-        }
-        __syncwarp();
-      }
-      for (int t = T - 1; t >= 0; --t) {      // backward through time
-        mbar_wait(da_ready, ph_da);
-        ph_da ^= 1u;
-        tc_fence_after();
-        if (lane == 0) {
-          if (t > 0) {
-            // dh_{t-1} = da (K-major, two 64-gate sub-tiles of [128 cells][128 B]) x W_hh (rows j, K step = 16 rows x 64 B)
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              umma_f16(TM_DH, umma_desc(hi128, da_addr + (k >> 2) * 16384 + (k & 3) * 32, 16), umma_desc(hi64, w_addr + k * 1024, 2048),
-                       id_dh, k > 0 ? 1u : 0u);
-            umma_commit(dh_ready);
-          }
-          // dWext += da^T (MN-major: k rows = cells, 2 m-chunks of 64 gates 16 KB apart) x [h|x|1] (k rows = cells, 128 B)
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_f16(TM_DW, umma_desc(hi128, da_addr + k * 2048, 16384), umma_desc(hi128, hx_addr + k * 2048, 16384), id_dw,
-                     (first_dw && k == 0) ? 0u : 1u);
-          first_dw = false;
-          umma_commit(da_free);
-        }
-        __syncwarp();
-      }
-    }
-    if (lane == 0) umma_commit(acc_done);
-    __syncwarp();
-  } else {
-    // ---------------- epilogue warps: thread = (cell row, unit half) ----------------
-    const int hh = warp >> 2;
-    const int row = (warp & 3) * 32 + lane;
-    const int u0 = UN * hh;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    // per-thread stash base: CTA ring + this thread's row + its unit half (chunks 2*hh, 2*hh+1 of every block); see stash_at()
-    __half* my_stash = scratch + (size_t)blockIdx.x * T * CELLS * STASH + (size_t)(2 * hh) * CELLS * 8 + (size_t)row * 8;
-    uint32_t ph_g = 0, ph_dh = 0, ph_free = 0;
-    long long da_uses = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const long long cell = tile * CELLS + row;
-      const bool live = cell < cells;
-      const size_t xb = live ? x_base(cell, T, NN) : 0;
-      // ---- (1) recompute forward, stash per step ----
-      {
-        float c[UN], h[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) c[u] = 0.f;
-        for (int t = 0; t < T; ++t) {
-          const float xv = live ? x_seq[xb + (size_t)t * NN] : 0.f;
-          if (t > 0) {
-            mbar_wait(g_ready, ph_g);
-            ph_g ^= 1u;
-            tc_fence_after();
-          }
-          cell_step<true, (MPGCN_LSTM_BWD_PAIRED != 0)>(TM_GATES + lane_base + u0, t > 0, xv, s_bias, s_wih, u0, c, h, my_stash, t, hh);
-          if (t + 1 < T) {
-            write_h_tile(sH, row, hh, h);
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(h_ready);
-          }
-        }
-      }
-      // ---- (2) backward through time ----
-      // The running gradients dh, dc (fp32, power-of-two scaled) live in TMEM, not in registers: dh in the columns the
-      // dh MMA writes (TM_DH), dc in the gate-accumulator columns, which are idle during this phase.  Seed them here.
-      const uint32_t t_dh = TM_DH + lane_base + u0, t_dc = TM_GATES + lane_base + u0;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint32_t r[8];
-#pragma unroll
-        for (int e = 0; e < 8; e += 4) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live) v = *reinterpret_cast<const float4*>(d_hT + (size_t)cell * C + u0 + 8 * q + e);
-          r[e] = __float_as_uint(v.x * S); r[e + 1] = __float_as_uint(v.y * S);
-          r[e + 2] = __float_as_uint(v.z * S); r[e + 3] = __float_as_uint(v.w * S);
-        }
-        tmem_st_32x8(t_dh + 8 * q, r);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) r[e] = 0u;
-        tmem_st_32x8(t_dc + 8 * q, r);
-      }
-      tmem_st_wait();
-      // c(t) is carried from the previous iteration (where it was loaded as c(t-1)); seed it with c(T-1)
-      uint4 vc[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) vc[q] = *stash_at(my_stash, T - 1, 4 * 4 + q);
-      for (int t = T - 1; t >= 0; --t) {
-        // issue the step's stash loads first (own 16 units of i f g o; c of step t-1); h(t-1) goes global -> smem directly
-        uint4 vi[2], vf[2], vg[2], vo[2], vcp[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          vi[q] = *stash_at(my_stash, t, 0 * 4 + q);
-          vf[q] = *stash_at(my_stash, t, 1 * 4 + q);
-          vg[q] = *stash_at(my_stash, t, 2 * 4 + q);
-          vo[q] = *stash_at(my_stash, t, 3 * 4 + q);
-          vcp[q] = make_uint4(0, 0, 0, 0);
-          if (t > 0) vcp[q] = *stash_at(my_stash, t - 1, 4 * 4 + q);
-        }
-        const float xv = live ? x_seq[xb + (size_t)t * NN] : 0.f;
-        if (da_uses > 0) {                 // the MMAs that read the da / [h|x|1] tiles one step ago must have retired
-          mbar_wait(da_free, ph_free);
-          ph_free ^= 1u;
-        }
-        da_uses++;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {       // h_{t-1}, this thread's 16 units, straight into the [h | x | 1 | 0] tile
-          uint8_t* dst = sHX + sw128_off(row, 2 * hh + q);
-          if (t > 0) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(stash_at(my_stash, t - 1, 5 * 4 + q)) : "memory");
-          } else {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-        float dx_acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float fi[8], ff[8], fg[8], fo[8], fc[8], fcp[8];
-          unpack8(vi[q], fi); unpack8(vf[q], ff); unpack8(vg[q], fg); unpack8(vo[q], fo); unpack8(vc[q], fc); unpack8(vcp[q], fcp);
-          float di[8], df[8], dg[8], d_o[8];
-          uint32_t rdh[8], rdc[8];
-          tmem_ld_32x8(t_dh + 8 * q, rdh);
-          tmem_ld_32x8(t_dc + 8 * q, rdc);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int u = 8 * q + e;
-            const float tcv = tanh_(fc[e]);
-            const float dhv = __uint_as_float(rdh[e]);
-            const float dcv = fmaf(dhv * fo[e], 1.f - tcv * tcv, __uint_as_float(rdc[e]));
-            d_o[e] = dhv * tcv * fo[e] * (1.f - fo[e]);
-            di[e] = dcv * fg[e] * fi[e] * (1.f - fi[e]);
-            df[e] = dcv * fcp[e] * ff[e] * (1.f - ff[e]);
-            dg[e] = dcv * fi[e] * (1.f - fg[e] * fg[e]);
-            rdc[e] = __float_as_uint(dcv * ff[e]);
-            if (d_x != nullptr)
-              dx_acc += di[e] * s_wih[u0 + u] + df[e] * s_wih[C + u0 + u] + dg[e] * s_wih[2 * C + u0 + u] + d_o[e] * s_wih[3 * C + u0 + u];
-          }
-          // gate j = blk*32 + u0 + 8q .. +7  ->  sub-tile (j >> 6), 16-byte chunk ((j & 63) >> 3)
-#define MPGCN_ST_DA(blk, arr)                                                                              \
-  *reinterpret_cast<uint4*>(sDA + (((blk) * 32 + u0 + 8 * q) >> 6) * 16384 +                               \
-                            sw128_off(row, (((blk) * 32 + u0 + 8 * q) & 63) >> 3)) = pack8(arr)
-          MPGCN_ST_DA(0, di);
-          MPGCN_ST_DA(1, df);
-          MPGCN_ST_DA(2, dg);
-          MPGCN_ST_DA(3, d_o);
-#undef MPGCN_ST_DA
-          tmem_st_32x8(t_dc + 8 * q, rdc);
-        }
-        // columns 32..63 of the [h | x | 1 | 0] row: half 0 writes chunks 4,5 and half 1 chunks 6,7
-        if (hh == 0) {
-          *reinterpret_cast<uint4*>(sHX + sw128_off(row, 4)) = make_uint4(pack2(xv, 1.f), 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(sHX + sw128_off(row, 5)) = make_uint4(0u, 0u, 0u, 0u);
-        } else {
-          *reinterpret_cast<uint4*>(sHX + sw128_off(row, 6)) = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(sHX + sw128_off(row, 7)) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (d_x != nullptr && live) atomicAdd(&d_x[xb + (size_t)t * NN], dx_acc * invS);   // two halves per cell
-#pragma unroll
-        for (int q = 0; q < 2; ++q) vc[q] = vcp[q];
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        tmem_st_wait();
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(da_ready);
-        if (t > 0) {                        // dh_{t-1} is complete in TMEM once the dh MMA of this step retires
-          mbar_wait(dh_ready, ph_dh);
-          ph_dh ^= 1u;
-          tc_fence_after();
-        }
-      }
-    }
-    // ---- flush the weight-gradient accumulator: TMEM lane = gate row j, this thread's 16 columns ----
-    mbar_wait(acc_done, 0);
-    tc_fence_after();
-    if (tiles > (long long)blockIdx.x) {
-      uint32_t r[UN];
-      tmem_ld_32x16(TM_DW + lane_base + u0, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int k = 0; k < UN; ++k) atomicAdd(&d_w_hh[row * C + u0 + k], __uint_as_float(r[k]) * invS);
-      if (hh == 0) {
-        tmem_ld_32x16(TM_DW + lane_base + 32, r);
-        tmem_ld_wait();
-        atomicAdd(&d_w_ih[row], __uint_as_float(r[0]) * invS);
-        atomicAdd(&d_b[row], __uint_as_float(r[1]) * invS);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1033,21 +593,18 @@ static int lstm_grid(long long cells) {
   return (int)(g < tiles ? g : tiles);
 }
 
-size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN) {
-  const long long cells = (long long)B * NN;
-  return 1024 + (size_t)lstm_grid(cells) * T * lstm_tc::CELLS * lstm_tc::STASH * sizeof(__half);
-}
-
 // dynamic shared memory requests: just what the kernels carve (registers already limit residency to two CTAs per SM,
 // whose TMEM allocations -- 2 x 128 / 2 x 256 columns -- always fit); the rest of the 228 KB stays L1
 static const int kLstmFwdSmem = 34 * 1024;
-static const int kLstmSmem = 72 * 1024;
-static const int kLstmSavedSmem = 107 * 1024;     // saved-state backward: + second hx buffer + extended weight tile
+static const int kLstmSavedSmem = 107 * 1024;     // da tile + three hx buffers + both weight tiles
 
 size_t lstm_tc_saved_bytes(int B, int T, long long NN) {
   const long long tiles = ((long long)B * NN + lstm_tc::CELLS - 1) / lstm_tc::CELLS;
   return (size_t)tiles * T * lstm_tc::SAVE_CHUNKS * lstm_tc::CELLS * 16;
 }
+
+// without a saved buffer from the forward, the backward first re-runs the (training) forward into its workspace
+size_t lstm_tc_bwd_workspace_bytes(int B, int T, long long NN) { return 1024 + align_up(lstm_tc_saved_bytes(B, T, NN), 256); }
 
 int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
                          void* saved, int B, int T, long long NN, cudaStream_t st) {
@@ -1083,30 +640,25 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   MPGCN_CHECK(saved == nullptr || (reinterpret_cast<uintptr_t>(saved) & 15) == 0, "lstm backward: saved buffer must be 16-byte aligned");
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "lstm backward: workspace must be 256-byte aligned");
   float* scale2 = static_cast<float*>(ws);
-  __half* scratch = reinterpret_cast<__half*>(static_cast<uint8_t*>(ws) + 1024);
+  if (saved == nullptr) {          // the caller kept no forward state: rebuild it (same kernel, same bits as the training forward)
+    void* tmp = static_cast<uint8_t*>(ws) + 1024;
+    if (int e = lstm_last_forward_tc(x_seq, w_ih, w_hh, b_ih, b_hh, nullptr, tmp, B, T, NN, st)) return e;
+    saved = tmp;
+  }
   if (int e = grad_scale_prepare(d_hT, (size_t)cells * C, scale2, d_hT_absmax, st)) return e;
   MPGCN_CUDA(cudaMemsetAsync(d_w_ih, 0, sizeof(float) * G4, st));
   MPGCN_CUDA(cudaMemsetAsync(d_w_hh, 0, sizeof(float) * G4 * C, st));
   MPGCN_CUDA(cudaMemsetAsync(d_b_ih, 0, sizeof(float) * G4, st));
   if (d_x) MPGCN_CUDA(cudaMemsetAsync(d_x, 0, sizeof(float) * (size_t)cells * T, st));
-  const size_t smem = 1024 + DA_BYTES + HX_BYTES + 2 * 8192 + 2 * G4 * sizeof(float) + 256;
   static bool attr = false;
   if (!attr) {
-    MPGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmSmem));
     MPGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_saved_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmSavedSmem));
     attr = true;
   }
-  MPGCN_CHECK(smem <= (size_t)kLstmSmem, "internal: lstm backward smem");
-  if (saved) {
-    prof_begin(PROF_LSTM_BWD, 12.0 * C * (C + 1) * (double)cells * T, st);
-    static_assert(1024 + DA_BYTES + 3 * HX_BYTES + WX_BYTES + 8192 + 2 * G4 * sizeof(float) + 256 <= (size_t)kLstmSavedSmem, "smem");
-    lstm_bwd_saved_tc_kernel<2><<<lstm_grid(cells), 256, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
-                                                                               static_cast<const __half*>(saved), scale2, cells, T, NN);
-  } else {
-    prof_begin(PROF_LSTM_BWD, 16.0 * C * (C + 1) * (double)cells * T, st);
-    lstm_bwd_tc_kernel<<<lstm_grid(cells), THREADS, kLstmSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x, scratch,
-                                                                     scale2, cells, T, NN);
-  }
+  static_assert(1024 + DA_BYTES + 3 * HX_BYTES + WX_BYTES + 8192 + 2 * G4 * sizeof(float) + 256 <= (size_t)kLstmSavedSmem, "smem");
+  prof_begin(PROF_LSTM_BWD, 12.0 * C * (C + 1) * (double)cells * T, st);
+  lstm_bwd_saved_tc_kernel<2><<<lstm_grid(cells), 256, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
+                                                                             static_cast<const __half*>(saved), scale2, cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
   prof_count(PROF_ELEMENTWISE);

@@ -133,7 +133,8 @@ def test_lstm_tensor_path_agrees_with_fp32_path(S, T, gmag, xmag, cuda_device):
 @pytest.mark.parametrize("S,T", [(700, 12), (130, 2), (64, 1)])
 def test_lstm_saved_state_backward_agrees_with_recompute_backward(S, T, cuda_device):
     """The two C-ABI backward flavours of the tcgen05 LSTM: (a) forward_train keeps c_t/h_t and backward_saved walks them,
-    (b) plain forward + backward_ex recomputes the recurrence.  Same hT bits; gradients within the fp16-stash noise."""
+    (b) plain forward + backward_ex, which rebuilds that state in its workspace first.  Same hT bits, same gradients (up to
+    the order of the atomic weight-gradient flush)."""
     from mpgcn_b200 import _lib
     lib = _lib.load()
     torch.manual_seed(7 * S + T)
