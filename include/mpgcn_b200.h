@@ -68,6 +68,34 @@ MPGCN_API int mpgcn_bdgcn_backward(const float* d_out, const float* out, const f
                          const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
                          int K, int C, int H, int precision, void* stream);
 
+/* Optional side inputs / outputs of the tensor-core layer (precision 1; ignored by precision 0).  They carry what a caller that
+ * chains layers already has, so that the library does not redo it; every field is nullable and results do not depend on them:
+ *   go_prepared, gd_prepared   supports converted once by mpgcn_bdgcn_prepare_supports (the same G_o / G_d serve every layer of a
+ *                              branch, forward and backward -- "each support staged once and reused");
+ *   x_f16                      forward: an fp16 copy of X (same layout), e.g. the out_f16 of the previous layer: skips the cast;
+ *   out_f16                    forward: receives an fp16 copy of `out`;  backward: that copy, read for the ReLU mask instead of
+ *                              the fp32 `out` (`out` may then be NULL);
+ *   d_out_absmax, dX_absmax    backward: the gradient-magnitude hand-over described below. */
+typedef struct mpgcn_bdgcn_extras {
+  const void* go_prepared;
+  const void* gd_prepared;
+  const void* x_f16;
+  void* out_f16;
+  const float* d_out_absmax;
+  float* dX_absmax;
+} mpgcn_bdgcn_extras;
+
+/* planes = (dynamic ? B : 1) * K support matrices [N,N] -> fp16 padded copy + diagonal remainders (256-byte aligned buffer) */
+MPGCN_API size_t mpgcn_bdgcn_supports_prepared_bytes(long long planes, int N);
+MPGCN_API int mpgcn_bdgcn_prepare_supports(const float* G, void* prepared, size_t prepared_bytes, long long planes, int N, void* stream);
+/* mpgcn_bdgcn_forward / mpgcn_bdgcn_backward with the optional extras (extras == NULL: identical to the plain calls) */
+MPGCN_API int mpgcn_bdgcn_forward_x(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, const float* bias, int act,
+                          float* out, void* saved, void* workspace, size_t workspace_bytes, int B, int N, int K, int C, int H,
+                          int precision, const mpgcn_bdgcn_extras* extras, void* stream);
+MPGCN_API int mpgcn_bdgcn_backward_x(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
+                           const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
+                           int K, int C, int H, int precision, const mpgcn_bdgcn_extras* extras, void* stream);
+
 /* Same, with the gradient-magnitude hand-over used by the fp16 path: d_out_absmax (nullable) = device scalar already holding
  * max|d_out| (as written by the call that produced d_out; skips one pass over d_out); dX_absmax (nullable) receives max|dX|
  * (0 when unknown).  Pure optimisation: results are identical with or without the hints. */

@@ -42,6 +42,12 @@ _SIGS = {
     "mpgcn_profile_reset": (None, []),
     "mpgcn_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "mpgcn_debug_tc_workspace_offset": (ctypes.c_longlong, [ctypes.c_int] * 5),
+    "mpgcn_bdgcn_supports_prepared_bytes": (ctypes.c_size_t, [ctypes.c_longlong, ctypes.c_int]),
+    "mpgcn_bdgcn_prepare_supports": (ctypes.c_int, [_c_f, _c_f, ctypes.c_size_t, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
+    "mpgcn_bdgcn_forward_x": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int, _c_f, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, ctypes.c_size_t] +
+                              [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_void_p]),
+    "mpgcn_bdgcn_backward_x": (ctypes.c_int, [_c_f, _c_f, _c_f, _c_f, ctypes.c_int, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, _c_f,
+                                              ctypes.c_size_t] + [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_void_p]),
     "mpgcn_bdgcn_backward_ex": (ctypes.c_int, [_c_f, _c_f, _c_f, _c_f, ctypes.c_int, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, _c_f,
                                                ctypes.c_size_t] + [ctypes.c_int] * 6 + [_c_f, _c_f, ctypes.c_void_p]),
     "mpgcn_lstm_last_backward_ex": (ctypes.c_int, [_c_f] * 12 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
@@ -61,6 +67,12 @@ _SIGS = {
                                                 ctypes.c_int, ctypes.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+class BdgcnExtras(ctypes.Structure):
+    """mpgcn_bdgcn_extras (include/mpgcn_b200.h): optional side inputs / outputs of the tensor-core layer."""
+    _fields_ = [("go_prepared", ctypes.c_void_p), ("gd_prepared", ctypes.c_void_p), ("x_f16", ctypes.c_void_p),
+                ("out_f16", ctypes.c_void_p), ("d_out_absmax", ctypes.c_void_p), ("dX_absmax", ctypes.c_void_p)]
 
 
 def build(verbose: bool = False) -> str:

@@ -55,39 +55,70 @@ size_t mpgcn_bdgcn_bwd_workspace_bytes(int B, int N, int K, int C, int H, int dy
   return precision == PREC_FP16_TC ? tc_bwd_ws_bytes(s) : simt_bwd_ws_bytes(s);
 }
 
-int mpgcn_bdgcn_forward(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, const float* bias, int act,
-                        float* out, void* saved, void* workspace, size_t workspace_bytes, int B, int N, int K, int C, int H,
-                        int precision, void* stream) {
+static BdgcnExtras to_extras(const mpgcn_bdgcn_extras* x) {
+  BdgcnExtras e;
+  if (x) {
+    e.go_prepared = x->go_prepared; e.gd_prepared = x->gd_prepared; e.x_f16 = x->x_f16; e.out_f16 = x->out_f16;
+    e.d_out_absmax = x->d_out_absmax; e.dx_absmax = x->dX_absmax;
+  }
+  return e;
+}
+
+size_t mpgcn_bdgcn_supports_prepared_bytes(long long planes, int N) { return (planes >= 1 && N >= 1) ? bdgcn_supports_prepared_bytes(planes, N) : 0; }
+
+int mpgcn_bdgcn_prepare_supports(const float* G, void* prepared, size_t prepared_bytes, long long planes, int N, void* stream) {
+  MPGCN_CHECK(G && prepared && planes >= 1 && N >= 1, "mpgcn_bdgcn_prepare_supports: bad argument");
+  MPGCN_CHECK(prepared_bytes >= bdgcn_supports_prepared_bytes(planes, N), "mpgcn_bdgcn_prepare_supports: buffer too small (%zu < %zu)",
+              prepared_bytes, bdgcn_supports_prepared_bytes(planes, N));
+  return bdgcn_prepare_supports(G, prepared, planes, N, static_cast<cudaStream_t>(stream));
+}
+
+int mpgcn_bdgcn_forward_x(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, const float* bias, int act,
+                          float* out, void* saved, void* workspace, size_t workspace_bytes, int B, int N, int K, int C, int H,
+                          int precision, const mpgcn_bdgcn_extras* extras, void* stream) {
   const BdgcnShape s = mk(B, N, K, C, H, dynamic ? 1 : 0, act);
   if (int e = check_shape(s, precision)) return e;
   MPGCN_CHECK(X && G_o && G_d && W && out && workspace, "mpgcn_bdgcn_forward: null pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (precision == PREC_FP16_TC) return bdgcn_forward_tc(s, X, G_o, G_d, W, bias, out, saved, workspace, workspace_bytes, st);
-  return bdgcn_forward_simt(s, X, G_o, G_d, W, bias, out, saved, workspace, workspace_bytes, st);
+  if (precision == PREC_FP16_TC) return bdgcn_forward_tc(s, X, G_o, G_d, W, bias, out, saved, workspace, workspace_bytes, to_extras(extras), st);
+  return bdgcn_forward_simt(s, X, G_o, G_d, W, bias, out, saved, workspace, workspace_bytes, st);      // exact path: extras unused
 }
 
-int mpgcn_bdgcn_backward_ex(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
-                            const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
-                            int K, int C, int H, int precision, const float* d_out_absmax, float* dX_absmax, void* stream);
+int mpgcn_bdgcn_forward(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, const float* bias, int act,
+                        float* out, void* saved, void* workspace, size_t workspace_bytes, int B, int N, int K, int C, int H,
+                        int precision, void* stream) {
+  return mpgcn_bdgcn_forward_x(X, G_o, G_d, dynamic, W, bias, act, out, saved, workspace, workspace_bytes, B, N, K, C, H, precision,
+                               nullptr, stream);
+}
 
-int mpgcn_bdgcn_backward(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
-                         const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
-                         int K, int C, int H, int precision, void* stream) {
-  return mpgcn_bdgcn_backward_ex(d_out, out, G_o, G_d, dynamic, W, act, saved, dX, dW, db, workspace, workspace_bytes, B, N, K, C, H,
-                                 precision, nullptr, nullptr, stream);
+int mpgcn_bdgcn_backward_x(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
+                           const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
+                           int K, int C, int H, int precision, const mpgcn_bdgcn_extras* extras, void* stream) {
+  const BdgcnShape s = mk(B, N, K, C, H, dynamic ? 1 : 0, act);
+  if (int e = check_shape(s, precision)) return e;
+  const bool have_out16 = extras && extras->out_f16 && precision == PREC_FP16_TC;
+  MPGCN_CHECK(d_out && (out || have_out16) && G_o && G_d && W && saved && dW && workspace, "mpgcn_bdgcn_backward: null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == PREC_FP16_TC)
+    return bdgcn_backward_tc(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, to_extras(extras), st);
+  if (extras && extras->dX_absmax) MPGCN_CUDA(cudaMemsetAsync(extras->dX_absmax, 0, sizeof(float), st));      // "unknown"
+  return bdgcn_backward_simt(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, st);
 }
 
 int mpgcn_bdgcn_backward_ex(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
                             const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
                             int K, int C, int H, int precision, const float* d_out_absmax, float* dX_absmax, void* stream) {
-  const BdgcnShape s = mk(B, N, K, C, H, dynamic ? 1 : 0, act);
-  if (int e = check_shape(s, precision)) return e;
-  MPGCN_CHECK(d_out && out && G_o && G_d && W && saved && dW && workspace, "mpgcn_bdgcn_backward: null pointer argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (precision == PREC_FP16_TC)
-    return bdgcn_backward_tc(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, d_out_absmax, dX_absmax, st);
-  if (dX_absmax) MPGCN_CUDA(cudaMemsetAsync(dX_absmax, 0, sizeof(float), st));   // fp32 path: no hint produced (0 = "unknown")
-  return bdgcn_backward_simt(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, st);
+  mpgcn_bdgcn_extras x{};
+  x.d_out_absmax = d_out_absmax; x.dX_absmax = dX_absmax;
+  return mpgcn_bdgcn_backward_x(d_out, out, G_o, G_d, dynamic, W, act, saved, dX, dW, db, workspace, workspace_bytes, B, N, K, C, H,
+                                precision, &x, stream);
+}
+
+int mpgcn_bdgcn_backward(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
+                         const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
+                         int K, int C, int H, int precision, void* stream) {
+  return mpgcn_bdgcn_backward_x(d_out, out, G_o, G_d, dynamic, W, act, saved, dX, dW, db, workspace, workspace_bytes, B, N, K, C, H,
+                                precision, nullptr, stream);
 }
 
 int mpgcn_adj_num_supports(int kernel_type, int K) { return adj_num_supports(kernel_type, K); }

@@ -249,8 +249,8 @@ static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, in
 }
 
 // FWD_B: out[b][m][e][h] = act( sum_{(o,n)} Gflat[(o,n)][m] U16[b][(o,n)][e][h] + bias[h] )
-static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16, const float* bias, float* out, const float* delta_o,
-                     cudaStream_t st) {
+static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16, const float* bias, float* out, __half* out16,
+                     const float* delta_o, cudaStream_t st) {
   const int N = s.N, K = s.K, Np = pad8(N);
   GemmParams p;
   init_params(p);
@@ -267,7 +267,7 @@ static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16,
   p.bm = omap(1, kBig, 1, 0, 0);
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;
   p.kb_total = p.kb_per_seg = ceil_div((long long)K * N, 64);
-  p.ep.out = out; p.ep.out_f16 = 0;
+  p.ep.out = out; p.ep.out_f16 = 0; p.ep.out16 = out16;
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
   p.ep.bias = bias; p.ep.relu = s.act;
@@ -345,16 +345,34 @@ static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16
   return launch_big(tc::A_K128, p, N, st);
 }
 
-static int convert_supports(const BdgcnShape& s, const float* Go, const float* Gd, __half* go16, __half* gd16, const __half** go_used,
-                            cudaStream_t st) {
-  const size_t rows = (size_t)(s.dynamic ? s.B : 1) * s.K * s.N;
-  if (int e = cvt_f32_to_f16_padded(Gd, gd16, rows, s.N, pad8(s.N), st)) return e;
-  if (Go == Gd) {
-    *go_used = gd16;
-  } else {
-    if (int e = cvt_f32_to_f16_padded(Go, go16, rows, s.N, pad8(s.N), st)) return e;
-    *go_used = go16;
+// Prepared supports: [planes][N][Np] fp16 (padding zeroed) followed, 256-byte aligned, by the [planes][N] diagonal remainders.
+// A caller that uses the same supports for several layers / for forward and backward converts them once.
+static size_t prep_g16_bytes(long long planes, int N) { return align_up((size_t)planes * N * pad8(N) * sizeof(__half), 256); }
+size_t bdgcn_supports_prepared_bytes(long long planes, int N) { return prep_g16_bytes(planes, N) + align_up((size_t)planes * N * sizeof(float), 256); }
+int bdgcn_prepare_supports(const float* G, void* prepared, long long planes, int N, cudaStream_t st) {
+  MPGCN_CHECK((reinterpret_cast<uintptr_t>(prepared) & 255) == 0, "prepared-supports buffer must be 256-byte aligned");
+  __half* g16 = static_cast<__half*>(prepared);
+  float* delta = reinterpret_cast<float*>(static_cast<uint8_t*>(prepared) + prep_g16_bytes(planes, N));
+  if (int e = cvt_f32_to_f16_padded(G, g16, (size_t)planes * N, N, pad8(N), st)) return e;
+  return support_diag_delta(G, delta, (size_t)planes, N, st);
+}
+
+// resolves the fp16 supports (and, for the forward, the diagonal remainders) of one side: prepared by the caller, shared
+// with the other side (static graph: Go == Gd), or converted here into the workspace
+struct SideG { const __half* g16; const float* delta; };
+static int resolve_side(const BdgcnShape& s, const float* G, const void* prepared, __half* ws16, float* ws_delta, bool want_delta,
+                        SideG* out, cudaStream_t st) {
+  const long long planes = (long long)(s.dynamic ? s.B : 1) * s.K;
+  if (prepared) {
+    MPGCN_CHECK((reinterpret_cast<uintptr_t>(prepared) & 255) == 0, "prepared-supports buffer must be 256-byte aligned");
+    out->g16 = static_cast<const __half*>(prepared);
+    out->delta = reinterpret_cast<const float*>(static_cast<const uint8_t*>(prepared) + prep_g16_bytes(planes, s.N));
+    return 0;
   }
+  if (int e = cvt_f32_to_f16_padded(G, ws16, (size_t)planes * s.N, s.N, pad8(s.N), st)) return e;
+  if (want_delta) { if (int e = support_diag_delta(G, ws_delta, (size_t)planes, s.N, st)) return e; }
+  out->g16 = ws16;
+  out->delta = ws_delta;
   return 0;
 }
 
@@ -362,46 +380,43 @@ static int convert_supports(const BdgcnShape& s, const float* Go, const float* G
 // layer forward / backward
 // ---------------------------------------------------------------------------------------
 int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const float* Gd, const float* W, const float* bias,
-                     float* out, void* saved, void* ws, size_t ws_bytes, cudaStream_t st) {
+                     float* out, void* saved, void* ws, size_t ws_bytes, const BdgcnExtras& ex, cudaStream_t st) {
   MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d K=%d)", s.C, s.H, s.K);
   const size_t NN = n2(s);
   const FwdLayout L = fwd_layout(s);
   MPGCN_CHECK(ws_bytes >= L.total, "bdgcn_forward: workspace too small (%zu < %zu bytes)", ws_bytes, L.total);
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
   uint8_t* wb = static_cast<uint8_t*>(ws);
-  __half* x16 = reinterpret_cast<__half*>(wb + L.x16);
-  __half* gd16 = reinterpret_cast<__half*>(wb + L.gd16);
-  __half* go16 = reinterpret_cast<__half*>(wb + L.go16);
+  __half* x16_ws = reinterpret_cast<__half*>(wb + L.x16);
   __half* w16 = reinterpret_cast<__half*>(wb + L.w16);
   __half* u16 = reinterpret_cast<__half*>(wb + L.u16);
-  float* delta_d = reinterpret_cast<float*>(wb + L.dd);
-  float* delta_o = reinterpret_cast<float*>(wb + L.dgo);
   __half* z16 = saved ? static_cast<__half*>(saved) : reinterpret_cast<__half*>(wb + L.z16);
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(z16) & 63) == 0, "`saved` buffer must be 64-byte aligned");
+  MPGCN_CHECK(((reinterpret_cast<uintptr_t>(ex.x_f16) | reinterpret_cast<uintptr_t>(ex.out_f16)) & 15) == 0, "fp16 side buffers must be 16-byte aligned");
 
-  const __half* go_used = nullptr;
-  if (int e = cvt_f32_to_f16(X, x16, (size_t)s.B * NN * 32, st)) return e;
-  if (int e = convert_supports(s, Go, Gd, go16, gd16, &go_used, st)) return e;
+  const __half* x16 = static_cast<const __half*>(ex.x_f16);
+  if (x16 == nullptr) {
+    if (int e = cvt_f32_to_f16(X, x16_ws, (size_t)s.B * NN * 32, st)) return e;
+    x16 = x16_ws;
+  }
+  SideG gd{}, go{};
+  if (int e = resolve_side(s, Gd, ex.gd_prepared, reinterpret_cast<__half*>(wb + L.gd16), reinterpret_cast<float*>(wb + L.dd), true, &gd, st)) return e;
+  if (Go == Gd && ex.go_prepared == nullptr) go = gd;
+  else if (int e = resolve_side(s, Go, ex.go_prepared, reinterpret_cast<__half*>(wb + L.go16), reinterpret_cast<float*>(wb + L.dgo), true, &go, st)) return e;
   const size_t wn = (size_t)s.K * s.K * 32 * 32;
   if (int e = cvt_f32_to_f16_hilo(W, w16, w16 + wn, wn, st)) return e;
-  const size_t planes = (size_t)(s.dynamic ? s.B : 1) * s.K;
-  if (int e = support_diag_delta(Gd, delta_d, planes, s.N, st)) return e;
-  const float* delta_o_used = delta_d;
-  if (Go != Gd) {
-    if (int e = support_diag_delta(Go, delta_o, planes, s.N, st)) return e;
-    delta_o_used = delta_o;
-  }
-  if (int e = run_fwd_a(s, gd16, x16, z16, delta_d, st)) return e;
+  if (int e = run_fwd_a(s, gd.g16, x16, z16, gd.delta, st)) return e;
   if (int e = run_mix(s, z16, w16, 2, u16, PROF_FWD_MIX, st)) return e;
-  if (int e = run_fwd_b(s, go_used, u16, bias, out, delta_o_used, st)) return e;
+  if (int e = run_fwd_b(s, go.g16, u16, bias, out, static_cast<__half*>(ex.out_f16), go.delta, st)) return e;
   return 0;
 }
 
 int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out, const float* Go, const float* Gd, const float* W,
-                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, const float* d_out_absmax,
-                      float* dx_absmax, cudaStream_t st) {
+                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, const BdgcnExtras& ex,
+                      cudaStream_t st) {
   MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d K=%d)", s.C, s.H, s.K);
   MPGCN_CHECK(saved != nullptr, "bdgcn_backward: forward was run without a `saved` buffer");
+  MPGCN_CHECK(out != nullptr || ex.out_f16 != nullptr || !s.act, "bdgcn_backward: the ReLU mask needs `out` or its fp16 copy");
   const size_t NN = n2(s);
   const __half* z16 = static_cast<const __half*>(saved);
   const BwdLayout L = bwd_layout(s);
@@ -409,28 +424,34 @@ int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out,
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
   uint8_t* wb = static_cast<uint8_t*>(ws);
   __half* dp16 = reinterpret_cast<__half*>(wb + L.dp16);
-  __half* gd16 = reinterpret_cast<__half*>(wb + L.gd16);
-  __half* go16 = reinterpret_cast<__half*>(wb + L.go16);
   __half* v16 = reinterpret_cast<__half*>(wb + L.v16);
   __half* y16 = reinterpret_cast<__half*>(wb + L.y16);
   __half* wq16 = reinterpret_cast<__half*>(wb + L.wq16);
   float* partials = reinterpret_cast<float*>(wb + L.partials);
   float* scale2 = reinterpret_cast<float*>(wb + L.scale);   // [S, 1/S]: power-of-two gradient scale (fp16 range)
 
-  const __half* go_used = nullptr;
   if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 32, st));
-  if (int e = grad_scale_prepare(d_out, (size_t)s.B * NN * 32, scale2, d_out_absmax, st)) return e;
-  if (int e = relu_bwd_prep(d_out, out, s.act, dp16, nullptr, db, (size_t)s.B * NN * 32, 32, scale2, st)) return e;
-  if (int e = convert_supports(s, Go, Gd, go16, gd16, &go_used, st)) return e;
-  if (int e = run_bwd_v(s, go_used, dp16, v16, st)) return e;
+  if (int e = grad_scale_prepare(d_out, (size_t)s.B * NN * 32, scale2, ex.d_out_absmax, st)) return e;
+  if (ex.out_f16 != nullptr) {
+    if (int e = relu_bwd_prep_f16mask(d_out, static_cast<const __half*>(ex.out_f16), s.act, dp16, db, (size_t)s.B * NN * 32, 32, scale2, st)) return e;
+  } else {
+    if (int e = relu_bwd_prep(d_out, out, s.act, dp16, nullptr, db, (size_t)s.B * NN * 32, 32, scale2, st)) return e;
+  }
+  SideG gd{}, go{};
+  if (dX || Go == Gd) {
+    if (int e = resolve_side(s, Gd, ex.gd_prepared, reinterpret_cast<__half*>(wb + L.gd16), nullptr, false, &gd, st)) return e;
+  }
+  if (Go == Gd && ex.go_prepared == nullptr) go = gd;
+  else if (int e = resolve_side(s, Go, ex.go_prepared, reinterpret_cast<__half*>(wb + L.go16), nullptr, false, &go, st)) return e;
+  if (int e = run_bwd_v(s, go.g16, dp16, v16, st)) return e;
   int slices = 0, mt = 0;
   if (int e = run_bwd_dw(s, z16, v16, partials, &slices, &mt, st)) return e;
   if (int e = reduce_dw_partials(partials, dW, slices, mt, s.K, scale2 + 1, st)) return e;
   if (dX) {
-    if (dx_absmax) MPGCN_CUDA(cudaMemsetAsync(dx_absmax, 0, sizeof(float), st));
+    if (ex.dx_absmax) MPGCN_CUDA(cudaMemsetAsync(ex.dx_absmax, 0, sizeof(float), st));
     if (int e = permute_w_bwd(W, wq16, nullptr, s.K, 32, 32, st)) return e;
     if (int e = run_mix(s, v16, wq16, 1, y16, PROF_BWD_MIX, st)) return e;
-    if (int e = run_bwd_dx(s, gd16, y16, dX, scale2 + 1, dx_absmax, st)) return e;
+    if (int e = run_bwd_dx(s, gd.g16, y16, dX, scale2 + 1, ex.dx_absmax, st)) return e;
   }
   return 0;
 }

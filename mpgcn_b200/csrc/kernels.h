@@ -46,6 +46,9 @@ int cvt_f32_to_f16_padded(const float* src, __half* dst, size_t rows, int cols, 
 // d_pre = d_out * (out > 0) (relu) or d_out; fp16 and/or fp32 output; db[h] += sum (db may be null; pre-zeroed)
 int relu_bwd_prep(const float* d_out, const float* out, int relu, __half* d_pre16, float* d_pre32, float* db, size_t n, int H,
                   const float* scale, cudaStream_t s);
+// the same with the ReLU mask taken from an fp16 copy of the forward output (tensor-core path: fp16 d_pre only, H % 4 == 0)
+int relu_bwd_prep_f16mask(const float* d_out, const __half* out16, int relu, __half* d_pre16, float* db, size_t n, int H,
+                          const float* scale, cudaStream_t s);
 // scale2[0] = S = 2^k with S*max|d_out| in [16,32), scale2[1] = 1/S (S = 1 for an all-zero or non-finite input).
 // fp16 has 5 exponent bits: realistic gradients (MSE mean over B*N*N cells ~ 1e-7) must be rescaled before the cast.
 // absmax_hint: optional device scalar already holding max|d_out| (produced by the epilogue that wrote d_out): skips the pass
@@ -106,10 +109,21 @@ int bdgcn_forward_simt(const BdgcnShape& s, const float* X, const float* Go, con
                        float* out, void* saved, void* ws, size_t ws_bytes, cudaStream_t st);
 int bdgcn_backward_simt(const BdgcnShape& s, const float* d_out, const float* out, const float* Go, const float* Gd, const float* W,
                         const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
+// optional side inputs / outputs of the tensor-core layer (mirror of mpgcn_bdgcn_extras in include/mpgcn_b200.h); all nullable
+struct BdgcnExtras {
+  const void* go_prepared = nullptr;    // supports already converted by bdgcn_prepare_supports (fp16 padded + diagonal remainders)
+  const void* gd_prepared = nullptr;
+  const void* x_f16 = nullptr;          // forward: fp16 copy of X (skips the conversion pass)
+  void* out_f16 = nullptr;              // forward: receives an fp16 copy of out;  backward: that copy (ReLU mask source instead of out)
+  const float* d_out_absmax = nullptr;  // backward: max|d_out| already known
+  float* dx_absmax = nullptr;           // backward: receives max|dX|
+};
+size_t bdgcn_supports_prepared_bytes(long long planes, int N);
+int bdgcn_prepare_supports(const float* G, void* prepared, long long planes, int N, cudaStream_t st);
 int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const float* Gd, const float* W, const float* bias,
-                     float* out, void* saved, void* ws, size_t ws_bytes, cudaStream_t st);
+                     float* out, void* saved, void* ws, size_t ws_bytes, const BdgcnExtras& ex, cudaStream_t st);
 int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out, const float* Go, const float* Gd, const float* W,
-                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, const float* d_out_absmax,
-                      float* dx_absmax, cudaStream_t st);
+                      const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, const BdgcnExtras& ex,
+                      cudaStream_t st);
 
 }  // namespace mpgcn

@@ -306,6 +306,53 @@ __global__ void relu_bwd_prep_vec4_kernel(const float4* __restrict__ d_out, cons
   }
 }
 
+__global__ void relu_bwd_prep_f16mask_kernel(const float4* __restrict__ d_out, const uint2* __restrict__ out16, int relu,
+                                             uint2* __restrict__ d16, float* __restrict__ db, size_t n4, int H4,
+                                             const float* __restrict__ scale) {
+  const float S = scale ? __ldg(scale) : 1.f;
+  extern __shared__ float s_db[];   // [4][blockDim.x]
+  const size_t stride = (size_t)gridDim.x * blockDim.x;   // multiple of H4 by construction
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 g = d_out[i];
+    if (relu) {
+      const uint2 o = out16[i];
+      const float2 o01 = __half22float2(*reinterpret_cast<const __half2*>(&o.x)), o23 = __half22float2(*reinterpret_cast<const __half2*>(&o.y));
+      g.x = o01.x > 0.f ? g.x : 0.f; g.y = o01.y > 0.f ? g.y : 0.f;
+      g.z = o23.x > 0.f ? g.z : 0.f; g.w = o23.y > 0.f ? g.w : 0.f;
+    }
+    const __half2 a = __halves2half2(f2h_sat(g.x * S), f2h_sat(g.y * S)), b = __halves2half2(f2h_sat(g.z * S), f2h_sat(g.w * S));
+    d16[i] = make_uint2(*reinterpret_cast<const unsigned int*>(&a), *reinterpret_cast<const unsigned int*>(&b));
+    l0 += g.x; l1 += g.y; l2 += g.z; l3 += g.w;
+  }
+  if (db) {
+    const int nt = blockDim.x;
+    s_db[threadIdx.x] = l0; s_db[nt + threadIdx.x] = l1; s_db[2 * nt + threadIdx.x] = l2; s_db[3 * nt + threadIdx.x] = l3;
+    __syncthreads();
+    if ((int)threadIdx.x < 4 * H4) {
+      const int q = threadIdx.x >> 2, e = threadIdx.x & 3;
+      float sum = 0.f;
+      for (int t = q; t < nt; t += H4) sum += s_db[e * nt + t];
+      const int quad0 = (int)(((size_t)blockIdx.x * blockDim.x) % H4);
+      atomicAdd(&db[((q + quad0) % H4) * 4 + e], sum);
+    }
+  }
+}
+
+int relu_bwd_prep_f16mask(const float* d_out, const __half* out16, int relu, __half* d16, float* db, size_t n, int H, const float* scale,
+                          cudaStream_t s) {
+  if (n == 0) return 0;
+  MPGCN_CHECK(H % 4 == 0 && 256 % (H / 4) == 0 && n % 4 == 0, "relu_bwd_prep_f16mask: H=%d / n=%zu unsupported", H, n);
+  MPGCN_CHECK(((reinterpret_cast<uintptr_t>(d_out) & 15) | (reinterpret_cast<uintptr_t>(out16) & 7) | (reinterpret_cast<uintptr_t>(d16) & 7)) == 0,
+              "relu_bwd_prep_f16mask: misaligned pointer");
+  const int threads = 256;
+  prof_count(PROF_ELEMENTWISE);
+  relu_bwd_prep_f16mask_kernel<<<grid_for(n / 4, threads), threads, 4 * threads * sizeof(float), s>>>(
+      reinterpret_cast<const float4*>(d_out), reinterpret_cast<const uint2*>(out16), relu, reinterpret_cast<uint2*>(d16), db, n / 4, H / 4, scale);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int relu_bwd_prep(const float* d_out, const float* out, int relu, __half* d16, float* d32, float* db, size_t n, int H,
                   const float* scale, cudaStream_t s) {
   if (n == 0) return 0;

@@ -94,14 +94,49 @@ def _take_hint(node, grad):
     return e[3] if (e[0] == grad.data_ptr() and e[1] == grad._version and e[2] == grad.numel()) else None
 
 
+# Supports staged once: the same G_o / G_d serve every layer of a branch, forward and backward (6 calls per training step),
+# so their fp16 conversion (+ diagonal remainders) is cached per support TENSOR OBJECT.  An entry is valid only while that
+# very object is alive (weak reference), unmodified (version counter), at the same address and used on the same stream.
+_SUPPORT_CACHE = {}
+_SUPPORT_CACHE_MAX = 16
+
+
+def _prepared_supports(lib, G, Gc, planes: int, N: int):
+    import weakref
+    key = id(G)
+    stream = _stream()
+    e = _SUPPORT_CACHE.get(key)
+    if e is not None:
+        ref, ver, ptr, st, blob = e
+        if ref() is G and ver == G._version and ptr == Gc.data_ptr() and st == stream and blob.device == Gc.device:
+            return blob
+        del _SUPPORT_CACHE[key]
+    if len(_SUPPORT_CACHE) >= _SUPPORT_CACHE_MAX:
+        for k in [k for k, v in _SUPPORT_CACHE.items() if v[0]() is None]:
+            del _SUPPORT_CACHE[k]
+        while len(_SUPPORT_CACHE) >= _SUPPORT_CACHE_MAX:
+            _SUPPORT_CACHE.pop(next(iter(_SUPPORT_CACHE)))
+    nbytes = lib.mpgcn_bdgcn_supports_prepared_bytes(planes, N)
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=Gc.device)
+    with torch.cuda.device(Gc.device):
+        _lib.check(lib.mpgcn_bdgcn_prepare_supports(_ptr(Gc), _ptr(blob), nbytes, planes, N, stream), "bdgcn_prepare_supports")
+    try:
+        _SUPPORT_CACHE[key] = (weakref.ref(G), G._version, Gc.data_ptr(), stream, blob)
+    except TypeError:        # not weak-referenceable: do not cache
+        pass
+    return blob
+
+
 class _BDGCNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, X, G_o, G_d, W, b, dynamic: bool, act: int, precision):
+        import ctypes
         lib = _lib.load()
         B, N, N2, C = X.shape
         K = G_o.shape[-3]
         H = W.shape[1]
         prec = resolve_precision(precision, B, N, K, C, H)
+        tc = prec == _lib.PREC_FP16_TC
         Xc, Goc, Wc = _f32c(X), _f32c(G_o), _f32c(W)
         Gdc = Goc if G_d is G_o else _f32c(G_d)
         bc = None if b is None else _f32c(b)
@@ -110,17 +145,31 @@ class _BDGCNFn(torch.autograd.Function):
         saved = _scratch(lib.mpgcn_bdgcn_saved_bytes(B, N, K, C, H, prec), X.device) if need_grad else None
         ws_bytes = lib.mpgcn_bdgcn_fwd_workspace_bytes(B, N, K, C, H, int(dynamic), prec)
         ws = _scratch(ws_bytes, X.device)
+        ex = _lib.BdgcnExtras()
+        preps = (None, None)
+        if tc:
+            # (The extras also allow handing an fp16 copy of the activation from layer to layer -- x_f16 / out_f16.  Measured on
+            # B200 that is neutral: the extra 256 MB written by the FWD_B epilogue cost what the separate cast pass costs.)
+            planes = (B if dynamic else 1) * K
+            with torch.cuda.device(X.device):
+                go_p = _prepared_supports(lib, G_o, Goc, planes, N)
+                gd_p = go_p if G_d is G_o else _prepared_supports(lib, G_d, Gdc, planes, N)
+            preps = (go_p, gd_p)
+            ex.go_prepared, ex.gd_prepared = _ptr(go_p), _ptr(gd_p)
         with torch.cuda.device(X.device):
-            _lib.check(lib.mpgcn_bdgcn_forward(_ptr(Xc), _ptr(Goc), _ptr(Gdc), int(dynamic), _ptr(Wc), _ptr(bc), act, _ptr(out),
-                                               _ptr(saved), _ptr(ws), ws.numel(), B, N, K, C, H, prec, _stream()), "bdgcn_forward")
+            _lib.check(lib.mpgcn_bdgcn_forward_x(_ptr(Xc), _ptr(Goc), _ptr(Gdc), int(dynamic), _ptr(Wc), _ptr(bc), act, _ptr(out),
+                                                 _ptr(saved), _ptr(ws), ws.numel(), B, N, K, C, H, prec, ctypes.addressof(ex), _stream()),
+                       "bdgcn_forward")
         ctx.shape = (B, N, K, C, H)
         ctx.meta = (bool(dynamic), act, prec, b is not None)
         ctx.x_producer = _producer_node(X) if need_grad else None
+        ctx.preps = preps
         ctx.save_for_backward(out, Goc, Gdc, Wc, saved if saved is not None else torch.empty(0, device=X.device))
         return out
 
     @staticmethod
     def backward(ctx, d_out):
+        import ctypes
         lib = _lib.load()
         out, Goc, Gdc, Wc, saved = ctx.saved_tensors
         B, N, K, C, H = ctx.shape
@@ -130,16 +179,20 @@ class _BDGCNFn(torch.autograd.Function):
         tc = prec == _lib.PREC_FP16_TC
         hint = _take_hint(ctx, d_out) if (tc and d_out.dtype == torch.float32 and d_out.is_contiguous()) else None
         d_out = _f32c(d_out)
+        dev = d_out.device
         need_dx = ctx.needs_input_grad[0]
-        dX = torch.empty((B, N, N, C), dtype=torch.float32, device=out.device) if need_dx else None
-        dx_absmax = torch.empty(1, dtype=torch.float32, device=out.device) if (need_dx and tc) else None
+        dX = torch.empty((B, N, N, C), dtype=torch.float32, device=dev) if need_dx else None
+        dx_absmax = torch.empty(1, dtype=torch.float32, device=dev) if (need_dx and tc) else None
         dW = torch.empty_like(Wc)
-        db = torch.empty(H, dtype=torch.float32, device=out.device) if has_bias else None
-        ws = _scratch(lib.mpgcn_bdgcn_bwd_workspace_bytes(B, N, K, C, H, int(dynamic), prec), out.device)
-        with torch.cuda.device(out.device):
-            _lib.check(lib.mpgcn_bdgcn_backward_ex(_ptr(d_out), _ptr(out), _ptr(Goc), _ptr(Gdc), int(dynamic), _ptr(Wc), act, _ptr(saved),
-                                                   _ptr(dX), _ptr(dW), _ptr(db), _ptr(ws), ws.numel(), B, N, K, C, H, prec, _ptr(hint),
-                                                   _ptr(dx_absmax), _stream()), "bdgcn_backward")
+        db = torch.empty(H, dtype=torch.float32, device=dev) if has_bias else None
+        ws = _scratch(lib.mpgcn_bdgcn_bwd_workspace_bytes(B, N, K, C, H, int(dynamic), prec), dev)
+        ex = _lib.BdgcnExtras()
+        ex.go_prepared, ex.gd_prepared = _ptr(ctx.preps[0]), _ptr(ctx.preps[1])
+        ex.d_out_absmax, ex.dX_absmax = _ptr(hint), _ptr(dx_absmax)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mpgcn_bdgcn_backward_x(_ptr(d_out), _ptr(out), _ptr(Goc), _ptr(Gdc), int(dynamic),
+                                                  _ptr(Wc), act, _ptr(saved), _ptr(dX), _ptr(dW), _ptr(db), _ptr(ws), ws.numel(), B, N, K,
+                                                  C, H, prec, ctypes.addressof(ex), _stream()), "bdgcn_backward")
         _put_hint(ctx.x_producer, dX, dx_absmax)
         return dX, None, None, dW, db, None, None, None
 

@@ -439,6 +439,80 @@ def test_inference_mode_needs_no_stash_and_trainer_call_pattern(cuda_device):
         assert torch.equal(model2(x_seq=x, G_list=[G, dyn]), model(x_seq=x, G_list=[G, dyn]))
 
 
+def test_layer_extras_prepared_supports_and_f16_copies(cuda_device):
+    """mpgcn_bdgcn_forward_x / _backward_x: supports prepared once, an fp16 copy of X handed in, an fp16 copy of `out` handed
+    out and used for the ReLU mask -- same results as the plain entry points (bit-identical forward)."""
+    import ctypes
+    lib = _lib.load()
+    torch.manual_seed(21)
+    B, N, K = 2, 70, 3
+    X = torch.tanh(torch.randn(B, N, N, 32, device=cuda_device))
+    Go = torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5
+    Gd = torch.randn(B, K, N, N, device=cuda_device) / N ** 0.5
+    Gd[:, 1] += 3 * torch.eye(N, device=cuda_device)          # a diagonally dominant support: the remainder correction is active
+    W = torch.randn(K * K * 32, 32, device=cuda_device) * 0.05
+    b = torch.randn(32, device=cuda_device) * 0.1
+    d_out = torch.randn(B, N, N, 32, device=cuda_device) * 1e-4
+    out_ref, saved_ref = abi.forward(X, Go, Gd, W, b, True, "fp16")
+    g_ref = abi.backward(d_out, out_ref, Go, Gd, W, True, saved_ref, "fp16")
+    st = torch.cuda.current_stream().cuda_stream
+    prec = _lib.PREC_FP16_TC
+    preps = []
+    for G in (Go, Gd):
+        nb = lib.mpgcn_bdgcn_supports_prepared_bytes(B * K, N)
+        blob = torch.empty(nb, dtype=torch.uint8, device=cuda_device)
+        _lib.check(lib.mpgcn_bdgcn_prepare_supports(G.data_ptr(), blob.data_ptr(), nb, B * K, N, st), "prepare")
+        preps.append(blob)
+    x16 = X.half()
+    out = torch.empty_like(out_ref)
+    out16 = torch.empty(out.shape, dtype=torch.float16, device=cuda_device)
+    saved = torch.empty(lib.mpgcn_bdgcn_saved_bytes(B, N, K, 32, 32, prec), dtype=torch.uint8, device=cuda_device)
+    ws = torch.empty(lib.mpgcn_bdgcn_fwd_workspace_bytes(B, N, K, 32, 32, 1, prec), dtype=torch.uint8, device=cuda_device)
+    ex = _lib.BdgcnExtras()
+    ex.go_prepared, ex.gd_prepared, ex.x_f16, ex.out_f16 = preps[0].data_ptr(), preps[1].data_ptr(), x16.data_ptr(), out16.data_ptr()
+    _lib.check(lib.mpgcn_bdgcn_forward_x(X.data_ptr(), Go.data_ptr(), Gd.data_ptr(), 1, W.data_ptr(), b.data_ptr(), 1, out.data_ptr(),
+                                         saved.data_ptr(), ws.data_ptr(), ws.numel(), B, N, K, 32, 32, prec, ctypes.addressof(ex), st), "fwd_x")
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_ref)
+    assert torch.equal(out16, out_ref.half())
+    dX, dW, db = torch.empty_like(X), torch.empty_like(W), torch.empty(32, device=cuda_device)
+    wsb = torch.empty(lib.mpgcn_bdgcn_bwd_workspace_bytes(B, N, K, 32, 32, 1, prec), dtype=torch.uint8, device=cuda_device)
+    amax = torch.zeros(1, device=cuda_device)
+    ex.x_f16, ex.dX_absmax = None, amax.data_ptr()
+    _lib.check(lib.mpgcn_bdgcn_backward_x(d_out.data_ptr(), None, Go.data_ptr(), Gd.data_ptr(), 1, W.data_ptr(), 1, saved.data_ptr(),
+                                          dX.data_ptr(), dW.data_ptr(), db.data_ptr(), wsb.data_ptr(), wsb.numel(), B, N, K, 32, 32, prec,
+                                          ctypes.addressof(ex), st), "bwd_x")
+    torch.cuda.synchronize()
+    for a, r, what in zip((dX, dW, db), g_ref, ("dX", "dW", "db")):
+        _check(a, r.cpu().numpy(), 1e-5, f"extras {what}", l2_only=True)
+    assert abs(float(amax) - float(dX.abs().max())) <= 1e-6 * float(dX.abs().max())
+    # a too-small prepared buffer and a missing ReLU-mask source are refused
+    assert lib.mpgcn_bdgcn_prepare_supports(Go.data_ptr(), preps[0].data_ptr(), 16, B * K, N, st) != 0
+    ex.out_f16 = None
+    assert lib.mpgcn_bdgcn_backward_x(d_out.data_ptr(), None, Go.data_ptr(), Gd.data_ptr(), 1, W.data_ptr(), 1, saved.data_ptr(),
+                                      dX.data_ptr(), dW.data_ptr(), db.data_ptr(), wsb.data_ptr(), wsb.numel(), B, N, K, 32, 32, prec,
+                                      ctypes.addressof(ex), st) != 0
+
+
+def test_support_cache_tracks_the_support_tensor(cuda_device):
+    """ops caches the fp16 staging of a support per tensor object: an in-place update (version bump) or a new tensor must be
+    re-staged."""
+    torch.manual_seed(8)
+    N, K, B = 48, 2, 2
+    l1 = shim.BDGCN(K=K, input_dim=32, hidden_dim=32, use_bias=True, activation=nn.ReLU).to(cuda_device)
+    l2 = shim.BDGCN(K=K, input_dim=32, hidden_dim=32, use_bias=True, activation=nn.ReLU).to(cuda_device)
+    X = torch.tanh(torch.randn(B, N, N, 32, device=cuda_device)).requires_grad_(True)
+    G = torch.randn(K, N, N, device=cuda_device) / N ** 0.5
+    y1 = l2(l1(X, G), G)
+    G.mul_(2.0)                                    # same object, same address, new contents
+    y2 = l2(l1(X, G), G)
+    y2_fresh = l2(l1(X, G.clone()), G.clone())     # never cached
+    assert not torch.allclose(y1, y2)
+    assert torch.equal(y2, y2_fresh)
+    y2.sum().backward()
+    assert torch.isfinite(X.grad).all() and float(X.grad.abs().max()) > 0
+
+
 def test_gradient_magnitude_hints_follow_the_autograd_graph(cuda_device, monkeypatch):
     """max|grad| hand-over (ops._put_hint / _take_hint): in the model every fp16 backward receives its scale from the kernel
     that wrote its incoming gradient (8 hand-overs: head -> layer 3 -> 2 -> 1 -> LSTM on two branches), results are
@@ -459,8 +533,9 @@ def test_gradient_magnitude_hints_follow_the_autograd_graph(cuda_device, monkeyp
         torch.cuda.synchronize()
         return _lib.profile_read()["ELEMENTWISE"]["launches"], [p.grad.clone() for p in model.parameters()]
 
+    run()                                     # stages the supports once (ops._prepared_supports), outside the counts below
     n_with, g_with = run()
-    monkeypatch.setattr(ops, "_producer_node", lambda t: None)
+    monkeypatch.setattr(ops, "_put_hint", lambda *a: None)
     n_without, g_without = run()
     monkeypatch.undo()
     assert n_without - n_with == 8, (n_with, n_without)          # one absmax pass saved per hand-over
