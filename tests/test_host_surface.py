@@ -125,3 +125,39 @@ def test_adj_processor_surface_and_errors():
     A = torch.tensor([[0., 2.], [0., 0.]])
     P = gshim.Adj_Processor.random_walk_normalize(A)
     assert torch.equal(P, torch.tensor([[0., 1.], [0., 0.]]))     # 1/0 -> 0 guard (reference GCN.py:105)
+
+
+def test_gradient_hint_routing_is_graph_based():
+    """ops._producer_node / _put_hint / _take_hint (host logic only): the hand-over walks pure view nodes back to one of our
+    autograd nodes, and a hint is honoured only for the very buffer it was written for, unmodified."""
+    import torch
+    from mpgcn_b200 import ops
+
+    class _LSTMLastFn(torch.autograd.Function):            # stands in for ops._LSTMLastFn: only the node's class name matters
+        @staticmethod
+        def forward(ctx, x):
+            return x * 2
+
+        @staticmethod
+        def backward(ctx, g):
+            return g * 2
+
+    x = torch.randn(4, 6, requires_grad=True)
+    h = _LSTMLastFn.apply(x)
+    node = h.grad_fn
+    assert ops._producer_node(h) is node
+    assert ops._producer_node(h.view(2, 2, 6).reshape(4, 6).view(2, 12)) is node       # views only: same memory
+    assert ops._producer_node(h * 1.0) is None                                           # a real op in between
+    assert ops._producer_node(x) is None and ops._producer_node(torch.zeros(3)) is None
+    g = torch.randn(4, 6)
+    scalar = torch.tensor([1.0])
+    ops._put_hint(node, g, scalar)
+    assert ops._take_hint(node, g) is scalar
+    assert ops._take_hint(node, g) is None                                               # consumed
+    ops._put_hint(node, g, scalar)
+    assert ops._take_hint(node, g.clone()) is None                                       # another buffer (e.g. accumulated gradient)
+    ops._put_hint(node, g, scalar)
+    g.add_(1.0)                                                                          # modified in place: version bump
+    assert ops._take_hint(node, g) is None
+    ops._put_hint(None, g, scalar)                                                       # no producer: nothing happens
+
