@@ -57,7 +57,8 @@ struct alignas(64) GemmParams {
   CUtensorMap a_map;
   CUtensorMap b_map;
   OperandMap am, bm;
-  int b_flat;                // 1: B tile = R separate (32 x BK) boxes of a flat [rows][cols] tensor
+  int b_flat;                // 1: B tile = R separate (32 x BK) boxes of a flat [rows][cols] tensor; 2 (pair kernel): 64-column
+                             // SWIZZLE_128B boxes (two chunks per box, 128-byte requests)
   int MT, NT, Z;             // tile grid: tile id = (z * NT + nt) * MT + mt
   int R;                     // 32-column chunks per tile
   int kb_total, kb_per_seg;  // k-blocks over all segments / per segment
@@ -488,6 +489,9 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
           const int r0 = nt * 8 + (int)rank * 4;      // this CTA's chunks of the 8-chunk tile
           if (!p.b_flat) {              // dims (ch, k, r, z), box (32, 64, 4)
             tma_load_4d_2cta(b_dst, &p.b_map, &full[stage], 0, kB, r0, zB);
+          } else if (p.b_flat == 2) {   // flat [k][cols] tensor, two SWIZZLE_128B atoms of [64 k][64 cols = 128 B] (2 chunks each)
+            for (int j = 0; j < 2; ++j)
+              tma_load_4d_2cta(b_dst + (size_t)j * BK * 128, &p.b_map, &full[stage], (r0 + 2 * j) * 32, kB, zB, 0);
           } else {
             for (int j = 0; j < 4; ++j)
               tma_load_4d_2cta(b_dst + (size_t)j * BK * 64, &p.b_map, &full[stage], (r0 + j) * 32, kB, zB, 0);
@@ -510,7 +514,10 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
       uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_f16(256, 256, C::A_MN ? 1 : 0, 1);
       const uint64_t a_hi = umma_desc_hi(C::A_SBO, C::A_LAYOUT);
-      const uint64_t b_hi = umma_desc_hi(C::B_SBO, 4u);
+      // B tile: four SWIZZLE_64B chunks of [64 k][32 cols], or (b_flat == 2) two SWIZZLE_128B atoms of [64 k][64 cols]
+      const bool b128 = p.b_flat == 2;
+      const uint64_t b_hi = b128 ? umma_desc_hi(1024, 2u) : umma_desc_hi(C::B_SBO, 4u);
+      const uint32_t b_kstep = b128 ? 16u * 128u : C::B_KSTEP, b_lbo = b128 ? (uint32_t)BK * 128u : C::B_LBO;
       for (int t = pair; t < num_tiles; t += num_pairs) {
         mbar_wait(&tempty[acc], acc_phase ^ 1u);
         tc_fence_after();
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t ad = umma_desc(a_hi, a_addr + k * C::A_KSTEP, C::A_LBO);
-              const uint64_t bd = umma_desc(b_hi, b_addr + k * C::B_KSTEP, C::B_LBO);
+              const uint64_t bd = umma_desc(b_hi, b_addr + k * b_kstep, b_lbo);
               umma_f16_2cta(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit_2cta(&empty[stage]);
