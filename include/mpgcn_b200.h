@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MPGCN_B200_ABI_VERSION 1
+#define MPGCN_B200_ABI_VERSION 2   /* 2: extras struct, prepared supports, LSTM training pair, dg_absmax, dyn graphs */
 
 #if defined(__GNUC__)
 #define MPGCN_API __attribute__((visibility("default")))

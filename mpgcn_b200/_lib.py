@@ -66,6 +66,7 @@ _SIGS = {
     "mpgcn_lstm_last_backward": (ctypes.c_int, [_c_f] * 12 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_void_p]),
 }
+ABI_VERSION = 2          # MPGCN_B200_ABI_VERSION of include/mpgcn_b200.h this binding was written against
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
 
@@ -99,7 +100,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.mpgcn_abi_version() != 1:
+    if lib.mpgcn_abi_version() != ABI_VERSION:
         raise RuntimeError("mpgcn_b200: ABI version mismatch between the Python binding and libmpgcn_b200.so")
     _lib = lib
     return lib

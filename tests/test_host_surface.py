@@ -27,7 +27,8 @@ def test_header_symbols_are_exported():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/mpgcn_b200.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS)
-    assert lib.mpgcn_abi_version() == 1
+    m = re.search(r"#define MPGCN_B200_ABI_VERSION\s+(\d+)", hdr)
+    assert m and lib.mpgcn_abi_version() == int(m.group(1)) == _lib.ABI_VERSION
 
 
 def test_workspace_queries_are_pure_host_functions():
