@@ -98,7 +98,7 @@ def _take_hint(node, grad):
 # so their fp16 conversion (+ diagonal remainders) is cached per support TENSOR OBJECT.  An entry is valid only while that
 # very object is alive (weak reference), unmodified (version counter), at the same address and used on the same stream.
 _SUPPORT_CACHE = {}
-_SUPPORT_CACHE_MAX = 16
+_SUPPORT_CACHE_MAX = 8
 
 
 def _prepared_supports(lib, G, Gc, planes: int, N: int):
@@ -111,11 +111,10 @@ def _prepared_supports(lib, G, Gc, planes: int, N: int):
         if ref() is G and ver == G._version and ptr == Gc.data_ptr() and st == stream and blob.device == Gc.device:
             return blob
         del _SUPPORT_CACHE[key]
-    if len(_SUPPORT_CACHE) >= _SUPPORT_CACHE_MAX:
-        for k in [k for k, v in _SUPPORT_CACHE.items() if v[0]() is None]:
-            del _SUPPORT_CACHE[k]
-        while len(_SUPPORT_CACHE) >= _SUPPORT_CACHE_MAX:
-            _SUPPORT_CACHE.pop(next(iter(_SUPPORT_CACHE)))
+    for k in [k for k, v in _SUPPORT_CACHE.items() if v[0]() is None]:      # supports that no longer exist: free their staging now
+        del _SUPPORT_CACHE[k]
+    while len(_SUPPORT_CACHE) >= _SUPPORT_CACHE_MAX:
+        _SUPPORT_CACHE.pop(next(iter(_SUPPORT_CACHE)))
     nbytes = lib.mpgcn_bdgcn_supports_prepared_bytes(planes, N)
     blob = torch.empty(nbytes, dtype=torch.uint8, device=Gc.device)
     with torch.cuda.device(Gc.device):
