@@ -109,6 +109,18 @@ __host__ __device__ inline size_t smem_bytes(int a_stage, int R, int BK, int sta
 }
 
 #ifdef __CUDACC__
+// one 32-byte (full L2 sector) store per lane: sm_100 has 256-bit global stores (STG.256); with 16-byte stores every lane of the
+// scattered epilogue patterns (rows 64 B .. 128 KB apart) sent two half-filled sector requests instead of one full one
+__device__ __forceinline__ void st_global_256(void* ptr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                              uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5),
+               "r"(a6), "r"(a7) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __device__ __forceinline__ void store_chunk(const Epilogue& ep, float alpha, const float* sbias, long long off, uint32_t (&acc)[32],
                                             float& amax) {
   float v[32];
@@ -123,40 +135,27 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, float alpha, con
 #pragma unroll
     for (int c = 0; c < 32; ++c) amax = fmaxf(amax, fabsf(v[c]));
   }
-  if (ep.out_f16) {
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out) + off);
+  if (ep.out_f16) {        // 64 bytes per row and chunk: two 32-byte stores
+    __half* dst = reinterpret_cast<__half*>(ep.out) + off;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      __half2 h0 = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
-      __half2 h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
-      __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
-      __half2 h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
-      uint4 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<uint32_t*>(&h1);
-      pk.z = *reinterpret_cast<uint32_t*>(&h2);
-      pk.w = *reinterpret_cast<uint32_t*>(&h3);
-      dst[q] = pk;
-    }
-  } else {
-    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off);
+    for (int q = 0; q < 2; ++q)
+      st_global_256(dst + 16 * q, pack_h2(v[16 * q + 0], v[16 * q + 1]), pack_h2(v[16 * q + 2], v[16 * q + 3]),
+                    pack_h2(v[16 * q + 4], v[16 * q + 5]), pack_h2(v[16 * q + 6], v[16 * q + 7]), pack_h2(v[16 * q + 8], v[16 * q + 9]),
+                    pack_h2(v[16 * q + 10], v[16 * q + 11]), pack_h2(v[16 * q + 12], v[16 * q + 13]), pack_h2(v[16 * q + 14], v[16 * q + 15]));
+  } else {                 // 128 bytes per row and chunk: four 32-byte stores
+    float* dst = reinterpret_cast<float*>(ep.out) + off;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 4; ++q)
+      st_global_256(dst + 8 * q, __float_as_uint(v[8 * q + 0]), __float_as_uint(v[8 * q + 1]), __float_as_uint(v[8 * q + 2]),
+                    __float_as_uint(v[8 * q + 3]), __float_as_uint(v[8 * q + 4]), __float_as_uint(v[8 * q + 5]),
+                    __float_as_uint(v[8 * q + 6]), __float_as_uint(v[8 * q + 7]));
     if (ep.out16) {
-      uint4* d16 = reinterpret_cast<uint4*>(ep.out16 + off);
+      __half* d16 = ep.out16 + off;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        __half2 h0 = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
-        __half2 h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
-        __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
-        __half2 h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
-        uint4 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        pk.z = *reinterpret_cast<uint32_t*>(&h2);
-        pk.w = *reinterpret_cast<uint32_t*>(&h3);
-        d16[q] = pk;
-      }
+      for (int q = 0; q < 2; ++q)
+        st_global_256(d16 + 16 * q, pack_h2(v[16 * q + 0], v[16 * q + 1]), pack_h2(v[16 * q + 2], v[16 * q + 3]),
+                      pack_h2(v[16 * q + 4], v[16 * q + 5]), pack_h2(v[16 * q + 6], v[16 * q + 7]), pack_h2(v[16 * q + 8], v[16 * q + 9]),
+                      pack_h2(v[16 * q + 10], v[16 * q + 11]), pack_h2(v[16 * q + 12], v[16 * q + 13]), pack_h2(v[16 * q + 14], v[16 * q + 15]));
     }
   }
 }
