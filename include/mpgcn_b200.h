@@ -16,6 +16,8 @@
  *     (thread-local).  Nothing ever aborts the process;
  *   - `precision`: 0 = exact fp32 CUDA-core kernels; 1 = fp16-operand / fp32-accumulate
  *     tcgen05 tensor-core engine (requires C == H == 32, K <= 8);
+ *   - tensors must be 16-byte aligned; the outputs of the precision-1 layer (`out`, `dX`, `out_f16`) 32-byte aligned
+ *     (256-bit stores).  Allocator-returned buffers always are;
  *   - `workspace` is caller-owned scratch of at least the size the matching *_workspace_bytes
  *     query returns (256-byte aligned); `saved` is the activation stash forward fills for
  *     backward (size from mpgcn_bdgcn_saved_bytes, 64-byte aligned); pass NULL for inference.

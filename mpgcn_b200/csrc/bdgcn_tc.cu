@@ -402,7 +402,9 @@ int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const
   __half* u16 = reinterpret_cast<__half*>(wb + L.u16);
   __half* z16 = saved ? static_cast<__half*>(saved) : reinterpret_cast<__half*>(wb + L.z16);
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(z16) & 63) == 0, "`saved` buffer must be 64-byte aligned");
-  MPGCN_CHECK(((reinterpret_cast<uintptr_t>(ex.x_f16) | reinterpret_cast<uintptr_t>(ex.out_f16)) & 15) == 0, "fp16 side buffers must be 16-byte aligned");
+  MPGCN_CHECK(((reinterpret_cast<uintptr_t>(ex.x_f16) | reinterpret_cast<uintptr_t>(ex.out_f16) | reinterpret_cast<uintptr_t>(out)) & 31) == 0,
+              "bdgcn_forward: `out` and the fp16 side buffers must be 32-byte aligned (256-bit stores)");
+  MPGCN_CHECK((reinterpret_cast<uintptr_t>(X) & 15) == 0, "bdgcn_forward: X must be 16-byte aligned");
 
   const __half* x16 = static_cast<const __half*>(ex.x_f16);
   if (x16 == nullptr) {
@@ -427,6 +429,8 @@ int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out,
   MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d K=%d)", s.C, s.H, s.K);
   MPGCN_CHECK(saved != nullptr, "bdgcn_backward: forward was run without a `saved` buffer");
   MPGCN_CHECK(out != nullptr || ex.out_f16 != nullptr || !s.act, "bdgcn_backward: the ReLU mask needs `out` or its fp16 copy");
+  MPGCN_CHECK((reinterpret_cast<uintptr_t>(dX) & 31) == 0, "bdgcn_backward: dX must be 32-byte aligned (256-bit stores)");
+  MPGCN_CHECK(((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "bdgcn_backward: d_out / out must be 16-byte aligned");
   const size_t NN = n2(s);
   const __half* z16 = static_cast<const __half*>(saved);
   const BwdLayout L = bwd_layout(s);

@@ -486,7 +486,11 @@ def test_layer_extras_prepared_supports_and_f16_copies(cuda_device):
     for a, r, what in zip((dX, dW, db), g_ref, ("dX", "dW", "db")):
         _check(a, r.cpu().numpy(), 1e-5, f"extras {what}", l2_only=True)
     assert abs(float(amax) - float(dX.abs().max())) <= 1e-6 * float(dX.abs().max())
-    # a too-small prepared buffer and a missing ReLU-mask source are refused
+    # a misaligned output (the epilogues use 256-bit stores), a too-small prepared buffer and a missing ReLU-mask source are refused
+    big = torch.empty(out.numel() + 8, device=cuda_device)
+    assert lib.mpgcn_bdgcn_forward(X.data_ptr(), Go.data_ptr(), Gd.data_ptr(), 1, W.data_ptr(), b.data_ptr(), 1, big.data_ptr() + 16,
+                                   saved.data_ptr(), ws.data_ptr(), ws.numel(), B, N, K, 32, 32, prec, st) != 0
+    assert b"32-byte aligned" in lib.mpgcn_last_error()
     assert lib.mpgcn_bdgcn_prepare_supports(Go.data_ptr(), preps[0].data_ptr(), 16, B * K, N, st) != 0
     ex.out_f16 = None
     assert lib.mpgcn_bdgcn_backward_x(d_out.data_ptr(), None, Go.data_ptr(), Gd.data_ptr(), 1, W.data_ptr(), 1, saved.data_ptr(),
