@@ -13,8 +13,12 @@ struct HeadPtrs {
   float* dg[kMaxBranches];           // backward: [cells][C] per branch
 };
 
+// MT = compile-time branch count (1..4; the branch loop is unrolled, so HeadPtrs stays in the constant bank: with a run-time
+// index the whole struct was copied to local memory and every p.g[m] became a local load) or 0 = run-time M
+template <int MT>
 __global__ void head_fwd_kernel(HeadPtrs p, const float* __restrict__ w /*[M][C]*/, const float* __restrict__ bias /*[M]*/,
-                                float* __restrict__ y, float* __restrict__ pre /*[M][cells] or null*/, long long cells, int C, int M) {
+                                float* __restrict__ y, float* __restrict__ pre /*[M][cells] or null*/, long long cells, int C, int Mrt) {
+  const int M = MT ? MT : Mrt;
   const int sub = threadIdx.x & 7;
   const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
   constexpr int U = 4;               // cells per thread and iteration: U x M independent 16-byte loads in flight
@@ -22,7 +26,9 @@ __global__ void head_fwd_kernel(HeadPtrs p, const float* __restrict__ w /*[M][C]
     float acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = 0.f;
-    for (int m = 0; m < M; ++m) {
+#pragma unroll
+    for (int m = 0; m < (MT ? MT : kMaxBranches); ++m) {
+      if (!MT && m >= M) break;
       float s[U];
       float4 v[U];
 #pragma unroll
@@ -64,9 +70,11 @@ __global__ void head_fwd_kernel(HeadPtrs p, const float* __restrict__ w /*[M][C]
 }
 
 // d g_m[cell,:] = dy[cell]/M * [pre_m > 0] * w_m ;  dw_m += sum_cell d_pre * g_m[cell,:] ;  db_m += sum_cell d_pre
+template <int MT>
 __global__ void head_bwd_kernel(HeadPtrs p, const float* __restrict__ w, const float* __restrict__ pre, const float* __restrict__ dy,
                                 float* __restrict__ dw /*[M][C]*/, float* __restrict__ db /*[M]*/, float* __restrict__ dg_absmax /*[M] or null*/,
-                                long long cells, int C, int M) {
+                                long long cells, int C, int Mrt) {
+  const int M = MT ? MT : Mrt;
   extern __shared__ float s_acc[];     // [M][C + 1] block-level accumulators
   for (int i = threadIdx.x; i < M * (C + 1); i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
@@ -74,7 +82,9 @@ __global__ void head_bwd_kernel(HeadPtrs p, const float* __restrict__ w, const f
   const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
   const float inv_m = 1.f / (float)M;
   // per-thread partial sums for the (few) weight elements this thread touches: C/8 per branch, kept in registers for C = 32
-  for (int m = 0; m < M; ++m) {
+#pragma unroll
+  for (int m = 0; m < (MT ? MT : kMaxBranches); ++m) {
+    if (!MT && m >= M) break;
     float wacc[4] = {0.f, 0.f, 0.f, 0.f}, bacc = 0.f;     // C <= 32 fast path; larger C falls through to smem atomics below
     float amax = 0.f;
     constexpr int U = 4;             // cells per thread and iteration
@@ -146,7 +156,13 @@ int head_forward(const float* const* g, const float* w, const float* bias, float
     p.g[m] = g[m];
   }
   prof_count(PROF_ELEMENTWISE);
-  head_fwd_kernel<<<head_grid(cells), 256, 0, st>>>(p, w, bias, y, pre, cells, C, M);
+  switch (M) {
+    case 1: head_fwd_kernel<1><<<head_grid(cells), 256, 0, st>>>(p, w, bias, y, pre, cells, C, M); break;
+    case 2: head_fwd_kernel<2><<<head_grid(cells), 256, 0, st>>>(p, w, bias, y, pre, cells, C, M); break;
+    case 3: head_fwd_kernel<3><<<head_grid(cells), 256, 0, st>>>(p, w, bias, y, pre, cells, C, M); break;
+    case 4: head_fwd_kernel<4><<<head_grid(cells), 256, 0, st>>>(p, w, bias, y, pre, cells, C, M); break;
+    default: head_fwd_kernel<0><<<head_grid(cells), 256, 0, st>>>(p, w, bias, y, pre, cells, C, M); break;
+  }
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -164,7 +180,14 @@ int head_backward(const float* const* g, const float* w, const float* pre, const
   MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * M, st));
   if (dg_absmax) MPGCN_CUDA(cudaMemsetAsync(dg_absmax, 0, sizeof(float) * M, st));
   prof_count(PROF_ELEMENTWISE);
-  head_bwd_kernel<<<head_grid(cells), 256, sizeof(float) * M * (C + 1), st>>>(p, w, pre, dy, dw, db, dg_absmax, cells, C, M);
+  const size_t sm = sizeof(float) * M * (C + 1);
+  switch (M) {
+    case 1: head_bwd_kernel<1><<<head_grid(cells), 256, sm, st>>>(p, w, pre, dy, dw, db, dg_absmax, cells, C, M); break;
+    case 2: head_bwd_kernel<2><<<head_grid(cells), 256, sm, st>>>(p, w, pre, dy, dw, db, dg_absmax, cells, C, M); break;
+    case 3: head_bwd_kernel<3><<<head_grid(cells), 256, sm, st>>>(p, w, pre, dy, dw, db, dg_absmax, cells, C, M); break;
+    case 4: head_bwd_kernel<4><<<head_grid(cells), 256, sm, st>>>(p, w, pre, dy, dw, db, dg_absmax, cells, C, M); break;
+    default: head_bwd_kernel<0><<<head_grid(cells), 256, sm, st>>>(p, w, pre, dy, dw, db, dg_absmax, cells, C, M); break;
+  }
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }
