@@ -22,9 +22,26 @@ _INVALID = "Invalid kernel_type. Must be one of [chebyshev, localpool, random_wa
 
 
 class Adj_Processor():
-    def __init__(self, kernel_type: str, K: int):
+    # Where CPU inputs are staged.  The trainer hands `process` CPU tensors (static adjacency, DataLoader batches) and moves the
+    # result `.to(params['GPU'])` afterwards (Model_Trainer.py:41-42,84), so the processor cannot see the target device:
+    # it uses, in this order, the `device` given here (class attribute = process-wide default, or per instance), the device of
+    # the first CUDA tensor this instance has seen, `torch.cuda.current_device()` -- call `torch.cuda.set_device(params['GPU'])`
+    #  or set `GCN.Adj_Processor.device` when the model does not live on cuda:0.
+    device = None
+
+    def __init__(self, kernel_type: str, K: int, device=None):
         self.kernel_type = kernel_type
         self.K = K if self.kernel_type != 'localpool' else 1
+        if device is not None:
+            self.device = torch.device(device)
+        self._seen_device = None
+
+    def _staging_device(self) -> torch.device:
+        if self.device is not None:
+            return torch.device(self.device)
+        if self._seen_device is not None:
+            return self._seen_device
+        return torch.device("cuda", torch.cuda.current_device())
 
     def num_supports(self) -> int:
         if self.kernel_type not in _KERNELS:
@@ -39,7 +56,9 @@ class Adj_Processor():
         if not flow.is_cuda:
             if not torch.cuda.is_available():
                 raise RuntimeError("mpgcn_b200.GCN.Adj_Processor needs a CUDA device; the engine has no CPU path")
-            flow = flow.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+            flow = flow.to(self._staging_device(), non_blocking=True)
+        elif self._seen_device is None:
+            self._seen_device = flow.device
         lib = _lib.load()
         kt = _KERNELS[self.kernel_type]
         B, N = flow.shape[0], flow.shape[1]

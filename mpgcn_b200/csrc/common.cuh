@@ -235,6 +235,15 @@ int make_tmap_f16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* 
 
 int device_sm_count();
 
+// Function attributes (the > 48 KB dynamic shared-memory opt-in) belong to a device / context, not to the process: a
+// kernel that already ran on cuda:0 still needs the opt-in on cuda:1.  One cache per kernel, indexed by device ordinal.
+struct DynSmemAttr { int bytes[64]; };
+int ensure_dyn_smem_impl(const void* kernel, int bytes, DynSmemAttr& cache);
+template <class Kernel>
+inline int ensure_dyn_smem(Kernel kernel, int bytes, DynSmemAttr& cache) {
+  return ensure_dyn_smem_impl(reinterpret_cast<const void*>(kernel), bytes, cache);
+}
+
 // ----------------------------------------------------------------------------------------
 // host: launch accounting / per-launch CUDA-event timing (bench.py's roofline evidence)
 // ----------------------------------------------------------------------------------------
@@ -242,7 +251,10 @@ enum ProfTag {
   PROF_FWD_A = 0, PROF_FWD_MIX, PROF_FWD_B, PROF_BWD_V, PROF_BWD_DW, PROF_BWD_MIX, PROF_BWD_DX,   // tcgen05 contractions
   PROF_SIMT_GEMM, PROF_ELEMENTWISE, PROF_LSTM_FWD, PROF_LSTM_BWD, PROF_NUM_TAGS
 };
-void prof_set_next(int tag, double flops);             // annotate the next contraction launch
+// All of these may be called from several host threads (one stream each): the counters sit behind a mutex, the
+// "next launch" annotation and the open begin/end bracket are thread-local.
+void prof_set_next(int tag, double flops);             // annotate the next contraction launch (this thread's)
+void prof_take_next(int* tag, double* flops);          // fetch and clear this thread's annotation
 void prof_count(int tag);                              // count one launch of our own kernels
 void prof_begin(int tag, double flops, cudaStream_t s);   // event before launch (no-op unless enabled)
 void prof_end(cudaStream_t s);                            // event after launch

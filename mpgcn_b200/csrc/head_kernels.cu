@@ -22,6 +22,9 @@ __global__ void head_fwd_kernel(HeadPtrs p, const float* __restrict__ w /*[M][C]
   const int sub = threadIdx.x & 7;
   const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
   constexpr int U = 4;               // cells per thread and iteration: U x M independent 16-byte loads in flight
+  // The eight lanes of a cell shuffle among themselves only: the four 8-lane groups of a warp own different cells, so near
+  // the end of the range (cells % 4 != 0, e.g. N = 47 with an odd batch) some groups have left the loop while others reduce.
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
   for (long long cell0 = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); cell0 < cells; cell0 += U * stride) {
     float acc[U];
 #pragma unroll
@@ -52,9 +55,9 @@ __global__ void head_fwd_kernel(HeadPtrs p, const float* __restrict__ w /*[M][C]
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        s[u] += __shfl_xor_sync(0xffffffffu, s[u], 1);
-        s[u] += __shfl_xor_sync(0xffffffffu, s[u], 2);
-        s[u] += __shfl_xor_sync(0xffffffffu, s[u], 4);
+        s[u] += __shfl_xor_sync(gmask, s[u], 1);
+        s[u] += __shfl_xor_sync(gmask, s[u], 2);
+        s[u] += __shfl_xor_sync(gmask, s[u], 4);
         s[u] += bias[m];
         const long long cell = cell0 + u * stride;
         if (pre != nullptr && sub == 0 && cell < cells) pre[(long long)m * cells + cell] = s[u];

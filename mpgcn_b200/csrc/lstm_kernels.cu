@@ -99,11 +99,8 @@ int lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, 
   if (CELLS > 32) CELLS = 32;
   const int threads = CELLS * C;
   const size_t smem = ((size_t)4 * C * C + 8 * C + 2 * (size_t)CELLS * C) * sizeof(float);
-  static size_t attr_smem = 0;
-  if (smem > 48 * 1024 && smem > attr_smem) {
-    MPGCN_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  static DynSmemAttr attr = {};
+  if (smem > 48 * 1024) { if (int e = ensure_dyn_smem(lstm_fwd_kernel, (int)smem, attr)) return e; }
   const long long tiles = (cells + CELLS - 1) / CELLS;
   long long grid = (long long)device_sm_count() * 8;
   if (grid > tiles) grid = tiles;
@@ -273,11 +270,8 @@ int lstm_last_backward(const float* x_seq, const float* w_ih, const float* w_hh,
   if (CELLS > 16) CELLS = 16;
   const int threads = CELLS * C;
   const size_t smem = fixed + (size_t)CELLS * per_cell;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    MPGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 4096)));
-    attr_smem = budget + 4096;
-  }
+  static DynSmemAttr attr = {};
+  if (int e = ensure_dyn_smem(lstm_bwd_kernel, (int)(budget + 4096), attr)) return e;
   MPGCN_CUDA(cudaMemsetAsync(d_w_ih, 0, sizeof(float) * G, st));
   MPGCN_CUDA(cudaMemsetAsync(d_w_hh, 0, sizeof(float) * G * C, st));
   MPGCN_CUDA(cudaMemsetAsync(d_b_ih, 0, sizeof(float) * G, st));

@@ -616,9 +616,10 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
     const char* e = getenv("MPGCN_B200_LSTM_FWD_SMEM_KB");     // tuning knob: dynamic smem request (L1 carve-out)
     fwd_smem = e ? atoi(e) * 1024 : kLstmFwdSmem;
     if (fwd_smem < kLstmFwdSmem) fwd_smem = kLstmFwdSmem;
-    MPGCN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem));
-    MPGCN_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem));
   }
+  static DynSmemAttr attr_f = {}, attr_t = {};
+  if (int e = ensure_dyn_smem(lstm_fwd_tc_kernel<false>, fwd_smem, attr_f)) return e;
+  if (int e = ensure_dyn_smem(lstm_fwd_tc_kernel<true>, fwd_smem, attr_t)) return e;
   prof_begin(PROF_LSTM_FWD, 8.0 * C * (C + 1) * (double)cells * T, st);
   if (saved)
     lstm_fwd_tc_kernel<true><<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, static_cast<__half*>(saved),
@@ -650,11 +651,8 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   MPGCN_CUDA(cudaMemsetAsync(d_w_hh, 0, sizeof(float) * G4 * C, st));
   MPGCN_CUDA(cudaMemsetAsync(d_b_ih, 0, sizeof(float) * G4, st));
   if (d_x) MPGCN_CUDA(cudaMemsetAsync(d_x, 0, sizeof(float) * (size_t)cells * T, st));
-  static bool attr = false;
-  if (!attr) {
-    MPGCN_CUDA(cudaFuncSetAttribute(lstm_bwd_saved_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLstmSavedSmem));
-    attr = true;
-  }
+  static DynSmemAttr attr = {};
+  if (int e = ensure_dyn_smem(lstm_bwd_saved_tc_kernel<2>, kLstmSavedSmem, attr)) return e;
   static_assert(1024 + DA_BYTES + 3 * HX_BYTES + WX_BYTES + 8192 + 2 * G4 * sizeof(float) + 256 <= (size_t)kLstmSavedSmem, "smem");
   prof_begin(PROF_LSTM_BWD, 12.0 * C * (C + 1) * (double)cells * T, st);
   lstm_bwd_saved_tc_kernel<2><<<lstm_grid(cells), 256, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,

@@ -21,6 +21,19 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+int ensure_dyn_smem_impl(const void* kernel, int bytes, DynSmemAttr& cache) {
+  static std::mutex mu;
+  int dev = 0;
+  MPGCN_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  const bool known = dev >= 0 && dev < 64;
+  if (!known || cache.bytes[dev] < bytes) {
+    MPGCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (known) cache.bytes[dev] = bytes;
+  }
+  return 0;
+}
+
 int device_sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -45,12 +58,13 @@ struct ProfState {
   struct Pending { cudaEvent_t a, b; int tag; };
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> pool;
-  int cur_tag = -1;
-  cudaEvent_t cur_a = nullptr;
-  int next_tag = -1;
-  double next_flops = 0;
+  std::mutex mu;
 } g_prof;
-cudaEvent_t prof_event() {
+thread_local int t_cur_tag = -1;
+thread_local cudaEvent_t t_cur_a = nullptr;
+thread_local int t_next_tag = -1;
+thread_local double t_next_flops = 0;
+cudaEvent_t prof_event() {          // caller holds g_prof.mu
   if (!g_prof.pool.empty()) { cudaEvent_t e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
   cudaEvent_t e = nullptr;
   cudaEventCreate(&e);
@@ -58,31 +72,46 @@ cudaEvent_t prof_event() {
 }
 }  // namespace
 
-void prof_set_next(int tag, double flops) { g_prof.next_tag = tag; g_prof.next_flops = flops; }
-void prof_count(int tag) { if (tag >= 0 && tag < PROF_NUM_TAGS) g_prof.launches[tag]++; }
+void prof_set_next(int tag, double flops) { t_next_tag = tag; t_next_flops = flops; }
+void prof_take_next(int* tag, double* flops) {
+  *tag = t_next_tag;
+  *flops = t_next_flops;
+  t_next_tag = -1;
+  t_next_flops = 0;
+}
+void prof_count(int tag) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  if (tag >= 0 && tag < PROF_NUM_TAGS) g_prof.launches[tag]++;
+}
 void prof_begin(int tag, double flops, cudaStream_t s) {
-  prof_count(tag);
-  if (tag >= 0 && tag < PROF_NUM_TAGS) g_prof.flops[tag] += flops;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  if (tag >= 0 && tag < PROF_NUM_TAGS) { g_prof.launches[tag]++; g_prof.flops[tag] += flops; }
   if (!g_prof.enabled) return;
-  g_prof.cur_tag = tag;
-  g_prof.cur_a = prof_event();
-  cudaEventRecord(g_prof.cur_a, s);
+  t_cur_tag = tag;
+  t_cur_a = prof_event();
+  cudaEventRecord(t_cur_a, s);
 }
 void prof_end(cudaStream_t s) {
-  if (!g_prof.enabled || g_prof.cur_a == nullptr) return;
+  if (t_cur_a == nullptr) return;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   cudaEvent_t b = prof_event();
   cudaEventRecord(b, s);
-  g_prof.pending.push_back({g_prof.cur_a, b, g_prof.cur_tag});
-  g_prof.cur_a = nullptr;
+  g_prof.pending.push_back({t_cur_a, b, t_cur_tag});
+  t_cur_a = nullptr;
 }
-void prof_enable(int on) { g_prof.enabled = on != 0; }
+void prof_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  g_prof.enabled = on != 0;
+}
 void prof_reset() {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   for (int i = 0; i < PROF_NUM_TAGS; ++i) { g_prof.launches[i] = 0; g_prof.flops[i] = 0; g_prof.ms[i] = 0; }
   for (auto& p : g_prof.pending) { g_prof.pool.push_back(p.a); g_prof.pool.push_back(p.b); }
   g_prof.pending.clear();
 }
 // resolves pending event pairs (caller must have synchronised the stream)
 int prof_read(int tag, long long* launches, double* flops, double* ms) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   for (auto& p : g_prof.pending) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess && p.tag >= 0 && p.tag < PROF_NUM_TAGS) g_prof.ms[p.tag] += t;
@@ -159,11 +188,8 @@ static const int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 template <int AK, int BK>
 static int launch_impl(GemmParams& p, cudaStream_t stream) {
   using C = Cfg<AK, BK>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MPGCN_CUDA(cudaFuncSetAttribute(contract_kernel<AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_done = true;
-  }
+  static DynSmemAttr attr = {};
+  if (int e = ensure_dyn_smem(contract_kernel<AK, BK>, kMaxSmem, attr)) return e;
   MPGCN_CHECK(p.R >= 1 && p.R <= 8, "R=%d out of range", p.R);
   // N of the UMMA must be a multiple of 16 for M=128: R odd -> N=32R is still a multiple of 32. ok.
   const size_t b_stage = (size_t)p.R * BK * 64;
@@ -188,10 +214,9 @@ static int launch_impl(GemmParams& p, cudaStream_t stream) {
   MPGCN_CHECK(tiles > 0 && tiles < (1ll << 31), "bad tile count %lld", tiles);
   MPGCN_CHECK(p.kb_total > 0 && p.kb_per_seg > 0, "empty contraction");
   int grid = (int)(tiles < device_sm_count() ? tiles : device_sm_count());
-  const int tag = g_prof.next_tag;
-  const double fl = g_prof.next_flops;
-  g_prof.next_tag = -1;
-  g_prof.next_flops = 0;
+  int tag = -1;
+  double fl = 0;
+  prof_take_next(&tag, &fl);
   prof_begin(tag, fl, stream);
   contract_kernel<AK, BK><<<grid, kThreads1, smem, stream>>>(p);
   prof_end(stream);
@@ -201,11 +226,8 @@ static int launch_impl(GemmParams& p, cudaStream_t stream) {
 
 template <int AK>
 static int launch2_impl(GemmParams& p, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    MPGCN_CUDA(cudaFuncSetAttribute(contract2_kernel<AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    attr_done = true;
-  }
+  static DynSmemAttr attr = {};
+  if (int e = ensure_dyn_smem(contract2_kernel<AK>, kMaxSmem, attr)) return e;
   MPGCN_CHECK(p.R == 8 && !p.split_k, "2-CTA kernel needs R = 8 and no split-K");
   const size_t stage_bytes = 32768;
   int stages = (int)((kMaxSmem - 1024 - 512) / stage_bytes);
@@ -237,10 +259,9 @@ static int launch2_impl(GemmParams& p, cudaStream_t stream) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  const int tag = g_prof.next_tag;
-  const double fl = g_prof.next_flops;
-  g_prof.next_tag = -1;
-  g_prof.next_flops = 0;
+  int tag = -1;
+  double fl = 0;
+  prof_take_next(&tag, &fl);
   prof_begin(tag, fl, stream);
   cudaError_t e = cudaLaunchKernelEx(&cfg, contract2_kernel<AK>, p);
   prof_end(stream);

@@ -8,6 +8,7 @@ libmpgcn_b200.so.
 """
 from __future__ import annotations
 
+import collections
 import os
 
 import torch
@@ -15,6 +16,10 @@ import torch
 from . import _lib
 
 _PREC_NAMES = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16_TC, "auto": -1}
+
+# bytes of training state (Z stash, LSTM c_t/h_t, head pre-activations) allocated by forward calls since the last .clear():
+# stays at zero under torch.no_grad() (tests/test_gpu_at_size.py::test_no_grad_allocates_no_training_state)
+STASH_BYTES = collections.Counter()
 
 
 def default_precision() -> str:
@@ -128,7 +133,7 @@ def _prepared_supports(lib, G, Gc, planes: int, N: int):
 
 class _BDGCNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, X, G_o, G_d, W, b, dynamic: bool, act: int, precision):
+    def forward(ctx, X, G_o, G_d, W, b, dynamic: bool, act: int, precision, grad_mode: bool):
         import ctypes
         lib = _lib.load()
         B, N, N2, C = X.shape
@@ -140,8 +145,12 @@ class _BDGCNFn(torch.autograd.Function):
         Gdc = Goc if G_d is G_o else _f32c(G_d)
         bc = None if b is None else _f32c(b)
         out = torch.empty((B, N, N, H), dtype=torch.float32, device=X.device)
-        need_grad = any(ctx.needs_input_grad)
+        # ctx.needs_input_grad ignores the grad mode (it is True under torch.no_grad() too), and inside Function.forward
+        # torch.is_grad_enabled() is always False: the wrapper reads the mode and hands it in.  Validation / test / the
+        # autoregressive rollout therefore allocate no Z stash.
+        need_grad = grad_mode and any(ctx.needs_input_grad)
         saved = _scratch(lib.mpgcn_bdgcn_saved_bytes(B, N, K, C, H, prec), X.device) if need_grad else None
+        STASH_BYTES["bdgcn"] += saved.numel() if saved is not None else 0
         ws_bytes = lib.mpgcn_bdgcn_fwd_workspace_bytes(B, N, K, C, H, int(dynamic), prec)
         ws = _scratch(ws_bytes, X.device)
         ex = _lib.BdgcnExtras()
@@ -193,7 +202,7 @@ class _BDGCNFn(torch.autograd.Function):
                                                   _ptr(Wc), act, _ptr(saved), _ptr(dX), _ptr(dW), _ptr(db), _ptr(ws), ws.numel(), B, N, K,
                                                   C, H, prec, ctypes.addressof(ex), _stream()), "bdgcn_backward")
         _put_hint(ctx.x_producer, dX, dx_absmax)
-        return dX, None, None, dW, db, None, None, None
+        return dX, None, None, dW, db, None, None, None, None
 
 
 def bdgcn(X: torch.Tensor, G, W: torch.Tensor, b, relu: bool, precision=None) -> torch.Tensor:
@@ -209,7 +218,13 @@ def bdgcn(X: torch.Tensor, G, W: torch.Tensor, b, relu: bool, precision=None) ->
         _require_cuda(g, "G")
         if g.device != X.device:
             raise RuntimeError("mpgcn_b200: X and G must be on the same device")
-    return _BDGCNFn.apply(X, G_o, G_d, W, b, dynamic, 1 if relu else 0, precision)
+    grad_mode = torch.is_grad_enabled()
+    if grad_mode and (G_o.requires_grad or G_d.requires_grad):
+        # the reference's einsums would deliver dL/dG through autograd; the trainer never asks for it (static G is a plain
+        # tensor, dynamic G comes from the data loader) and the engine has no dG kernels: refuse instead of returning None
+        raise NotImplementedError("mpgcn_b200.bdgcn: gradients with respect to the supports G are not implemented "
+                                  "(pass G.detach(), or learnable supports through the reference's einsum path)")
+    return _BDGCNFn.apply(X, G_o, G_d, W, b, dynamic, 1 if relu else 0, precision, grad_mode)
 
 
 def resolve_lstm_precision(name, T, C) -> int:
@@ -227,7 +242,7 @@ def resolve_lstm_precision(name, T, C) -> int:
 
 class _LSTMLastFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_seq, w_ih, w_hh, b_ih, b_hh, precision):
+    def forward(ctx, x_seq, w_ih, w_hh, b_ih, b_hh, precision, grad_mode: bool):
         lib = _lib.load()
         B, T = x_seq.shape[0], x_seq.shape[1]
         NN = x_seq[0, 0].numel()
@@ -237,8 +252,10 @@ class _LSTMLastFn(torch.autograd.Function):
         ws = [_f32c(t) for t in (w_ih, w_hh, b_ih, b_hh)]
         hT = torch.empty((B * NN, C), dtype=torch.float32, device=x_seq.device)
         # training: the forward keeps c_t / h_t of every step (fp16) so that the backward is one reverse walk
-        nsave = lib.mpgcn_lstm_saved_bytes(B, T, NN, C, prec) if any(ctx.needs_input_grad[:5]) else 0
+        nsave = lib.mpgcn_lstm_saved_bytes(B, T, NN, C, prec) if (grad_mode and any(ctx.needs_input_grad[:5])) else 0
         saved = torch.empty(nsave, dtype=torch.uint8, device=x_seq.device) if nsave else None
+        # (precision 0 keeps no state -- its backward recomputes -- so count the request, not the buffer)
+        STASH_BYTES["lstm"] += nsave if nsave else (1 if (grad_mode and any(ctx.needs_input_grad[:5])) else 0)
         with torch.cuda.device(x_seq.device):
             _lib.check(lib.mpgcn_lstm_last_forward_train(_ptr(xc), *[_ptr(t) for t in ws], _ptr(hT), _ptr(saved), nsave, B, T, NN, C, prec,
                                                          _stream()), "lstm_last_forward")
@@ -266,18 +283,18 @@ class _LSTMLastFn(torch.autograd.Function):
                                                           saved.numel() if saved is not None else 0, _ptr(ws), ws.numel(), B, T, NN, C,
                                                           prec, _ptr(hint), _stream()), "lstm_last_backward")
         ctx.lstm_saved = None
-        return d_x, g_wih, g_whh, g_bih, g_bhh, None
+        return d_x, g_wih, g_whh, g_bih, g_bhh, None, None
 
 
 def lstm_last(x_seq: torch.Tensor, w_ih, w_hh, b_ih, b_hh, precision=None) -> torch.Tensor:
     """h_T of a 1-layer, input-size-1 LSTM run over every OD cell of x_seq [B,T,N,N,1] -> [B*N*N, C]."""
     _require_cuda(x_seq, "x_seq")
-    return _LSTMLastFn.apply(x_seq, w_ih, w_hh, b_ih, b_hh, precision)
+    return _LSTMLastFn.apply(x_seq, w_ih, w_hh, b_ih, b_hh, precision, torch.is_grad_enabled())
 
 
 class _HeadFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, w, b, *gs):
+    def forward(ctx, grad_mode, w, b, *gs):
         import ctypes
         lib = _lib.load()
         M = len(gs)
@@ -286,8 +303,9 @@ class _HeadFn(torch.autograd.Function):
         gc = [_f32c(g) for g in gs]
         wc, bc = _f32c(w), _f32c(b)
         y = torch.empty(gs[0].shape[:-1] + (1,), dtype=torch.float32, device=gs[0].device)
-        need = any(ctx.needs_input_grad)
+        need = grad_mode and any(ctx.needs_input_grad)
         pre = torch.empty((M, cells), dtype=torch.float32, device=y.device) if need else None
+        STASH_BYTES["head"] += pre.numel() * 4 if pre is not None else 0
         ptrs = (ctypes.c_void_p * M)(*[g.data_ptr() for g in gc])
         with torch.cuda.device(y.device):
             _lib.check(lib.mpgcn_head_forward(ptrs, _ptr(wc), _ptr(bc), _ptr(y), _ptr(pre), cells, C, M, _stream()), "head_forward")
@@ -303,7 +321,9 @@ class _HeadFn(torch.autograd.Function):
         wc, pre, *gc = ctx.saved_tensors
         M, C, cells = ctx.dims
         dy = _f32c(dy)
-        dgs = [torch.empty_like(g) if ctx.needs_input_grad[2 + m] else None for m, g in enumerate(gc)]
+        if pre.numel() == 0:
+            raise RuntimeError("mpgcn_b200.fc_relu_mean: backward called but forward ran without requires_grad inputs")
+        dgs = [torch.empty_like(g) if ctx.needs_input_grad[3 + m] else None for m, g in enumerate(gc)]
         dw = torch.empty_like(wc)
         db = torch.empty(M, dtype=torch.float32, device=dy.device)
         ptrs = (ctypes.c_void_p * M)(*[g.data_ptr() for g in gc])
@@ -314,11 +334,11 @@ class _HeadFn(torch.autograd.Function):
                                                _stream()), "head_backward")
         for m, d in enumerate(dgs):
             _put_hint(ctx.g_producers[m], d, amax[m:m + 1])
-        return (dw, db) + tuple(dgs)
+        return (None, dw, db) + tuple(dgs)
 
 
 def fc_relu_mean(gs, w, b) -> torch.Tensor:
     """(1/M) * sum_m relu(g_m @ w[m] + b[m]) for M branch activations g_m [..., C]; w [M, C], b [M] -> [..., 1]."""
     for g in gs:
         _require_cuda(g, "branch activation")
-    return _HeadFn.apply(w, b, *gs)
+    return _HeadFn.apply(torch.is_grad_enabled(), w, b, *gs)

@@ -110,6 +110,67 @@ def gen_bdgcn(ref_mpgcn, ref_gcn):
         print("wrote", name, "out", out.shape)
 
 
+# At-size layer cases (C = H = 32, B = 1; tile boundaries of the tcgen05 engine: N = 129 -> second 128-row tile / first 2-CTA
+# pair tile, N = 200 = BASELINE.json configs[1]).  To keep the fixtures small the activations are NOT stored: X and d_out are
+# regenerated from the seed by `big_case_inputs` (numpy PCG64 streams are stable across versions; a checksum is stored and
+# asserted by the tests), and of the reference's outputs only `BIG_ROWS` origin rows of out / dX are kept (every element of
+# out depends on all of X, so a row subset pins the whole contraction), plus dW and db in full.
+BIG_CASES = [
+    # name, dynamic, K, N, support kind
+    ("bdgcn_s_k3_n129_c32", False, 3, 129, "rw"),
+    ("bdgcn_d_k3_n129_c32", True, 3, 129, "dense"),
+    ("bdgcn_s_k3_n200_c32", False, 3, 200, "dense"),
+]
+
+
+def big_rows(N):
+    """Origin rows kept in an at-size fixture: tile edges (63/64, 127/128, last) and a spread in between."""
+    rows = {0, 1, 31, 32, 63, 64, 65, 100, 126, 127, 128, N - 2, N - 1} | set(range(7, N, 17))
+    return np.asarray(sorted(r for r in rows if 0 <= r < N)[:28], dtype=np.int64)
+
+
+def big_case_inputs(seed, N, C=32, H=32):
+    """(X [1,N,N,C], d_out [1,N,N,H]) of an at-size fixture, from the seed alone."""
+    rng = np.random.default_rng(seed)
+    X = np.tanh(rng.standard_normal((1, N, N, C))).astype(np.float32)
+    d_out = rng.standard_normal((1, N, N, H)).astype(np.float32)
+    return X, d_out
+
+
+def gen_bdgcn_big(ref_mpgcn, ref_gcn):
+    for idx, (name, dyn, K, N, gk) in enumerate(BIG_CASES):
+        seed = 6000 + idx
+        C = H = 32
+        rng = np.random.default_rng(seed + 500)
+        torch.manual_seed(seed)
+        layer = ref_mpgcn.BDGCN(K=K, input_dim=C, hidden_dim=H, use_bias=True, activation=torch.nn.ReLU)
+        with torch.no_grad():
+            layer.b.copy_(torch.from_numpy(rng.standard_normal(H).astype(np.float32) * 0.1))
+        X, d_out = big_case_inputs(seed, N, C, H)
+        Xt = torch.from_numpy(X).requires_grad_(True)
+        if dyn:
+            go, gd = make_supports(ref_gcn, gk, K, N, 1, rng), make_supports(ref_gcn, gk, K, N, 1, rng)
+            G = (torch.from_numpy(go), torch.from_numpy(gd))
+        else:
+            g = make_supports(ref_gcn, gk, K, N, 0, rng)
+            G = torch.from_numpy(g)
+        out = layer(Xt, G)
+        out.backward(torch.from_numpy(d_out))
+        rows = big_rows(N)
+        rec = dict(seed=seed, N=N, K=K, dynamic=int(dyn), act="relu", rows=rows, W=_np(layer.W), b=_np(layer.b),
+                   x_checksum=np.float64(X.astype(np.float64).sum()), d_out_checksum=np.float64(d_out.astype(np.float64).sum()),
+                   x_probe=X[0, rows[:4], 5, :4].copy(),
+                   out_rows=_np(out)[:, rows], dX_rows=_np(Xt.grad)[:, rows], dW=_np(layer.W.grad), db=_np(layer.b.grad),
+                   out_absmax=np.float32(np.abs(_np(out)).max()), dX_absmax=np.float32(np.abs(_np(Xt.grad)).max()),
+                   out_norm=np.float64(np.linalg.norm(_np(out).astype(np.float64))), dX_norm=np.float64(np.linalg.norm(_np(Xt.grad).astype(np.float64))))
+        if dyn:
+            rec.update(G_o=go, G_d=gd)
+        else:
+            rec.update(G=g)
+        np.savez_compressed(os.path.join(OUT, name.replace("bdgcn_", "big_bdgcn_") + ".npz"), **rec)
+        print("wrote", name, "rows", len(rows))
+
+
 LSTM_CASES = [("lstm_s50_t5_c8", 50, 5, 8), ("lstm_s96_t4_c32", 96, 4, 32), ("lstm_s33_t12_c32", 33, 12, 32)]
 
 
@@ -141,27 +202,43 @@ MODEL_CASES = [
 ]
 
 
+def _gen_one_model(ref_mpgcn, ref_gcn, seed, N, K, gk, T, B, hid):
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    model = ref_mpgcn.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=hid, lstm_num_layers=1,
+                            gcn_hidden_dim=hid, gcn_num_layers=3, num_nodes=N, user_bias=True,
+                            activation=torch.nn.ReLU)        # Model_Trainer.py:47-56
+    x_seq = (rng.random((B, T, N, N, 1)) * 8).astype(np.float32)
+    g_static = make_supports(ref_gcn, gk, K, N, 0, rng)
+    g_o = make_supports(ref_gcn, gk, K, N, B, rng)
+    g_d = make_supports(ref_gcn, gk, K, N, B, rng)
+    d_y = rng.standard_normal((B, 1, N, N, 1)).astype(np.float32)
+    y = model(x_seq=torch.from_numpy(x_seq), G_list=[torch.from_numpy(g_static), (torch.from_numpy(g_o), torch.from_numpy(g_d))])
+    y.backward(torch.from_numpy(d_y))
+    if not all(float(p.grad.abs().max()) > 0 for p in model.parameters()):
+        return None
+    rec = dict(x_seq=x_seq, G_static=g_static, G_o=g_o, G_d=g_d, d_y=d_y, y=_np(y), K=K, hidden=hid, seed=seed)
+    for k, v in model.state_dict().items():
+        rec["param:" + k] = _np(v)
+    for k, p in model.named_parameters():
+        rec["grad:" + k] = _np(p.grad)
+    return rec
+
+
 def gen_model(ref_mpgcn, ref_gcn):
+    """Default init can leave a branch's FC ReLU dead on every cell (all of that branch's gradients exactly zero: round 1's
+    cfg1 fixture pinned only the static half of the model), so each case takes the first seed of 3000+idx, 3100+idx, ...
+    for which every parameter of BOTH branches receives a non-zero gradient."""
     for idx, (name, N, K, gk, T, B, hid) in enumerate(MODEL_CASES):
-        rng = np.random.default_rng(3000 + idx)
-        torch.manual_seed(3000 + idx)
-        model = ref_mpgcn.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=hid, lstm_num_layers=1,
-                                gcn_hidden_dim=hid, gcn_num_layers=3, num_nodes=N, user_bias=True,
-                                activation=torch.nn.ReLU)        # Model_Trainer.py:47-56
-        x_seq = (rng.random((B, T, N, N, 1)) * 8).astype(np.float32)
-        g_static = make_supports(ref_gcn, gk, K, N, 0, rng)
-        g_o = make_supports(ref_gcn, gk, K, N, B, rng)
-        g_d = make_supports(ref_gcn, gk, K, N, B, rng)
-        d_y = rng.standard_normal((B, 1, N, N, 1)).astype(np.float32)
-        y = model(x_seq=torch.from_numpy(x_seq), G_list=[torch.from_numpy(g_static), (torch.from_numpy(g_o), torch.from_numpy(g_d))])
-        y.backward(torch.from_numpy(d_y))
-        rec = dict(x_seq=x_seq, G_static=g_static, G_o=g_o, G_d=g_d, d_y=d_y, y=_np(y), K=K, hidden=hid)
-        for k, v in model.state_dict().items():
-            rec["param:" + k] = _np(v)
-        for k, p in model.named_parameters():
-            rec["grad:" + k] = _np(p.grad)
+        for seed in range(3000 + idx, 6000, 100):
+            rec = _gen_one_model(ref_mpgcn, ref_gcn, seed, N, K, gk, T, B, hid)
+            if rec is not None:
+                break
+            print("  ", name, "seed", seed, "leaves a dead branch, trying the next")
+        else:
+            raise RuntimeError(f"{name}: no seed with two live branches")
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
-        print("wrote", name, "y", y.shape)
+        print("wrote", name, "y", rec["y"].shape, "seed", seed)
 
 
 ADJ_CASES = [
@@ -222,11 +299,20 @@ def main():
         sys.exit(f"reference not found at {REF}; fixtures can only be regenerated in the build container")
     ref_mpgcn = _load_ref("MPGCN")
     ref_gcn = _load_ref("GCN")
-    gen_bdgcn(ref_mpgcn, ref_gcn)
-    gen_lstm()
-    gen_model(ref_mpgcn, ref_gcn)
-    gen_adj(ref_gcn)
-    gen_dyn(_load_ref("Data_Container_OD"))
+    only = sys.argv[1:]                  # e.g. `gen_golden.py big model`: regenerate only those groups
+    want = lambda k: not only or k in only
+    if want("bdgcn"):
+        gen_bdgcn(ref_mpgcn, ref_gcn)
+    if want("big"):
+        gen_bdgcn_big(ref_mpgcn, ref_gcn)
+    if want("lstm"):
+        gen_lstm()
+    if want("model"):
+        gen_model(ref_mpgcn, ref_gcn)
+    if want("adj"):
+        gen_adj(ref_gcn)
+    if want("dyn"):
+        gen_dyn(_load_ref("Data_Container_OD"))
 
 
 if __name__ == "__main__":

@@ -28,7 +28,7 @@ import numpy as np
 __all__ = [
     "bdgcn_forward", "bdgcn_backward", "lstm_last_forward", "lstm_last_backward",
     "fc_relu_forward", "fc_relu_backward", "mpgcn_forward", "mpgcn_forward_backward",
-    "bdgcn_forward_factored", "rel_errors", "adj_process",
+    "bdgcn_forward_factored", "bdgcn_backward_factored", "rel_errors", "adj_process",
 ]
 
 
@@ -139,23 +139,67 @@ def bdgcn_backward(X, G, W, b, act, d_out, mask_from=None):
     return dX, dW, db
 
 
-def bdgcn_forward_factored(X, G, W, b=None, act="relu"):
-    """Algebraically identical 2K-product evaluation order used by the CUDA engine
-    (SURVEY.md section 7.1):  Z_d = X x_2 G_d ;  U_o = sum_d Z_d W[o,d] ;  pre = sum_o G_o^T x_1 U_o."""
-    X = np.asarray(X)
-    go, gd = _support_pair(G, X.shape[0])
+def _factored_forward(X, go, gd, W, b):
+    """Shared by the factored forward / backward: returns (pre, Z) with Z[d][b] = X[b] x_2 G_d as [n, l, e] arrays.
+    Every product is ONE BLAS call per sample (np.tensordot), so the oracle reaches N = 1000..2000 in seconds."""
     Bsz, N, _, C = X.shape
     K = go.shape[1]
     H = W.shape[1]
     W4 = W.reshape(K, K, C, H)
     pre = np.zeros((Bsz, N, N, H), dtype=X.dtype)
-    Z = [np.einsum("bncl,bce->bnel", X, np.broadcast_to(gd[:, d], (Bsz, N, N)), optimize=True) for d in range(K)]
-    for o in range(K):
-        U = sum(Z[d] @ W4[o, d] for d in range(K))                   # [B,n,e,H]
-        pre += np.einsum("bnm,bneh->bmeh", np.broadcast_to(go[:, o], (Bsz, N, N)), U, optimize=True)
+    Z = [[None] * Bsz for _ in range(K)]
+    for bi in range(Bsz):
+        for d in range(K):
+            Gd = gd[bi if gd.shape[0] > 1 else 0, d]                       # [c, e]
+            Z[d][bi] = np.tensordot(X[bi], Gd, axes=([1], [0]))            # [n, l, e]   (MPGCN.py:31/39, once per d)
+        for o in range(K):
+            U = sum(np.einsum("nle,lh->neh", Z[d][bi], W4[o, d], optimize=True) for d in range(K))   # [n, e, h]
+            Go = go[bi if go.shape[0] > 1 else 0, o]                       # [n, m]
+            pre[bi] += np.tensordot(Go, U, axes=([0], [0]))                # [m, e, h]   (MPGCN.py:30/38 + :45)
     if b is not None:
         pre = pre + b
+    return pre, Z
+
+
+def bdgcn_forward_factored(X, G, W, b=None, act="relu"):
+    """Algebraically identical 2K-product evaluation order used by the CUDA engine
+    (SURVEY.md section 7.1):  Z_d = X x_2 G_d ;  U_o = sum_d Z_d W[o,d] ;  pre = sum_o G_o^T x_1 U_o.
+    Checked against the reference-order `bdgcn_forward` in tests/test_oracle_golden.py (1e-12 in float64)."""
+    X = np.asarray(X)
+    go, gd = _support_pair(G, X.shape[0])
+    pre, _ = _factored_forward(X, go, gd, np.asarray(W), b)
     return np.maximum(pre, 0) if act == "relu" else pre
+
+
+def bdgcn_backward_factored(X, G, W, b, act, d_out, mask_from=None):
+    """Gradients of the layer in the factored order -- the same numbers as `bdgcn_backward`
+    (checked to 1e-12 in float64 in tests/test_oracle_golden.py), at 2K instead of 2K^2 N^3-products, each one BLAS call:
+        dPre = dOut * [pre > 0] ;  V_o = G_o x_1 dPre ;  dW[o,d] = sum Z_d^T V_o ;  Y_d = sum_o V_o W[o,d]^T ;
+        dX = sum_d Y_d x_2 G_d^T.
+    Returns (out, dX, dW, db)."""
+    X = np.asarray(X)
+    W = np.asarray(W)
+    go, gd = _support_pair(G, X.shape[0])
+    Bsz, N, _, C = X.shape
+    K = go.shape[1]
+    H = W.shape[1]
+    W4 = W.reshape(K, K, C, H)
+    pre, Z = _factored_forward(X, go, gd, W, b)
+    out = np.maximum(pre, 0) if act == "relu" else pre
+    d_pre = d_out * ((pre if mask_from is None else np.asarray(mask_from)) > 0) if act == "relu" else np.asarray(d_out)
+    db = d_pre.sum(axis=(0, 1, 2)) if b is not None else None
+    dW4 = np.zeros((K, K, C, H), dtype=X.dtype)
+    dX = np.zeros_like(X)
+    for bi in range(Bsz):
+        V = [np.tensordot(go[bi if go.shape[0] > 1 else 0, o], d_pre[bi], axes=([1], [0])) for o in range(K)]   # [n, e, h]
+        for d in range(K):
+            Y = np.zeros((N, N, C), dtype=X.dtype)                                                          # [n, e, l]
+            for o in range(K):
+                dW4[o, d] += np.tensordot(Z[d][bi], V[o], axes=([0, 2], [0, 1]))                            # [l, h]
+                Y += V[o] @ W4[o, d].T
+            Gd = gd[bi if gd.shape[0] > 1 else 0, d]                                                        # [c, e]
+            dX[bi] += np.transpose(np.tensordot(Y, Gd, axes=([1], [1])), (0, 2, 1))                         # [n, l, c] -> [n, c, l]
+    return out, dX, dW4.reshape(K * K * C, H), db
 
 
 # --------------------------------------------------------------------------------------
@@ -246,7 +290,7 @@ def _p(params, key):
     return np.asarray(params[key])
 
 
-def mpgcn_forward(params, x_seq, G_list, M, gcn_num_layers, act="relu"):
+def mpgcn_forward(params, x_seq, G_list, M, gcn_num_layers, act="relu", factored=False):
     """MPGCN.forward (MPGCN.py:89-112).  `params` maps the reference's state_dict keys
     (branch_models.{m}.temporal.weight_ih_l0 ... ) to arrays.
     x_seq [B,T,N,N,I]; G_list has M entries (static array or dynamic pair).
@@ -263,21 +307,22 @@ def mpgcn_forward(params, x_seq, G_list, M, gcn_num_layers, act="relu"):
         g = h.reshape(Bsz, N, N, -1)                                 # MPGCN.py:104
         for n in range(gcn_num_layers):                              # MPGCN.py:105-106
             bkey = pre + f"spatial.{n}.b"
-            g = bdgcn_forward(g, G_list[m], _p(params, pre + f"spatial.{n}.W"),
-                              _p(params, bkey) if bkey in params else None, act)
+            g = (bdgcn_forward_factored if factored else bdgcn_forward)(g, G_list[m], _p(params, pre + f"spatial.{n}.W"),
+                                                                        _p(params, bkey) if bkey in params else None, act)
         outs.append(fc_relu_forward(g, _p(params, pre + "fc.0.weight"), _p(params, pre + "fc.0.bias")))  # :107
     y = np.mean(np.stack(outs, axis=-1), axis=-1)                    # MPGCN.py:110
     return y[:, None]                                                # MPGCN.py:112
 
 
-def mpgcn_forward_backward(params, x_seq, G_list, M, gcn_num_layers, d_y, act="relu", masks=None):
+def mpgcn_forward_backward(params, x_seq, G_list, M, gcn_num_layers, d_y, act="relu", masks=None, factored=False):
     """Forward + gradients of every parameter (what `loss.backward()` produces through
     MPGCN.py:89-112).  d_y [B,1,N,N,I] is dL/d(output).  Returns (y, grads dict keyed like
     the state_dict).
 
     masks: optional {m: {"layers": [out_0, .., out_{L-1}], "fc": fc_out}} -- forward outputs of another
     implementation whose signs replace the oracle's own ReLU masks in the backward pass (see
-    bdgcn_backward's `mask_from`): the gradient of the function that implementation computed."""
+    bdgcn_backward's `mask_from`): the gradient of the function that implementation computed.
+    factored: evaluate the BDGCN layers in the factored (BLAS-shaped) order -- same numbers, usable at N = 200+."""
     x_seq = np.asarray(x_seq)
     Bsz, T, N, _, I = x_seq.shape
     lstm_in = np.transpose(x_seq, (0, 2, 3, 1, 4)).reshape(Bsz * N * N, T, I)
@@ -291,8 +336,8 @@ def mpgcn_forward_backward(params, x_seq, G_list, M, gcn_num_layers, d_y, act="r
         acts = [h.reshape(Bsz, N, N, -1)]
         for n in range(gcn_num_layers):
             bkey = pre + f"spatial.{n}.b"
-            acts.append(bdgcn_forward(acts[-1], G_list[m], _p(params, pre + f"spatial.{n}.W"),
-                                      _p(params, bkey) if bkey in params else None, act))
+            acts.append((bdgcn_forward_factored if factored else bdgcn_forward)(
+                acts[-1], G_list[m], _p(params, pre + f"spatial.{n}.W"), _p(params, bkey) if bkey in params else None, act))
         outs.append(fc_relu_forward(acts[-1], _p(params, pre + "fc.0.weight"), _p(params, pre + "fc.0.bias")))
         tapes.append((lw, acts))
     y = np.mean(np.stack(outs, axis=-1), axis=-1)[:, None]
@@ -306,9 +351,12 @@ def mpgcn_forward_backward(params, x_seq, G_list, M, gcn_num_layers, d_y, act="r
         grads[pre + "fc.0.weight"], grads[pre + "fc.0.bias"] = dw, db
         for n in reversed(range(gcn_num_layers)):
             bkey = pre + f"spatial.{n}.b"
-            d, dW, dbb = bdgcn_backward(acts[n], G_list[m], _p(params, pre + f"spatial.{n}.W"),
-                                        _p(params, bkey) if bkey in params else None, act, d,
-                                        mask_from=None if mk is None else mk["layers"][n])
+            largs = (acts[n], G_list[m], _p(params, pre + f"spatial.{n}.W"), _p(params, bkey) if bkey in params else None, act, d)
+            mf = None if mk is None else mk["layers"][n]
+            if factored:
+                _, d, dW, dbb = bdgcn_backward_factored(*largs, mask_from=mf)
+            else:
+                d, dW, dbb = bdgcn_backward(*largs, mask_from=mf)
             grads[pre + f"spatial.{n}.W"] = dW
             if dbb is not None:
                 grads[bkey] = dbb
