@@ -180,7 +180,11 @@ MPGCN_API int mpgcn_head_backward(const float* const* g, const float* w, const f
  * (0 FWD_A, 1 FWD_MIX, 2 FWD_B, 3 BWD_V, 4 BWD_DW, 5 BWD_MIX, 6 BWD_DX: tcgen05 contractions; 7 fp32 SIMT GEMM;
  * 8 elementwise/layout; 9 LSTM forward; 10 LSTM backward).  With profiling enabled, tags 0-6, 9, 10 are also
  * bracketed by CUDA events on the launch stream; mpgcn_profile_read (HOST pointers; call after synchronising)
- * returns launches, algorithmic flops and summed device milliseconds since the last reset. */
+ * returns launches, algorithmic flops and summed device milliseconds since the last reset.
+ * Tags 11 (mpgcn_bdgcn_forward*), 12 (mpgcn_bdgcn_backward*) and 13 (mpgcn_head_*) are REGIONS: whole C-ABI calls -- every
+ * kernel of the call and the gaps between them -- with `launches` counting calls and `flops` the layer's algorithmic work
+ * (per sample F_fwd = 2KN^3(C+H) + 2K^2N^2CH, F_bwd = 2KN^3(C+H) + 4K^2N^2CH); bench.py's `roofline_layer`.
+ * Thread-safe: counters behind a mutex, the open bracket is per calling thread. */
 MPGCN_API void mpgcn_profile_enable(int on);
 MPGCN_API void mpgcn_profile_reset(void);
 MPGCN_API int mpgcn_profile_read(int tag, long long* launches, double* flops, double* ms);

@@ -112,7 +112,9 @@ def check(code: int, what: str) -> None:
         raise RuntimeError(f"mpgcn_b200.{what} failed: {msg.decode() if msg else 'unknown error'}")
 
 
-PROFILE_TAGS = ("FWD_A", "FWD_MIX", "FWD_B", "BWD_V", "BWD_DW", "BWD_MIX", "BWD_DX", "SIMT_GEMM", "ELEMENTWISE", "LSTM_FWD", "LSTM_BWD")
+PROFILE_TAGS = ("FWD_A", "FWD_MIX", "FWD_B", "BWD_V", "BWD_DW", "BWD_MIX", "BWD_DX", "SIMT_GEMM", "ELEMENTWISE", "LSTM_FWD", "LSTM_BWD",
+                "LAYER_FWD", "LAYER_BWD", "HEAD")
+REGION_TAGS = ("LAYER_FWD", "LAYER_BWD", "HEAD")      # whole C-ABI calls (their `launches` count calls, not kernels)
 
 
 def profile_read() -> dict:

@@ -21,6 +21,12 @@ static BdgcnShape mk(int B, int N, int K, int C, int H, int dynamic, int act) {
   return s;
 }
 
+// algorithmic flops of one layer call: F_f = 2KN^3(C+H) + 2K^2N^2CH, F_fb = 4KN^3(C+H) + 6K^2N^2CH
+static double layer_flops(const BdgcnShape& s, bool backward) {
+  const double n3 = 2.0 * s.K * (double)s.N * s.N * s.N * (s.C + s.H), mix = 2.0 * s.K * s.K * (double)s.N * s.N * s.C * s.H;
+  return s.B * (backward ? n3 + 2.0 * mix : n3 + mix);
+}
+
 static int check_shape(const BdgcnShape& s, int precision) {
   MPGCN_CHECK(s.B >= 1 && s.N >= 1 && s.K >= 1 && s.C >= 1 && s.H >= 1, "bad BDGCN shape B=%d N=%d K=%d C=%d H=%d", s.B, s.N, s.K, s.C, s.H);
   MPGCN_CHECK(precision == PREC_FP32_SIMT || precision == PREC_FP16_TC, "unknown precision %d", precision);
@@ -80,6 +86,7 @@ int mpgcn_bdgcn_forward_x(const float* X, const float* G_o, const float* G_d, in
   if (int e = check_shape(s, precision)) return e;
   MPGCN_CHECK(X && G_o && G_d && W && out && workspace, "mpgcn_bdgcn_forward: null pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfRegion region(PROF_LAYER_FWD, layer_flops(s, false), st);
   if (precision == PREC_FP16_TC) return bdgcn_forward_tc(s, X, G_o, G_d, W, bias, out, saved, workspace, workspace_bytes, to_extras(extras), st);
   return bdgcn_forward_simt(s, X, G_o, G_d, W, bias, out, saved, workspace, workspace_bytes, st);      // exact path: extras unused
 }
@@ -99,6 +106,7 @@ int mpgcn_bdgcn_backward_x(const float* d_out, const float* out, const float* G_
   const bool have_out16 = extras && extras->out_f16 && precision == PREC_FP16_TC;
   MPGCN_CHECK(d_out && (out || have_out16) && G_o && G_d && W && saved && dW && workspace, "mpgcn_bdgcn_backward: null pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfRegion region(PROF_LAYER_BWD, layer_flops(s, true), st);
   if (precision == PREC_FP16_TC)
     return bdgcn_backward_tc(s, d_out, out, G_o, G_d, W, saved, dX, dW, db, workspace, workspace_bytes, to_extras(extras), st);
   if (extras && extras->dX_absmax) MPGCN_CUDA(cudaMemsetAsync(extras->dX_absmax, 0, sizeof(float), st));      // "unknown"
@@ -132,12 +140,14 @@ int mpgcn_adj_process(const float* flow, float* supports, int B, int N, int kern
 int mpgcn_head_forward(const float* const* g, const float* w, const float* bias, float* y, float* pre, long long cells, int C, int M,
                        void* stream) {
   MPGCN_CHECK(g && w && bias && y && cells >= 1, "mpgcn_head_forward: null pointer or empty input");
+  ProfRegion region(PROF_HEAD, 2.0 * cells * C * M, static_cast<cudaStream_t>(stream));
   return head_forward(g, w, bias, y, pre, cells, C, M, static_cast<cudaStream_t>(stream));
 }
 
 int mpgcn_head_backward(const float* const* g, const float* w, const float* pre, const float* dy, float* const* dg, float* dw, float* db,
                         float* dg_absmax, long long cells, int C, int M, void* stream) {
   MPGCN_CHECK(g && w && pre && dy && dw && db && cells >= 1, "mpgcn_head_backward: null pointer or empty input");
+  ProfRegion region(PROF_HEAD, 4.0 * cells * C * M, static_cast<cudaStream_t>(stream));
   return head_backward(g, w, pre, dy, dg, dw, db, dg_absmax, cells, C, M, static_cast<cudaStream_t>(stream));
 }
 

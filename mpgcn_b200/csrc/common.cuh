@@ -249,8 +249,12 @@ inline int ensure_dyn_smem(Kernel kernel, int bytes, DynSmemAttr& cache) {
 // ----------------------------------------------------------------------------------------
 enum ProfTag {
   PROF_FWD_A = 0, PROF_FWD_MIX, PROF_FWD_B, PROF_BWD_V, PROF_BWD_DW, PROF_BWD_MIX, PROF_BWD_DX,   // tcgen05 contractions
-  PROF_SIMT_GEMM, PROF_ELEMENTWISE, PROF_LSTM_FWD, PROF_LSTM_BWD, PROF_NUM_TAGS
+  PROF_SIMT_GEMM, PROF_ELEMENTWISE, PROF_LSTM_FWD, PROF_LSTM_BWD,
+  // regions, not kernels: a whole C-ABI call (every kernel of it, the gaps between them included); they count calls, not launches
+  PROF_LAYER_FWD, PROF_LAYER_BWD, PROF_HEAD,
+  PROF_NUM_TAGS
 };
+constexpr int PROF_FIRST_REGION_TAG = PROF_LAYER_FWD;
 // All of these may be called from several host threads (one stream each): the counters sit behind a mutex, the
 // "next launch" annotation and the open begin/end bracket are thread-local.
 void prof_set_next(int tag, double flops);             // annotate the next contraction launch (this thread's)
@@ -258,5 +262,13 @@ void prof_take_next(int* tag, double* flops);          // fetch and clear this t
 void prof_count(int tag);                              // count one launch of our own kernels
 void prof_begin(int tag, double flops, cudaStream_t s);   // event before launch (no-op unless enabled)
 void prof_end(cudaStream_t s);                            // event after launch
+// whole-call bracket (nests around the per-launch brackets): event pair recorded only while profiling is enabled
+struct ProfRegion {
+  void* a = nullptr;
+  int tag;
+  cudaStream_t s;
+  ProfRegion(int tag, double flops, cudaStream_t s);
+  ~ProfRegion();
+};
 
 }  // namespace mpgcn

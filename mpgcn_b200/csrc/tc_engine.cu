@@ -99,6 +99,21 @@ void prof_end(cudaStream_t s) {
   g_prof.pending.push_back({t_cur_a, b, t_cur_tag});
   t_cur_a = nullptr;
 }
+ProfRegion::ProfRegion(int tag_, double flops, cudaStream_t s_) : tag(tag_), s(s_) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  if (tag >= 0 && tag < PROF_NUM_TAGS) { g_prof.launches[tag]++; g_prof.flops[tag] += flops; }
+  if (!g_prof.enabled) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, s);
+  a = e;
+}
+ProfRegion::~ProfRegion() {
+  if (a == nullptr) return;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  cudaEvent_t b = prof_event();
+  cudaEventRecord(b, s);
+  g_prof.pending.push_back({static_cast<cudaEvent_t>(a), b, tag});
+}
 void prof_enable(int on) {
   std::lock_guard<std::mutex> lock(g_prof.mu);
   g_prof.enabled = on != 0;

@@ -46,3 +46,63 @@ def forecast(model, x_seq: torch.Tensor, G_list, pred_len: int, use_cuda_graph: 
             return torch.cat(outs, dim=1)
     finally:
         model.train(was_training)
+
+
+class _GraphedInference:
+    """`model.forward` replacement installed by `install`: under torch.no_grad() in eval mode on CUDA, a call whose input
+    shape and support tensors (identity + version) match the last captured call replays that CUDA graph -- copy x in,
+    replay, clone y out -- and anything else (training, grad mode, new supports) falls through to / re-captures the
+    normal forward.  `ModelTrainer.test` (Model_Trainer.py:157-165) calls the model `pred_len` times per batch with the
+    same supports: one capture, pred_len - 1 replays; the window slide stays the trainer's own `torch.cat`."""
+
+    def __init__(self, model):
+        self.model = model
+        self.eager = model.forward          # the bound, un-patched method
+        self.key = None
+        self.graph = self.static_x = self.static_y = self.keep = None
+        self.captures = self.replays = 0
+
+    @staticmethod
+    def _flat(G_list):
+        out = []
+        for g in G_list:
+            out.extend(g if isinstance(g, (tuple, list)) else [g])
+        return out
+
+    def __call__(self, x_seq, G_list):
+        if torch.is_grad_enabled() or self.model.training or not x_seq.is_cuda:
+            return self.eager(x_seq=x_seq, G_list=G_list)
+        gs = self._flat(G_list)
+        key = (tuple(x_seq.shape), x_seq.device, tuple((id(g), g._version, g.data_ptr()) for g in gs))
+        if key != self.key:
+            self.key = None
+            self.graph = self.static_x = self.static_y = None
+            static_x = x_seq.clone()
+            side = torch.cuda.Stream(device=x_seq.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):               # warm-up outside the capture: function attributes, support staging
+                self.eager(x_seq=static_x, G_list=G_list)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_y = self.eager(x_seq=static_x, G_list=G_list)
+            self.graph, self.static_x, self.static_y, self.keep, self.key = graph, static_x, static_y, gs, key
+            self.captures += 1
+        self.static_x.copy_(x_seq)
+        self.graph.replay()
+        self.replays += 1
+        return self.static_y.clone()
+
+
+def install(model):
+    """Opt-in: route the model's inference calls through a captured CUDA graph (see _GraphedInference).  Returns the model.
+    `model.forward.captures / .replays` count what happened; `uninstall(model)` restores the plain forward."""
+    if not isinstance(getattr(model, "forward", None), _GraphedInference):
+        model.forward = _GraphedInference(model)
+    return model
+
+
+def uninstall(model):
+    if isinstance(model.__dict__.get("forward"), _GraphedInference):
+        del model.__dict__["forward"]
+    return model

@@ -91,3 +91,51 @@ def estimate_model_step_seconds(N, K, T, M=2, L=3, C=32, lstm_sample_cells=None,
     total = M * (L * t_layer + t_lstm)
     return total, dict(t_bdgcn_layer_s=t_layer, t_lstm_sample_s=t_lstm_sample, lstm_sample_cells=sample, t_lstm_scaled_s=t_lstm,
                        formula="M*(L*t_layer + t_lstm), B=1")
+
+
+class PortBDGCN(torch.nn.Module):
+    """The port's layer as a module with the reference's parameter names (W [K*K*C, H], b [H]); MPGCN.py:6-50."""
+
+    def __init__(self, K, input_dim, hidden_dim, use_bias=True, activation=None):
+        super().__init__()
+        self.K = K
+        self.W = torch.nn.Parameter(torch.empty(K * K * input_dim, hidden_dim))
+        torch.nn.init.xavier_normal_(self.W)
+        self.b = torch.nn.Parameter(torch.zeros(hidden_dim)) if use_bias else None
+        self.relu = activation is not None
+
+    def forward(self, X, G):
+        return bdgcn_layer(X, G, self.W, self.b, relu=self.relu)
+
+
+class PortMPGCN(torch.nn.Module):
+    """The port's model: per branch nn.LSTM over B*N*N cells (zero state, last step) -> L x PortBDGCN -> Linear+ReLU, mean over
+    branches (MPGCN.py:54-112), including the reference's materialisations (zero (h0, c0), the full lstm_out, stack + mean).
+    Used only where the real reference (baseline/_ref) is not available."""
+
+    def __init__(self, M, K, input_dim, lstm_hidden_dim, lstm_num_layers, gcn_hidden_dim, gcn_num_layers, num_nodes, user_bias,
+                 activation=None):
+        super().__init__()
+        self.M, self.N, self.C, self.layers = M, num_nodes, lstm_hidden_dim, lstm_num_layers
+        self.branch_models = torch.nn.ModuleList()
+        for _ in range(M):
+            br = torch.nn.ModuleDict()
+            br["temporal"] = torch.nn.LSTM(input_size=input_dim, hidden_size=lstm_hidden_dim, num_layers=lstm_num_layers, batch_first=True)
+            br["spatial"] = torch.nn.ModuleList(PortBDGCN(K, lstm_hidden_dim if n == 0 else gcn_hidden_dim, gcn_hidden_dim, user_bias, activation)
+                                                for n in range(gcn_num_layers))
+            br["fc"] = torch.nn.Sequential(torch.nn.Linear(gcn_hidden_dim, input_dim), torch.nn.ReLU())
+            self.branch_models.append(br)
+
+    def forward(self, x_seq, G_list):
+        B, T, N, _, I = x_seq.shape
+        lstm_in = x_seq.permute(0, 2, 3, 1, 4).reshape(B * N * N, T, I)
+        outs = []
+        for m in range(self.M):
+            br = self.branch_models[m]
+            h0 = x_seq.new_zeros(self.layers, B * N * N, self.C)
+            out, _ = br["temporal"](lstm_in, (h0, h0.clone()))
+            g = out[:, -1, :].reshape(B, N, N, self.C)
+            for layer in br["spatial"]:
+                g = layer(g, G_list[m])
+            outs.append(br["fc"](g))
+        return torch.mean(torch.stack(outs, dim=-1), dim=-1).unsqueeze(dim=1)
