@@ -354,7 +354,7 @@ def run_ours(a):
         if sharded:
             loss = mshard.sharded_mse_loss(plan, fwd(x, go, gd), y)
             loss.backward()
-            mshard.allreduce_sum_gradients(params)      # every rank holds partial parameter gradients of the SAME samples
+            mshard.allreduce_sum_gradients(params, plan, model)      # every rank holds partial parameter gradients of the SAME samples
         else:
             loss = crit(fwd(x, go, gd), y)
             loss.backward()

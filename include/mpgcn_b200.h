@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define MPGCN_B200_ABI_VERSION 2   /* 2: extras struct, prepared supports, LSTM training pair, dg_absmax, dyn graphs */
+#define MPGCN_B200_ABI_VERSION 3   /* 2: extras struct, prepared supports, LSTM training pair, dg_absmax, dyn graphs;
+                                      3: layer parts (origin-row / support shards), bias_act, relu_backward, region tags */
 
 #if defined(__GNUC__)
 #define MPGCN_API __attribute__((visibility("default")))
@@ -104,6 +105,40 @@ MPGCN_API int mpgcn_bdgcn_backward_x(const float* d_out, const float* out, const
 MPGCN_API int mpgcn_bdgcn_backward_ex(const float* d_out, const float* out, const float* G_o, const float* G_d, int dynamic, const float* W, int act,
                             const void* saved, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int B, int N,
                             int K, int C, int H, int precision, const float* d_out_absmax, float* dX_absmax, void* stream);
+
+/* ---- PARTS of a layer: what one GPU evaluates when a layer is sharded -----------------------------------
+ * The reference has no multi-GPU code; these entry points are the B200-native addition behind the same BDGCN.forward math
+ * (MPGCN.py:24-50).  A part is described by
+ *     rows [row0, row0 + rows) of the N ORIGIN rows n that this call holds of X / dX (and of the internal Z, U, V, Y), and
+ *     Ko origin supports in G_o ([Ko,N,N] or [B,Ko,N,N]), Kd destination supports in G_d, W = the [Ko*Kd*C, H] slice of the
+ *     layer's weight in (o, d, l) row order.
+ *   origin-row shard (8(e) row 1): rows = N / g, Ko = Kd = K, the same G for every rank;
+ *   K shard          (8(e) row 2): rows = N, Ko = K, Kd = K / g, G_d = this rank's destination supports, W[:, D_j] its slice.
+ * forward_part writes the RAW PARTIAL pre-activation for EVERY origin row m
+ *     pre_partial[b,m,e,h] = sum_{o < Ko} sum_{n in rows} G_o[n,m] * ( sum_{d < Kd, l} (sum_c X[b,n,c,l] G_d[c,e]) W[o,d,l,h] )
+ * -- no bias, no activation: the caller sums the partials over the ranks (reduce-scatter over m / all-reduce) and then applies
+ * mpgcn_bias_act.  backward_part takes dPre [B,N,N,H] for every origin row m (the caller masks its own rows with
+ * mpgcn_relu_backward and all-gathers them / has them replicated) and returns dX for its rows ([B,rows,N,C]; K shard: the
+ * partial sum over its d, to be all-reduced) and dW for its slice (row shard: partial over its rows, to be all-reduced).
+ *   X [B,rows,N,C]   pre_partial [B,N,N,H]   saved: mpgcn_bdgcn_part_saved_bytes   d_pre [B,N,N,H]   dX [B,rows,N,C] or NULL
+ *   d_pre_absmax (nullable): device scalar already holding max|d_pre| (skips one pass; precision 1 only). */
+typedef struct mpgcn_bdgcn_part {
+  int row0, rows;
+  int Ko, Kd;
+} mpgcn_bdgcn_part;
+MPGCN_API size_t mpgcn_bdgcn_part_saved_bytes(int B, int N, int C, int H, int precision, const mpgcn_bdgcn_part* part);
+MPGCN_API size_t mpgcn_bdgcn_part_fwd_workspace_bytes(int B, int N, int C, int H, int dynamic, int precision, const mpgcn_bdgcn_part* part);
+MPGCN_API size_t mpgcn_bdgcn_part_bwd_workspace_bytes(int B, int N, int C, int H, int dynamic, int precision, const mpgcn_bdgcn_part* part);
+MPGCN_API int mpgcn_bdgcn_forward_part(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, float* pre_partial,
+                             void* saved, void* workspace, size_t workspace_bytes, int B, int N, int C, int H, int precision,
+                             const mpgcn_bdgcn_part* part, void* stream);
+MPGCN_API int mpgcn_bdgcn_backward_part(const float* d_pre, const float* G_o, const float* G_d, int dynamic, const float* W, const void* saved,
+                              float* dX, float* dW, void* workspace, size_t workspace_bytes, int B, int N, int C, int H, int precision,
+                              const mpgcn_bdgcn_part* part, const float* d_pre_absmax, void* stream);
+/* x[i] = act(x[i] + bias[i % H]) in place -- the `+= b`, activation of MPGCN.py:47-49, applied AFTER the exchange step */
+MPGCN_API int mpgcn_bias_act(float* x, const float* bias, int act, long long n, int H, void* stream);
+/* d_pre = d_out * [out > 0] (act 1) or d_out (act 0); db[h] = sum d_pre (nullable) -- the head of the backward, BEFORE the exchange */
+MPGCN_API int mpgcn_relu_backward(const float* d_out, const float* out, int act, float* d_pre, float* db, long long n, int H, void* stream);
 
 /* nn.LSTM(input_size=1, hidden=C, layers=1, batch_first) over the B*NN OD cells with zero initial
  * state, returning only the last hidden state (reference MPGCN.py:69,80-87,100-104).

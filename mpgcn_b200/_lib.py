@@ -63,10 +63,19 @@ _SIGS = {
     "mpgcn_lstm_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]),
     "mpgcn_lstm_last_forward": (ctypes.c_int, [_c_f] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
                                                ctypes.c_void_p]),
+    "mpgcn_bdgcn_part_saved_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5 + [ctypes.c_void_p]),
+    "mpgcn_bdgcn_part_fwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    "mpgcn_bdgcn_part_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 6 + [ctypes.c_void_p]),
+    "mpgcn_bdgcn_forward_part": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, ctypes.c_size_t] + [ctypes.c_int] * 5 +
+                                 [ctypes.c_void_p, ctypes.c_void_p]),
+    "mpgcn_bdgcn_backward_part": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, _c_f, ctypes.c_size_t] + [ctypes.c_int] * 5 +
+                                  [ctypes.c_void_p, _c_f, ctypes.c_void_p]),
+    "mpgcn_bias_act": (ctypes.c_int, [_c_f, _c_f, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
+    "mpgcn_relu_backward": (ctypes.c_int, [_c_f, _c_f, ctypes.c_int, _c_f, _c_f, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]),
     "mpgcn_lstm_last_backward": (ctypes.c_int, [_c_f] * 12 + [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_void_p]),
 }
-ABI_VERSION = 2          # MPGCN_B200_ABI_VERSION of include/mpgcn_b200.h this binding was written against
+ABI_VERSION = 3          # MPGCN_B200_ABI_VERSION of include/mpgcn_b200.h this binding was written against
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
 
@@ -74,6 +83,11 @@ class BdgcnExtras(ctypes.Structure):
     """mpgcn_bdgcn_extras (include/mpgcn_b200.h): optional side inputs / outputs of the tensor-core layer."""
     _fields_ = [("go_prepared", ctypes.c_void_p), ("gd_prepared", ctypes.c_void_p), ("x_f16", ctypes.c_void_p),
                 ("out_f16", ctypes.c_void_p), ("d_out_absmax", ctypes.c_void_p), ("dX_absmax", ctypes.c_void_p)]
+
+
+class BdgcnPart(ctypes.Structure):
+    """mpgcn_bdgcn_part (include/mpgcn_b200.h): origin rows [row0, row0 + rows), Ko origin / Kd destination supports."""
+    _fields_ = [("row0", ctypes.c_int), ("rows", ctypes.c_int), ("Ko", ctypes.c_int), ("Kd", ctypes.c_int)]
 
 
 def build(verbose: bool = False) -> str:

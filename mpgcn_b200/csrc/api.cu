@@ -18,7 +18,25 @@ using namespace mpgcn;
 static BdgcnShape mk(int B, int N, int K, int C, int H, int dynamic, int act) {
   BdgcnShape s;
   s.B = B; s.N = N; s.K = K; s.C = C; s.H = H; s.dynamic = dynamic; s.act = act;
+  s.R = N; s.row0 = 0; s.Ko = K; s.Kd = K; s.partial = 0;      // the whole layer
   return s;
+}
+
+// a PART of the layer (include/mpgcn_b200.h: mpgcn_bdgcn_part)
+static BdgcnShape mk_part(int B, int N, int C, int H, int dynamic, const mpgcn_bdgcn_part* part) {
+  BdgcnShape s = mk(B, N, part ? (part->Ko > part->Kd ? part->Ko : part->Kd) : 1, C, H, dynamic, 0);
+  if (part) { s.R = part->rows; s.row0 = part->row0; s.Ko = part->Ko; s.Kd = part->Kd; }
+  s.partial = 1;
+  return s;
+}
+static int check_part(const BdgcnShape& s, int precision) {
+  MPGCN_CHECK(s.B >= 1 && s.N >= 1 && s.C >= 1 && s.H >= 1, "bad BDGCN shape B=%d N=%d C=%d H=%d", s.B, s.N, s.C, s.H);
+  MPGCN_CHECK(s.Ko >= 1 && s.Kd >= 1 && s.R >= 1 && s.row0 >= 0 && s.row0 + s.R <= s.N,
+              "bad layer part: rows [%d, %d) of N=%d, Ko=%d, Kd=%d", s.row0, s.row0 + s.R, s.N, s.Ko, s.Kd);
+  MPGCN_CHECK(precision == PREC_FP32_SIMT || precision == PREC_FP16_TC, "unknown precision %d", precision);
+  if (precision == PREC_FP16_TC)
+    MPGCN_CHECK(tc_supported(s), "precision 1 (tcgen05) needs C == H == 32 and Ko, Kd <= 8 (got C=%d H=%d Ko=%d Kd=%d)", s.C, s.H, s.Ko, s.Kd);
+  return 0;
 }
 
 // algorithmic flops of one layer call: F_f = 2KN^3(C+H) + 2K^2N^2CH, F_fb = 4KN^3(C+H) + 6K^2N^2CH
@@ -127,6 +145,62 @@ int mpgcn_bdgcn_backward(const float* d_out, const float* out, const float* G_o,
                          int K, int C, int H, int precision, void* stream) {
   return mpgcn_bdgcn_backward_x(d_out, out, G_o, G_d, dynamic, W, act, saved, dX, dW, db, workspace, workspace_bytes, B, N, K, C, H,
                                 precision, nullptr, stream);
+}
+
+size_t mpgcn_bdgcn_part_saved_bytes(int B, int N, int C, int H, int precision, const mpgcn_bdgcn_part* part) {
+  const BdgcnShape s = mk_part(B, N, C, H, 0, part);
+  return precision == PREC_FP16_TC ? tc_saved_bytes(s) : simt_saved_bytes(s);
+}
+size_t mpgcn_bdgcn_part_fwd_workspace_bytes(int B, int N, int C, int H, int dynamic, int precision, const mpgcn_bdgcn_part* part) {
+  const BdgcnShape s = mk_part(B, N, C, H, dynamic, part);
+  return precision == PREC_FP16_TC ? tc_fwd_ws_bytes(s) : simt_fwd_ws_bytes(s);
+}
+size_t mpgcn_bdgcn_part_bwd_workspace_bytes(int B, int N, int C, int H, int dynamic, int precision, const mpgcn_bdgcn_part* part) {
+  const BdgcnShape s = mk_part(B, N, C, H, dynamic, part);
+  return precision == PREC_FP16_TC ? tc_bwd_ws_bytes(s) : simt_bwd_ws_bytes(s);
+}
+
+int mpgcn_bdgcn_forward_part(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, float* pre_partial, void* saved,
+                             void* workspace, size_t workspace_bytes, int B, int N, int C, int H, int precision,
+                             const mpgcn_bdgcn_part* part, void* stream) {
+  MPGCN_CHECK(part != nullptr, "mpgcn_bdgcn_forward_part: part descriptor is NULL");
+  const BdgcnShape s = mk_part(B, N, C, H, dynamic ? 1 : 0, part);
+  if (int e = check_part(s, precision)) return e;
+  MPGCN_CHECK(X && G_o && G_d && W && pre_partial && workspace, "mpgcn_bdgcn_forward_part: null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfRegion region(PROF_LAYER_FWD, layer_flops(s, false) * s.R / s.N * (s.Ko + s.Kd) / (2.0 * s.K), st);
+  if (precision == PREC_FP16_TC)
+    return bdgcn_forward_tc(s, X, G_o, G_d, W, nullptr, pre_partial, saved, workspace, workspace_bytes, BdgcnExtras(), st);
+  return bdgcn_forward_simt(s, X, G_o, G_d, W, nullptr, pre_partial, saved, workspace, workspace_bytes, st);
+}
+
+int mpgcn_bdgcn_backward_part(const float* d_pre, const float* G_o, const float* G_d, int dynamic, const float* W, const void* saved, float* dX,
+                              float* dW, void* workspace, size_t workspace_bytes, int B, int N, int C, int H, int precision,
+                              const mpgcn_bdgcn_part* part, const float* d_pre_absmax, void* stream) {
+  MPGCN_CHECK(part != nullptr, "mpgcn_bdgcn_backward_part: part descriptor is NULL");
+  const BdgcnShape s = mk_part(B, N, C, H, dynamic ? 1 : 0, part);
+  if (int e = check_part(s, precision)) return e;
+  MPGCN_CHECK(d_pre && G_o && G_d && W && saved && dW && workspace, "mpgcn_bdgcn_backward_part: null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfRegion region(PROF_LAYER_BWD, layer_flops(s, true) * s.R / s.N * (s.Ko + s.Kd) / (2.0 * s.K), st);
+  if (precision == PREC_FP16_TC) {
+    BdgcnExtras ex;
+    ex.d_out_absmax = d_pre_absmax;
+    return bdgcn_backward_tc(s, d_pre, nullptr, G_o, G_d, W, saved, dX, dW, nullptr, workspace, workspace_bytes, ex, st);
+  }
+  return bdgcn_backward_simt(s, d_pre, nullptr, G_o, G_d, W, saved, dX, dW, nullptr, workspace, workspace_bytes, st);
+}
+
+int mpgcn_bias_act(float* x, const float* bias, int act, long long n, int H, void* stream) {
+  MPGCN_CHECK(x && n >= 1 && (act == 0 || act == 1), "mpgcn_bias_act: bad argument");
+  return bias_act_inplace(x, bias, act, (size_t)n, H, static_cast<cudaStream_t>(stream));
+}
+
+int mpgcn_relu_backward(const float* d_out, const float* out, int act, float* d_pre, float* db, long long n, int H, void* stream) {
+  MPGCN_CHECK(d_out && d_pre && n >= 1 && (act == 0 || (act == 1 && out)), "mpgcn_relu_backward: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * H, st));
+  return relu_bwd_prep(d_out, out, act, nullptr, d_pre, db, (size_t)n, H, nullptr, st);
 }
 
 int mpgcn_adj_num_supports(int kernel_type, int K) { return adj_num_supports(kernel_type, K); }

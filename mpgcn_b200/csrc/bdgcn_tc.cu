@@ -104,15 +104,20 @@ static int launch_big(int ak, GemmParams& p, int m_rows, cudaStream_t st) {
   return tc::launch_contract(ak, 64, p, st);
 }
 
-bool tc_supported(const BdgcnShape& s) { return s.C == 32 && s.H == 32 && s.K >= 1 && s.K <= 8 && s.N >= 1 && s.B >= 1; }
+bool tc_supported(const BdgcnShape& s) {
+  return s.C == 32 && s.H == 32 && s.Ko >= 1 && s.Ko <= 8 && s.Kd >= 1 && s.Kd <= 8 && s.N >= 1 && s.B >= 1 && s.R >= 1 && s.row0 >= 0 &&
+         s.row0 + s.R <= s.N;
+}
 
-static size_t n2(const BdgcnShape& s) { return (size_t)s.N * s.N; }
-static size_t g16_elems(const BdgcnShape& s) { return (size_t)(s.dynamic ? s.B : 1) * s.K * s.N * pad8(s.N); }
+// cells of an activation slab: R origin rows x N destinations
+static size_t rn(const BdgcnShape& s) { return (size_t)s.R * s.N; }
+static size_t g16_elems(const BdgcnShape& s, int K) { return (size_t)(s.dynamic ? s.B : 1) * K * s.N * pad8(s.N); }
+static size_t g_planes(const BdgcnShape& s, int K) { return (size_t)(s.dynamic ? s.B : 1) * K; }
 
-size_t tc_saved_bytes(const BdgcnShape& s) { return (size_t)s.B * s.K * n2(s) * s.C * sizeof(__half); }
+size_t tc_saved_bytes(const BdgcnShape& s) { return (size_t)s.B * s.Kd * rn(s) * s.C * sizeof(__half); }
 
 // workspace layouts (byte offsets); also served to tests by mpgcn_debug_tc_workspace_offset()
-struct FwdLayout { size_t x16, gd16, go16, w16, u16, z16, dd, dgo, total; };
+struct FwdLayout { size_t x16, gd16, go16, w16, u16, z16, dd, dgo, dgo_masked, total; };
 struct BwdLayout { size_t dp16, gd16, go16, v16, y16, wq16, partials, scale, total; };
 static size_t take(size_t& off, size_t bytes) {
   off = align_up(off, 1024);
@@ -123,22 +128,23 @@ static size_t take(size_t& off, size_t bytes) {
 static FwdLayout fwd_layout(const BdgcnShape& s) {
   FwdLayout L;
   size_t off = 0;
-  L.x16 = take(off, (size_t)s.B * n2(s) * 32 * 2);
-  L.gd16 = take(off, g16_elems(s) * 2);
-  L.go16 = take(off, g16_elems(s) * 2);
-  L.w16 = take(off, (size_t)2 * s.K * s.K * 32 * 32 * 2);      // [hi | lo]
-  L.u16 = take(off, (size_t)s.B * s.K * n2(s) * 32 * 2);
-  L.dd = take(off, (size_t)(s.dynamic ? s.B : 1) * s.K * s.N * 4);   // support-diagonal fp16 remainders (destination / origin)
-  L.dgo = take(off, (size_t)(s.dynamic ? s.B : 1) * s.K * s.N * 4);
+  L.x16 = take(off, (size_t)s.B * rn(s) * 32 * 2);
+  L.gd16 = take(off, g16_elems(s, s.Kd) * 2);
+  L.go16 = take(off, g16_elems(s, s.Ko) * 2);
+  L.w16 = take(off, (size_t)2 * s.Ko * s.Kd * 32 * 32 * 2);      // [hi | lo]
+  L.u16 = take(off, (size_t)s.B * s.Ko * rn(s) * 32 * 2);
+  L.dd = take(off, g_planes(s, s.Kd) * s.N * 4);   // support-diagonal fp16 remainders (destination / origin)
+  L.dgo = take(off, g_planes(s, s.Ko) * s.N * 4);
+  L.dgo_masked = take(off, g_planes(s, s.Ko) * s.N * 4);   // origin remainders restricted to the row slab
   L.z16 = take(off, tc_saved_bytes(s));            // used only when the caller passes no `saved` buffer
   L.total = align_up(off, 1024);
   return L;
 }
 size_t tc_fwd_ws_bytes(const BdgcnShape& s) { return fwd_layout(s).total; }
 static int dw_slices(const BdgcnShape& s, int* kb_per_slice, int* kb_total) {
-  const int kbps = ceil_div((long long)n2(s), 64);
+  const int kbps = ceil_div((long long)rn(s), 64);
   const int total = s.B * kbps;
-  const int MT = ceil_div(s.K, 4);
+  const int MT = ceil_div(s.Kd, 4);
   int want = device_sm_count() / MT;
   if (want < 1) want = 1;
   int per = ceil_div(total, want);
@@ -150,15 +156,15 @@ static int dw_slices(const BdgcnShape& s, int* kb_per_slice, int* kb_total) {
 static BwdLayout bwd_layout(const BdgcnShape& s) {
   BwdLayout L;
   size_t off = 0;
-  L.dp16 = take(off, (size_t)s.B * n2(s) * 32 * 2);
-  L.gd16 = take(off, g16_elems(s) * 2);
-  L.go16 = take(off, g16_elems(s) * 2);
-  L.v16 = take(off, (size_t)s.B * s.K * n2(s) * 32 * 2);
-  L.y16 = take(off, (size_t)s.B * s.K * n2(s) * 32 * 2);
-  L.wq16 = take(off, (size_t)s.K * s.K * 32 * 32 * 2);
+  L.dp16 = take(off, (size_t)s.B * s.N * s.N * 32 * 2);        // dPre: every origin row m, always
+  L.gd16 = take(off, g16_elems(s, s.Kd) * 2);
+  L.go16 = take(off, g16_elems(s, s.Ko) * 2);
+  L.v16 = take(off, (size_t)s.B * s.Ko * rn(s) * 32 * 2);
+  L.y16 = take(off, (size_t)s.B * s.Kd * rn(s) * 32 * 2);
+  L.wq16 = take(off, (size_t)s.Ko * s.Kd * 32 * 32 * 2);
   int per = 1, total = 1;
   const int slices = dw_slices(s, &per, &total);
-  L.partials = take(off, (size_t)slices * ceil_div(s.K, 4) * 128 * s.K * 32 * 4);
+  L.partials = take(off, (size_t)slices * ceil_div(s.Kd, 4) * 128 * s.Ko * 32 * 4);
   L.scale = take(off, 64);
   L.total = align_up(off, 1024);
   return L;
@@ -193,165 +199,205 @@ long long tc_debug_offset(const BdgcnShape& s, int which) {
 }
 
 // ---------------------------------------------------------------------------------------
-// individual contractions
+// individual contractions.  Activations are [B][*][R rows n][N][32] slabs (R = N for a whole layer); supports G_d has Kd
+// planes per sample, G_o has Ko.
 // ---------------------------------------------------------------------------------------
 // FWD_A:  Z16[b][d][n][e][l] = sum_c G_d[c][e] X16[b][n][c][l]
 static int run_fwd_a(const BdgcnShape& s, const __half* gd16, const __half* x16, __half* z16, const float* delta_d, cudaStream_t st) {
-  const int N = s.N, K = s.K, Np = pad8(N);
+  const int N = s.N, R = s.R, K = s.Kd, Np = pad8(N);
   GemmParams p;
   init_params(p);
-  if (int e = map_support_mn(&p.a_map, gd16, N, Np, N, (long long)(s.dynamic ? s.B : 1) * K)) return e;
-  if (int e = map_chunks(&p.b_map, x16, N, 32, N, (long long)N * 32, s.B, (long long)N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
+  if (int e = map_support_mn(&p.a_map, gd16, N, Np, N, (long long)g_planes(s, K))) return e;
+  if (int e = map_chunks(&p.b_map, x16, N, 32, R, (long long)N * 32, s.B, (long long)R * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
   p.am = omap(1, s.dynamic ? kBig : K, 1, 0, 0);        // z = b*K + d -> support index
   p.bm = omap(K, kBig, 1, 0, 0);                        // -> b
-  p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B * K; p.R = 8;
+  p.MT = ceil_div(N, 128); p.NT = ceil_div(R, 8); p.Z = s.B * K; p.R = 8;
+  p.z_inner = K;                                        // the K supports of one (sample, row block) run back to back: X16 block from L2
   p.kb_total = p.kb_per_seg = ceil_div(N, 64);
   p.ep.out = z16; p.ep.out_f16 = 1;
-  p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
-  p.ep.m_valid = N; p.ep.r_valid = N;
+  p.ep.sZ = (long long)R * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
+  p.ep.m_valid = N; p.ep.r_valid = R;
   // Z[b,d,n,e,:] += (G_d[e,e] - fp16(G_d[e,e])) * X16[b,n,e,:]
   p.ep.corr_src = x16; p.ep.corr_delta = delta_d; p.ep.corr_nseg = 1;
-  p.ep.cZ = (long long)N * N * 32; p.ep.cI = 32; p.ep.cR = (long long)N * 32; p.ep.cSeg = 0;
-  prof_set_next(PROF_FWD_A, 2.0 * s.B * K * (double)N * N * N * 32);
+  p.ep.cZ = (long long)R * N * 32; p.ep.cI = 32; p.ep.cR = (long long)N * 32; p.ep.cSeg = 0;
+  prof_set_next(PROF_FWD_A, 2.0 * s.B * K * (double)R * N * N * 32);
   return launch_big(tc::A_MN128, p, N, st);
 }
 
-// MIX: D16[b][r][row][32] = sum_{seg} A16[b][seg][row][32] * Wm16[r][(seg,32)][32]   (both channel mixes)
-static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, int w_halves, __half* d16, int tag, cudaStream_t st) {
-  const int K = s.K;
-  const long long NN = (long long)s.N * s.N;
+// MIX: D16[b][r][row][32] = sum_{seg < Kin} A16[b][seg][row][32] * Wm16[r][(seg,32)][32], r < Kout   (both channel mixes)
+static int run_mix(const BdgcnShape& s, const __half* a16, const __half* w16, int w_halves, __half* d16, int tag, int Kin, int Kout,
+                   cudaStream_t st) {
+  const long long NN = (long long)rn(s);
   GemmParams p;
   init_params(p);
   static int mode = -1;     // A/B knob: 0 default, 1 = W streams with A (one plane per k-block), 2 = W resident, one plane per k-block
   if (mode < 0) { const char* e = getenv("MPGCN_B200_MIX_MODE"); mode = e ? atoi(e) : 0; }
-  const size_t w_bytes = (size_t)K * w_halves * K * 32 * 64;      // K * w_halves tiles of K chunks x [32 k][64 B]
+  const size_t w_bytes = (size_t)Kout * w_halves * Kin * 32 * 64;      // Kin * w_halves tiles of Kout chunks x [32 k][64 B]
   int bk = 32;
-  if (mode == 0 && (K == 2 || K == 3)) {
-    // One k-block per tile: a single TMA box brings the K planes of a 128-cell tile (the single-thread producer / MMA loops
+  if (mode == 0 && (Kin == 2 || Kin == 3)) {
+    // One k-block per tile: a single TMA box brings the Kin planes of a 128-cell tile (the single-thread producer / MMA loops
     // cost ~0.3 us per k-block, which bounded the per-plane version at a third of the HBM rate), W resident in shared memory
-    bk = 32 * K;
-    if (int e = map_planes(&p.a_map, a16, NN, (long long)s.B * K, K)) return e;
-    if (int e = map_chunks(&p.b_map, w16, (long long)K * 32, 32, K, (long long)K * 32 * 32, w_halves, (long long)K * K * 32 * 32, bk, K)) return e;
-    p.am = omap(1, kBig, K, 0, 0);                 // z = b -> first plane b*K
+    bk = 32 * Kin;
+    if (int e = map_planes(&p.a_map, a16, NN, (long long)s.B * Kin, Kin)) return e;
+    if (int e = map_chunks(&p.b_map, w16, (long long)Kin * 32, 32, Kout, (long long)Kin * 32 * 32, w_halves, (long long)Kout * Kin * 32 * 32, bk, Kout)) return e;
+    p.am = omap(1, kBig, Kin, 0, 0);               // z = b -> first plane b*Kin
     p.bm = omap(1, 1, 0, 1, 0);                    // resident tile index = weight half
     p.kb_total = 1; p.kb_per_seg = 1; p.b_res_reps = w_halves;
   } else {
-    if (int e = map_planes(&p.a_map, a16, NN, (long long)s.B * K)) return e;
-    if (int e = map_chunks(&p.b_map, w16, (long long)K * 32, 32, K, (long long)K * 32 * 32, w_halves, (long long)K * K * 32 * 32, 32, K)) return e;
-    // segment s: plane = b*K + (s % K); weight rows (s % K)*32 of half s / K  (half 0 = fp16(W), half 1 = fp16(W - half 0))
-    p.am = omap(1, kBig, K, 1, 0, K, 0);
-    p.bm = omap(1, 1, 0, 0, 32, K, 1);
-    if (mode == 1 || w_bytes > 160 * 1024) { p.kb_total = K * w_halves; p.kb_per_seg = 1; }      // large K: W streams with A
-    else { p.kb_total = K; p.kb_per_seg = 1; p.b_res_reps = w_halves; }                           // W resident, A plane by plane
+    if (int e = map_planes(&p.a_map, a16, NN, (long long)s.B * Kin)) return e;
+    if (int e = map_chunks(&p.b_map, w16, (long long)Kin * 32, 32, Kout, (long long)Kin * 32 * 32, w_halves, (long long)Kout * Kin * 32 * 32, 32, Kout)) return e;
+    // segment s: plane = b*Kin + (s % Kin); weight rows (s % Kin)*32 of half s / Kin  (half 0 = fp16(W), half 1 = fp16(W - half 0))
+    p.am = omap(1, kBig, Kin, 1, 0, Kin, 0);
+    p.bm = omap(1, 1, 0, 0, 32, Kin, 1);
+    if (mode == 1 || w_bytes > 160 * 1024) { p.kb_total = Kin * w_halves; p.kb_per_seg = 1; }      // large K: W streams with A
+    else { p.kb_total = Kin; p.kb_per_seg = 1; p.b_res_reps = w_halves; }                           // W resident, A plane by plane
   }
-  p.MT = ceil_div(NN, 128); p.NT = 1; p.Z = s.B; p.R = K;
+  p.MT = ceil_div(NN, 128); p.NT = 1; p.Z = s.B; p.R = Kout;
   p.ep.out = d16; p.ep.out_f16 = 1;
-  p.ep.sZ = (long long)K * NN * 32; p.ep.sI = 32; p.ep.sR = NN * 32;
-  p.ep.m_valid = (int)NN; p.ep.r_valid = K;
-  prof_set_next(tag, 2.0 * s.B * (double)K * K * NN * 32 * 32);   // algorithmic flops (the fp16 hi/lo weight split doubles the executed MMAs)
+  p.ep.sZ = (long long)Kout * NN * 32; p.ep.sI = 32; p.ep.sR = NN * 32;
+  p.ep.m_valid = (int)NN; p.ep.r_valid = Kout;
+  prof_set_next(tag, 2.0 * s.B * (double)Kin * Kout * NN * 32 * 32);   // algorithmic flops (the fp16 hi/lo weight split doubles the executed MMAs)
   return tc::launch_contract(tc::A_K64, bk, p, st);
 }
 
-// FWD_B: out[b][m][e][h] = act( sum_{(o,n)} Gflat[(o,n)][m] U16[b][(o,n)][e][h] + bias[h] )
+// FWD_B: out[b][m][e][h] = act( sum_{(o,n)} G_o[row0 + n][m] U16[b][o][n][e][h] + bias[h] )      n < R, every m < N
 static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16, const float* bias, float* out, __half* out16,
                      const float* delta_o, cudaStream_t st) {
-  const int N = s.N, K = s.K, Np = pad8(N);
+  const int N = s.N, R = s.R, K = s.Ko, Np = pad8(N);
+  const bool slab = !(R == N && s.row0 == 0);
   GemmParams p;
   init_params(p);
-  if (int e = map_support_mn(&p.a_map, go16, N, Np, (long long)K * N, s.dynamic ? s.B : 1)) return e;
-  // U16 [b][(o,n)][e][h] read as (h, k = (o,n) rows, r = e, b): dims listed with non-monotonic strides (the r stride,
-  // 64 B, is smaller than the k stride) so that ONE box (32 ch, 64 k, 4|8 r) lands in the canonical [r][k][64 B] layout
-  if (flat_b_mode() == 2 && tc::use_2cta(N)) {
-    if (int e = map_flat(&p.b_map, u16, (long long)N * 32, (long long)K * N, s.B, 64, 64)) return e;
-    p.b_flat = 2;
-  } else if (flat_b_boxes()) {
-    if (int e = map_flat(&p.b_map, u16, (long long)N * 32, (long long)K * N, s.B, 64)) return e;
-    p.b_flat = 1;
+  if (!slab) {
+    // whole layer: the contraction index (o, n) is a plain row index of the flat [K*N][N] support stack and of U16
+    if (int e = map_support_mn(&p.a_map, go16, N, Np, (long long)K * N, s.dynamic ? s.B : 1)) return e;
+    // U16 [b][(o,n)][e][h] read as (h, k = (o,n) rows, r = e, b): dims listed with non-monotonic strides (the r stride,
+    // 64 B, is smaller than the k stride) so that ONE box (32 ch, 64 k, 4|8 r) lands in the canonical [r][k][64 B] layout
+    if (flat_b_mode() == 2 && tc::use_2cta(N)) {
+      if (int e = map_flat(&p.b_map, u16, (long long)N * 32, (long long)K * N, s.B, 64, 64)) return e;
+      p.b_flat = 2;
+    } else if (flat_b_boxes()) {
+      if (int e = map_flat(&p.b_map, u16, (long long)N * 32, (long long)K * N, s.B, 64)) return e;
+      p.b_flat = 1;
+    } else {
+      if (int e = map_chunks(&p.b_map, u16, (long long)K * N, (long long)N * 32, N, 32, s.B, (long long)K * N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
+    }
+    p.am = omap(1, s.dynamic ? kBig : 1, 1, 0, 0);
+    p.bm = omap(1, kBig, 1, 0, 0);
+    p.kb_total = p.kb_per_seg = ceil_div((long long)K * N, 64);
   } else {
-    if (int e = map_chunks(&p.b_map, u16, (long long)K * N, (long long)N * 32, N, 32, s.B, (long long)K * N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
+    // origin-row slab: one k-segment per support o.  A = rows [row0, row0 + R) of G_o (k coordinate o*N + kk inside the flat
+    // stack, base pointer moved to row0); B = U16 [b][o][n < R]: TMA zero-fills rows >= R, which also cancels the rows of the
+    // NEXT slab that the last k-block of a segment reads from G.
+    const long long gplanes = s.dynamic ? s.B : 1;
+    {
+      const uint64_t dims[4] = {(uint64_t)N, (uint64_t)((long long)K * N - s.row0), (uint64_t)gplanes, 1};
+      const uint64_t str[3] = {(uint64_t)Np * 2, (uint64_t)K * N * Np * 2, (uint64_t)K * N * Np * 2 * (uint64_t)gplanes};
+      const uint32_t box[4] = {64, 64, 1, 1};
+      if (int e = make_tmap_f16(&p.a_map, go16 + (size_t)s.row0 * Np, 4, dims, str, box, TMAP_SW128)) return e;
+    }
+    if (flat_b_mode() == 2 && tc::use_2cta(N)) {
+      if (int e = map_flat(&p.b_map, u16, (long long)N * 32, R, (long long)s.B * K, 64, 64)) return e;
+      p.b_flat = 2;
+    } else if (flat_b_boxes()) {
+      if (int e = map_flat(&p.b_map, u16, (long long)N * 32, R, (long long)s.B * K, 64)) return e;
+      p.b_flat = 1;
+    } else {
+      if (int e = map_chunks(&p.b_map, u16, R, (long long)N * 32, N, 32, (long long)s.B * K, (long long)R * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
+    }
+    p.am = omap(1, s.dynamic ? kBig : 1, 1, 0, N);          // k coordinate += o * N
+    p.bm = omap(1, kBig, K, 1, 0);                          // plane = b*K + o
+    p.kb_per_seg = ceil_div(R, 64);
+    p.kb_total = K * p.kb_per_seg;
   }
-  p.am = omap(1, s.dynamic ? kBig : 1, 1, 0, 0);
-  p.bm = omap(1, kBig, 1, 0, 0);
   p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;
-  p.kb_total = p.kb_per_seg = ceil_div((long long)K * N, 64);
   p.ep.out = out; p.ep.out_f16 = 0; p.ep.out16 = out16;
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
-  p.ep.bias = bias; p.ep.relu = s.act;
-  // pre[b,m,e,:] += sum_o (G_o[m,m] - fp16(G_o[m,m])) * U16[b,o,m,e,:]
-  p.ep.corr_src = u16; p.ep.corr_delta = delta_o; p.ep.corr_nseg = K;
-  p.ep.cZ = (long long)K * N * N * 32; p.ep.cSeg = (long long)N * N * 32; p.ep.cI = (long long)N * 32; p.ep.cR = 32;
-  prof_set_next(PROF_FWD_B, 2.0 * s.B * K * (double)N * N * N * 32);
+  p.ep.bias = s.partial ? nullptr : bias; p.ep.relu = s.partial ? 0 : s.act;
+  // pre[b,m,e,:] += sum_o (G_o[m,m] - fp16(G_o[m,m])) * U16[b,o,m,e,:]   (delta_o is zero outside the slab: the row n = m of U
+  // exists only for row0 <= m < row0 + R; corr_src is moved so that row index m addresses slab row m - row0)
+  p.ep.corr_src = u16 - (long long)s.row0 * N * 32; p.ep.corr_delta = delta_o; p.ep.corr_nseg = K;
+  // (the epilogue forms the sample offset as zB * cZ with zB = b in the flat mode and b*K in the slab mode)
+  p.ep.cZ = slab ? (long long)R * N * 32 : (long long)K * R * N * 32;
+  p.ep.cSeg = (long long)R * N * 32; p.ep.cI = (long long)N * 32; p.ep.cR = 32;
+  prof_set_next(PROF_FWD_B, 2.0 * s.B * K * (double)R * N * N * 32);
   return launch_big(tc::A_MN128, p, N, st);
 }
 
-// BWD_V: V16[b][o][n][e][h] = sum_m G_o[n][m] dP16[b][m][e][h]
+// BWD_V: V16[b][o][n][e][h] = sum_m G_o[row0 + n][m] dP16[b][m][e][h]       n < R
 static int run_bwd_v(const BdgcnShape& s, const __half* go16, const __half* dp16, __half* v16, cudaStream_t st) {
-  const int N = s.N, K = s.K, Np = pad8(N);
+  const int N = s.N, R = s.R, K = s.Ko, Np = pad8(N);
   GemmParams p;
   init_params(p);
-  if (int e = map_support_k(&p.a_map, go16, N, Np, (long long)(s.dynamic ? s.B : 1) * K)) return e;
-  if (flat_b_mode() == 2 && tc::use_2cta(N)) {
+  {   // rows [row0, row0 + R) of every support plane, K-major
+    const long long nz = (long long)g_planes(s, K);
+    const uint64_t dims[4] = {(uint64_t)N, (uint64_t)R, (uint64_t)nz, 1};
+    const uint64_t str[3] = {(uint64_t)Np * 2, (uint64_t)N * Np * 2, (uint64_t)N * Np * 2 * (uint64_t)nz};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int e = make_tmap_f16(&p.a_map, go16 + (size_t)s.row0 * Np, 4, dims, str, box, TMAP_SW128)) return e;
+  }
+  if (flat_b_mode() == 2 && tc::use_2cta(R)) {
     if (int e = map_flat(&p.b_map, dp16, (long long)N * 32, N, s.B, 64, 64)) return e;
     p.b_flat = 2;
   } else if (flat_b_boxes()) {
     if (int e = map_flat(&p.b_map, dp16, (long long)N * 32, N, s.B, 64)) return e;
     p.b_flat = 1;
   } else {   // dP16 [b][m][e][h] read as (h, k = m, r = e, b), see run_fwd_b
-    if (int e = map_chunks(&p.b_map, dp16, N, (long long)N * 32, N, 32, s.B, (long long)N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
+    if (int e = map_chunks(&p.b_map, dp16, N, (long long)N * 32, N, 32, s.B, (long long)N * N * 32, 64, tc::use_2cta(R) ? 4 : 8)) return e;
   }
   p.am = omap(1, s.dynamic ? kBig : K, 1, 0, 0);        // z = b*K + o
   p.bm = omap(K, kBig, 1, 0, 0);
-  p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B * K; p.R = 8;
+  p.MT = ceil_div(R, 128); p.NT = ceil_div(N, 8); p.Z = s.B * K; p.R = 8;
+  p.z_inner = K;                                        // dP16 block of one (sample, e block) serves the K supports back to back
   p.kb_total = p.kb_per_seg = ceil_div(N, 64);
   p.ep.out = v16; p.ep.out_f16 = 1;
-  p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
-  p.ep.m_valid = N; p.ep.r_valid = N;
-  prof_set_next(PROF_BWD_V, 2.0 * s.B * K * (double)N * N * N * 32);
-  return launch_big(tc::A_K128, p, N, st);
+  p.ep.sZ = (long long)R * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
+  p.ep.m_valid = R; p.ep.r_valid = N;
+  prof_set_next(PROF_BWD_V, 2.0 * s.B * K * (double)R * N * N * 32);
+  return launch_big(tc::A_K128, p, R, st);
 }
 
 // BWD_DW: P[slice][mt][(d%4)*32+l][o][h] = sum over the slice's (b,row) range of Z16[b][d][row][l] V16[b][o][row][h]
 static int run_bwd_dw(const BdgcnShape& s, const __half* z16, const __half* v16, float* partials, int* slices_out, int* mt_out,
                       cudaStream_t st) {
-  const int K = s.K;
-  const long long NN = (long long)s.N * s.N;
+  const int Ko = s.Ko, Kd = s.Kd;
+  const long long NN = (long long)rn(s);
   GemmParams p;
   init_params(p);
-  if (int e = map_chunks(&p.a_map, z16, NN, 32, K, NN * 32, s.B, (long long)K * NN * 32, 64, 4)) return e;
-  if (int e = map_chunks(&p.b_map, v16, NN, 32, K, NN * 32, s.B, (long long)K * NN * 32, 64, K)) return e;
+  if (int e = map_chunks(&p.a_map, z16, NN, 32, Kd, NN * 32, s.B, (long long)Kd * NN * 32, 64, 4)) return e;
+  if (int e = map_chunks(&p.b_map, v16, NN, 32, Ko, NN * 32, s.B, (long long)Ko * NN * 32, 64, Ko)) return e;
   p.am = omap(1, 1, 0, 1, 0);           // z (slice) ignored; batch element = segment
   p.bm = omap(1, 1, 0, 1, 0);
   int per = 1, total = 1;
   const int slices = dw_slices(s, &per, &total);
-  p.MT = ceil_div(K, 4); p.NT = 1; p.Z = slices; p.R = K;
+  p.MT = ceil_div(Kd, 4); p.NT = 1; p.Z = slices; p.R = Ko;
   p.kb_total = total; p.kb_per_seg = ceil_div(NN, 64);
   p.split_k = 1; p.kb_per_slice = per;
   p.ep.out = partials; p.ep.out_f16 = 0;
-  p.ep.sZ = (long long)p.MT * 128 * K * 32; p.ep.sI = (long long)K * 32; p.ep.sR = 32;
-  p.ep.m_valid = p.MT * 128; p.ep.r_valid = K;
+  p.ep.sZ = (long long)p.MT * 128 * Ko * 32; p.ep.sI = (long long)Ko * 32; p.ep.sR = 32;
+  p.ep.m_valid = p.MT * 128; p.ep.r_valid = Ko;
   *slices_out = slices;
   *mt_out = p.MT;
-  prof_set_next(PROF_BWD_DW, 2.0 * s.B * (double)K * K * NN * 32 * 32);
+  prof_set_next(PROF_BWD_DW, 2.0 * s.B * (double)Ko * Kd * NN * 32 * 32);
   return tc::launch_contract(tc::A_MN64, 64, p, st);
 }
 
-// BWD_DX: dX[b][n][c][l] = sum_{d,e} G_d[c][e] Y16[b][d][n][e][l]
+// BWD_DX: dX[b][n][c][l] = sum_{d,e} G_d[c][e] Y16[b][d][n][e][l]       n < R
 static int run_bwd_dx(const BdgcnShape& s, const __half* gd16, const __half* y16, float* dX, const float* inv_scale, float* dx_absmax,
                       cudaStream_t st) {
-  const int N = s.N, K = s.K, Np = pad8(N);
+  const int N = s.N, R = s.R, K = s.Kd, Np = pad8(N);
   GemmParams p;
   init_params(p);
-  if (int e = map_support_k(&p.a_map, gd16, N, Np, (long long)(s.dynamic ? s.B : 1) * K)) return e;
-  if (int e = map_chunks(&p.b_map, y16, N, 32, N, (long long)N * 32, (long long)s.B * K, (long long)N * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
+  if (int e = map_support_k(&p.a_map, gd16, N, Np, (long long)g_planes(s, K))) return e;
+  if (int e = map_chunks(&p.b_map, y16, N, 32, R, (long long)N * 32, (long long)s.B * K, (long long)R * N * 32, 64, tc::use_2cta(N) ? 4 : 8)) return e;
   p.am = omap(1, s.dynamic ? kBig : 1, s.dynamic ? K : 0, 1, 0);   // support index = (b*K) + d
   p.bm = omap(1, kBig, K, 1, 0);                                    // plane = b*K + d
-  p.MT = ceil_div(N, 128); p.NT = ceil_div(N, 8); p.Z = s.B; p.R = 8;
+  p.MT = ceil_div(N, 128); p.NT = ceil_div(R, 8); p.Z = s.B; p.R = 8;
   p.kb_per_seg = ceil_div(N, 64); p.kb_total = K * p.kb_per_seg;
   p.ep.out = dX; p.ep.out_f16 = 0; p.ep.alpha_dev = inv_scale; p.ep.absmax_out = dx_absmax;
-  p.ep.sZ = (long long)N * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
-  p.ep.m_valid = N; p.ep.r_valid = N;
-  prof_set_next(PROF_BWD_DX, 2.0 * s.B * K * (double)N * N * N * 32);
+  p.ep.sZ = (long long)R * N * 32; p.ep.sI = 32; p.ep.sR = (long long)N * 32;
+  p.ep.m_valid = N; p.ep.r_valid = R;
+  prof_set_next(PROF_BWD_DX, 2.0 * s.B * K * (double)R * N * N * 32);
   return launch_big(tc::A_K128, p, N, st);
 }
 
@@ -370,9 +416,9 @@ int bdgcn_prepare_supports(const float* G, void* prepared, long long planes, int
 // resolves the fp16 supports (and, for the forward, the diagonal remainders) of one side: prepared by the caller, shared
 // with the other side (static graph: Go == Gd), or converted here into the workspace
 struct SideG { const __half* g16; const float* delta; };
-static int resolve_side(const BdgcnShape& s, const float* G, const void* prepared, __half* ws16, float* ws_delta, bool want_delta,
+static int resolve_side(const BdgcnShape& s, int K, const float* G, const void* prepared, __half* ws16, float* ws_delta, bool want_delta,
                         SideG* out, cudaStream_t st) {
-  const long long planes = (long long)(s.dynamic ? s.B : 1) * s.K;
+  const long long planes = (long long)g_planes(s, K);
   if (prepared) {
     MPGCN_CHECK((reinterpret_cast<uintptr_t>(prepared) & 255) == 0, "prepared-supports buffer must be 256-byte aligned");
     out->g16 = static_cast<const __half*>(prepared);
@@ -391,8 +437,8 @@ static int resolve_side(const BdgcnShape& s, const float* G, const void* prepare
 // ---------------------------------------------------------------------------------------
 int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const float* Gd, const float* W, const float* bias,
                      float* out, void* saved, void* ws, size_t ws_bytes, const BdgcnExtras& ex, cudaStream_t st) {
-  MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d K=%d)", s.C, s.H, s.K);
-  const size_t NN = n2(s);
+  MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d Ko=%d Kd=%d)", s.C, s.H, s.Ko, s.Kd);
+  const size_t NN = rn(s);
   const FwdLayout L = fwd_layout(s);
   MPGCN_CHECK(ws_bytes >= L.total, "bdgcn_forward: workspace too small (%zu < %zu bytes)", ws_bytes, L.total);
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
@@ -412,26 +458,33 @@ int bdgcn_forward_tc(const BdgcnShape& s, const float* X, const float* Go, const
     x16 = x16_ws;
   }
   SideG gd{}, go{};
-  if (int e = resolve_side(s, Gd, ex.gd_prepared, reinterpret_cast<__half*>(wb + L.gd16), reinterpret_cast<float*>(wb + L.dd), true, &gd, st)) return e;
-  if (Go == Gd && ex.go_prepared == nullptr) go = gd;
-  else if (int e = resolve_side(s, Go, ex.go_prepared, reinterpret_cast<__half*>(wb + L.go16), reinterpret_cast<float*>(wb + L.dgo), true, &go, st)) return e;
-  const size_t wn = (size_t)s.K * s.K * 32 * 32;
+  if (int e = resolve_side(s, s.Kd, Gd, ex.gd_prepared, reinterpret_cast<__half*>(wb + L.gd16), reinterpret_cast<float*>(wb + L.dd), true, &gd, st)) return e;
+  if (Go == Gd && ex.go_prepared == nullptr && s.Ko == s.Kd) go = gd;
+  else if (int e = resolve_side(s, s.Ko, Go, ex.go_prepared, reinterpret_cast<__half*>(wb + L.go16), reinterpret_cast<float*>(wb + L.dgo), true, &go, st)) return e;
+  const float* delta_o = go.delta;
+  if (!(s.R == s.N && s.row0 == 0)) {     // the origin-side remainder applies to the rows n = m of this slab only
+    float* masked = reinterpret_cast<float*>(wb + L.dgo_masked);
+    if (int e = mask_delta_rows(go.delta, masked, g_planes(s, s.Ko), s.N, s.row0, s.R, st)) return e;
+    delta_o = masked;
+  }
+  const size_t wn = (size_t)s.Ko * s.Kd * 32 * 32;
   if (int e = cvt_f32_to_f16_hilo(W, w16, w16 + wn, wn, st)) return e;
   if (int e = run_fwd_a(s, gd.g16, x16, z16, gd.delta, st)) return e;
-  if (int e = run_mix(s, z16, w16, 2, u16, PROF_FWD_MIX, st)) return e;
-  if (int e = run_fwd_b(s, go.g16, u16, bias, out, static_cast<__half*>(ex.out_f16), go.delta, st)) return e;
+  if (int e = run_mix(s, z16, w16, 2, u16, PROF_FWD_MIX, s.Kd, s.Ko, st)) return e;
+  if (int e = run_fwd_b(s, go.g16, u16, bias, out, static_cast<__half*>(ex.out_f16), delta_o, st)) return e;
   return 0;
 }
 
 int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out, const float* Go, const float* Gd, const float* W,
                       const void* saved, float* dX, float* dW, float* db, void* ws, size_t ws_bytes, const BdgcnExtras& ex,
                       cudaStream_t st) {
-  MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d K=%d)", s.C, s.H, s.K);
+  MPGCN_CHECK(tc_supported(s), "tensor-core path needs C = H = 32 and K <= 8 (got C=%d H=%d Ko=%d Kd=%d)", s.C, s.H, s.Ko, s.Kd);
   MPGCN_CHECK(saved != nullptr, "bdgcn_backward: forward was run without a `saved` buffer");
-  MPGCN_CHECK(out != nullptr || ex.out_f16 != nullptr || !s.act, "bdgcn_backward: the ReLU mask needs `out` or its fp16 copy");
+  const int act = s.partial ? 0 : s.act;       // a partial call receives dPre: the mask was applied by the caller, after the exchange
+  MPGCN_CHECK(out != nullptr || ex.out_f16 != nullptr || !act, "bdgcn_backward: the ReLU mask needs `out` or its fp16 copy");
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(dX) & 31) == 0, "bdgcn_backward: dX must be 32-byte aligned (256-bit stores)");
   MPGCN_CHECK(((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "bdgcn_backward: d_out / out must be 16-byte aligned");
-  const size_t NN = n2(s);
+  const size_t NNfull = (size_t)s.N * s.N;
   const __half* z16 = static_cast<const __half*>(saved);
   const BwdLayout L = bwd_layout(s);
   MPGCN_CHECK(ws_bytes >= L.total, "bdgcn_backward: workspace too small (%zu < %zu bytes)", ws_bytes, L.total);
@@ -445,26 +498,27 @@ int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out,
   float* scale2 = reinterpret_cast<float*>(wb + L.scale);   // [S, 1/S]: power-of-two gradient scale (fp16 range)
 
   if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 32, st));
-  if (int e = grad_scale_prepare(d_out, (size_t)s.B * NN * 32, scale2, ex.d_out_absmax, st)) return e;
-  if (ex.out_f16 != nullptr) {
-    if (int e = relu_bwd_prep_f16mask(d_out, static_cast<const __half*>(ex.out_f16), s.act, dp16, db, (size_t)s.B * NN * 32, 32, scale2, st)) return e;
+  if (int e = grad_scale_prepare(d_out, (size_t)s.B * NNfull * 32, scale2, ex.d_out_absmax, st)) return e;
+  if (ex.out_f16 != nullptr && act) {
+    if (int e = relu_bwd_prep_f16mask(d_out, static_cast<const __half*>(ex.out_f16), act, dp16, db, (size_t)s.B * NNfull * 32, 32, scale2, st)) return e;
   } else {
-    if (int e = relu_bwd_prep(d_out, out, s.act, dp16, nullptr, db, (size_t)s.B * NN * 32, 32, scale2, st)) return e;
+    if (int e = relu_bwd_prep(d_out, out, act, dp16, nullptr, db, (size_t)s.B * NNfull * 32, 32, scale2, st)) return e;
   }
   SideG gd{}, go{};
-  if (dX || Go == Gd) {
-    if (int e = resolve_side(s, Gd, ex.gd_prepared, reinterpret_cast<__half*>(wb + L.gd16), nullptr, false, &gd, st)) return e;
+  const bool shared = Go == Gd && s.Ko == s.Kd;
+  if (dX || shared) {
+    if (int e = resolve_side(s, s.Kd, Gd, ex.gd_prepared, reinterpret_cast<__half*>(wb + L.gd16), nullptr, false, &gd, st)) return e;
   }
-  if (Go == Gd && ex.go_prepared == nullptr) go = gd;
-  else if (int e = resolve_side(s, Go, ex.go_prepared, reinterpret_cast<__half*>(wb + L.go16), nullptr, false, &go, st)) return e;
+  if (shared && ex.go_prepared == nullptr) go = gd;
+  else if (int e = resolve_side(s, s.Ko, Go, ex.go_prepared, reinterpret_cast<__half*>(wb + L.go16), nullptr, false, &go, st)) return e;
   if (int e = run_bwd_v(s, go.g16, dp16, v16, st)) return e;
   int slices = 0, mt = 0;
   if (int e = run_bwd_dw(s, z16, v16, partials, &slices, &mt, st)) return e;
-  if (int e = reduce_dw_partials(partials, dW, slices, mt, s.K, scale2 + 1, st)) return e;
+  if (int e = reduce_dw_partials(partials, dW, slices, mt, s.Ko, s.Kd, scale2 + 1, st)) return e;
   if (dX) {
     if (ex.dx_absmax) MPGCN_CUDA(cudaMemsetAsync(ex.dx_absmax, 0, sizeof(float), st));
-    if (int e = permute_w_bwd(W, wq16, nullptr, s.K, 32, 32, st)) return e;
-    if (int e = run_mix(s, v16, wq16, 1, y16, PROF_BWD_MIX, st)) return e;
+    if (int e = permute_w_bwd(W, wq16, nullptr, s.Ko, s.Kd, 32, 32, st)) return e;
+    if (int e = run_mix(s, v16, wq16, 1, y16, PROF_BWD_MIX, s.Ko, s.Kd, st)) return e;
     if (int e = run_bwd_dx(s, gd.g16, y16, dX, scale2 + 1, ex.dx_absmax, st)) return e;
   }
   return 0;

@@ -53,10 +53,14 @@ int relu_bwd_prep_f16mask(const float* d_out, const __half* out16, int relu, __h
 // fp16 has 5 exponent bits: realistic gradients (MSE mean over B*N*N cells ~ 1e-7) must be rescaled before the cast.
 // absmax_hint: optional device scalar already holding max|d_out| (produced by the epilogue that wrote d_out): skips the pass
 int grad_scale_prepare(const float* d_out, size_t n, float* scale2, const float* absmax_hint, cudaStream_t s);
-// W[o][d][l][h] fp32 -> Wq[d][o][h][l] (fp16 and/or fp32)
-int permute_w_bwd(const float* W, __half* wq16, float* wq32, int K, int C, int H, cudaStream_t s);
-// dW[o][d][l][h] = sum_slices P[slice][mt][(d%4)*32 + l][o][h]   (C = H = 32)
-int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int K, const float* inv_scale, cudaStream_t s);
+// W[o][d][l][h] fp32 (o < Ko, d < Kd) -> Wq[d][o][h][l] (fp16 and/or fp32)
+int permute_w_bwd(const float* W, __half* wq16, float* wq32, int Ko, int Kd, int C, int H, cudaStream_t s);
+// dW[o][d][l][h] = sum_slices P[slice][mt][(d%4)*32 + l][o][h]   (C = H = 32; o < Ko, d < Kd)
+int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int Ko, int Kd, const float* inv_scale, cudaStream_t s);
+// out[p][i] = (row0 <= i < row0 + rows) ? delta[p][i] : 0   (diagonal remainders restricted to an origin-row slab)
+int mask_delta_rows(const float* delta, float* out, size_t planes, int N, int row0, int rows, cudaStream_t s);
+// x[i] = act(x[i] + bias[i % H]) in place (bias nullable; act 0 none / 1 ReLU): the epilogue a partial layer call leaves out
+int bias_act_inplace(float* x, const float* bias, int act, size_t n, int H, cudaStream_t s);
 
 // ---- per-cell LSTM, last hidden state (lstm_kernels.cu) ------------------------------------
 int lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,
@@ -97,6 +101,13 @@ struct BdgcnShape {
   int B, N, K, C, H;
   int dynamic;      // supports are per-sample [B,K,N,N] pairs
   int act;          // 0 none, 1 relu
+  // Which PART of the layer this call evaluates (multi-GPU shards); a whole layer has
+  // R = N, row0 = 0, Ko = Kd = K, partial = 0.
+  int R, row0;      // origin rows n in [row0, row0 + R) are present: X / Z / U / V / Y / dX are [B, R, N, *] slabs
+  int Ko, Kd;       // supports in G_o / in G_d; W is the [Ko*Kd*C, H] slice in (o, d, l) row order
+  int partial;      // forward writes the raw partial pre-activation sum_{o, n in slab} ... (no bias, no activation);
+                    // backward receives dPre (already masked) instead of dOut
+  bool whole() const { return R == N && row0 == 0 && Ko == K && Kd == K && !partial; }
 };
 enum Precision { PREC_FP32_SIMT = 0, PREC_FP16_TC = 1 };
 

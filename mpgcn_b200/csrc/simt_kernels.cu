@@ -412,48 +412,90 @@ int grad_scale_prepare(const float* d_out, size_t n, float* scale2, const float*
   return 0;
 }
 
-__global__ void permute_w_bwd_kernel(const float* __restrict__ W, __half* __restrict__ q16, float* __restrict__ q32, int K, int C, int H) {
-  const int total = K * K * C * H;
+__global__ void permute_w_bwd_kernel(const float* __restrict__ W, __half* __restrict__ q16, float* __restrict__ q32, int Ko, int Kd, int C,
+                                     int H) {
+  const int total = Ko * Kd * C * H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    // destination index i = ((d*K + o)*H + h)*C + l
+    // destination index i = ((d*Ko + o)*H + h)*C + l
     const int l = i % C;
     const int h = (i / C) % H;
-    const int o = (i / (C * H)) % K;
-    const int d = i / (C * H * K);
-    const float v = W[((size_t)(o * K + d) * C + l) * H + h];
+    const int o = (i / (C * H)) % Ko;
+    const int d = i / (C * H * Ko);
+    const float v = W[((size_t)(o * Kd + d) * C + l) * H + h];
     if (q16) q16[i] = f2h_sat(v);
     if (q32) q32[i] = v;
   }
 }
 
-int permute_w_bwd(const float* W, __half* wq16, float* wq32, int K, int C, int H, cudaStream_t s) {
+int permute_w_bwd(const float* W, __half* wq16, float* wq32, int Ko, int Kd, int C, int H, cudaStream_t s) {
   prof_count(PROF_ELEMENTWISE);
-  permute_w_bwd_kernel<<<grid_for((size_t)K * K * C * H, 256), 256, 0, s>>>(W, wq16, wq32, K, C, H);
+  permute_w_bwd_kernel<<<grid_for((size_t)Ko * Kd * C * H, 256), 256, 0, s>>>(W, wq16, wq32, Ko, Kd, C, H);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }
 
-__global__ void reduce_dw_kernel(const float* __restrict__ P, float* __restrict__ dW, int slices, int MT, int K,
+__global__ void reduce_dw_kernel(const float* __restrict__ P, float* __restrict__ dW, int slices, int MT, int Ko, int Kd,
                                  const float* __restrict__ inv_scale) {
   const float a = inv_scale ? __ldg(inv_scale) : 1.f;
-  // dW index i = ((o*K + d)*32 + l)*32 + h ; partial row = (d%4)*32 + l of m-tile d/4
-  const int total = K * K * 32 * 32;
+  // dW index i = ((o*Kd + d)*32 + l)*32 + h ; partial row = (d%4)*32 + l of m-tile d/4
+  const int total = Ko * Kd * 32 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int h = i % 32;
     const int l = (i / 32) % 32;
-    const int d = (i / 1024) % K;
-    const int o = i / (1024 * K);
+    const int d = (i / 1024) % Kd;
+    const int o = i / (1024 * Kd);
     const int mt = d / 4;
     const size_t row = (size_t)mt * 128 + (d % 4) * 32 + l;
     float sum = 0.f;
-    for (int s = 0; s < slices; ++s) sum += P[(((size_t)s * MT * 128 + row) * K + o) * 32 + h];
+    for (int s = 0; s < slices; ++s) sum += P[(((size_t)s * MT * 128 + row) * Ko + o) * 32 + h];
     dW[i] = sum * a;
   }
 }
 
-int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int K, const float* inv_scale, cudaStream_t s) {
+int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int Ko, int Kd, const float* inv_scale, cudaStream_t s) {
   prof_count(PROF_ELEMENTWISE);
-  reduce_dw_kernel<<<grid_for((size_t)K * K * 1024, 256), 256, 0, s>>>(P, dW, slices, MT, K, inv_scale);
+  reduce_dw_kernel<<<grid_for((size_t)Ko * Kd * 1024, 256), 256, 0, s>>>(P, dW, slices, MT, Ko, Kd, inv_scale);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void mask_delta_rows_kernel(const float* __restrict__ delta, float* __restrict__ out, size_t total, int N, int row0, int rows) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % N) - row0;
+    out[i] = (r >= 0 && r < rows) ? delta[i] : 0.f;
+  }
+}
+int mask_delta_rows(const float* delta, float* out, size_t planes, int N, int row0, int rows, cudaStream_t s) {
+  prof_count(PROF_ELEMENTWISE);
+  mask_delta_rows_kernel<<<grid_for(planes * N, 256), 256, 0, s>>>(delta, out, planes * N, N, row0, rows);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// in place: x = act(x + bias[channel]); H % 4 == 0 and 16-byte alignment take the float4 path
+__global__ void bias_act_vec4_kernel(float4* __restrict__ x, const float* __restrict__ bias, int act, size_t n4, int H4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    if (bias) {
+      const float4 b = reinterpret_cast<const float4*>(bias)[i % H4];
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (act) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    x[i] = v;
+  }
+}
+__global__ void bias_act_kernel(float* __restrict__ x, const float* __restrict__ bias, int act, size_t n, int H) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = x[i] + (bias ? bias[i % H] : 0.f);
+    x[i] = act ? fmaxf(v, 0.f) : v;
+  }
+}
+int bias_act_inplace(float* x, const float* bias, int act, size_t n, int H, cudaStream_t s) {
+  MPGCN_CHECK(H >= 1, "bias_act: H=%d", H);
+  prof_count(PROF_ELEMENTWISE);
+  const bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+  if (vec) bias_act_vec4_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(reinterpret_cast<float4*>(x), bias, act, n / 4, H / 4);
+  else bias_act_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, bias, act, n, H);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }

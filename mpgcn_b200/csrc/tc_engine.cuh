@@ -69,6 +69,9 @@ struct alignas(64) GemmParams {
   // through the ring with A.  Needs NT == 1, kb_per_seg == 1, no split-K, a z-independent B map.
   int b_res_reps;
   int nt_fastest;            // tile order: 0 = m-tiles vary fastest (default), 1 = n-tiles vary fastest
+  int z_inner;               // > 1: z = zo * z_inner + zi and zi varies right after the m-tiles (before the n-tiles): the z_inner
+                             // contractions that share one B block (the K supports applied to one X16 / dP16 row block) run back to
+                             // back, so that block is fetched from HBM once and then served from L2
   Epilogue ep;
 };
 
@@ -109,6 +112,28 @@ __host__ __device__ inline size_t smem_bytes(int a_stage, int R, int BK, int sta
 }
 
 #ifdef __CUDACC__
+// tile id -> (m tile, n tile, z); see GemmParams::nt_fastest / z_inner
+__device__ __forceinline__ void decode_tile(const GemmParams& p, int t, int& mt, int& nt, int& z) {
+  if (p.z_inner > 1) {
+    mt = t % p.MT;
+    int rest = t / p.MT;
+    const int zi = rest % p.z_inner;
+    rest /= p.z_inner;
+    nt = rest % p.NT;
+    z = (rest / p.NT) * p.z_inner + zi;
+  } else if (p.nt_fastest) {
+    nt = t % p.NT;
+    const int rest = t / p.NT;
+    mt = rest % p.MT;
+    z = rest / p.MT;
+  } else {
+    mt = t % p.MT;
+    const int rest = t / p.MT;
+    nt = rest % p.NT;
+    z = rest / p.NT;
+  }
+}
+
 // one 32-byte (full L2 sector) store per lane: sm_100 has 256-bit global stores (STG.256); with 16-byte stores every lane of the
 // scattered epilogue patterns (rows 64 B .. 128 KB apart) sent two half-filled sector requests instead of one full one
 __device__ __forceinline__ void st_global_256(void* ptr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
@@ -223,10 +248,8 @@ __global__ void __launch_bounds__(kThreads1, 1) contract_kernel(const __grid_con
         }
       }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int mt = t % p.MT;
-        const int rest = t / p.MT;
-        const int nt = rest % p.NT;
-        const int z = rest / p.NT;
+        int mt, nt, z;
+        decode_tile(p, t, mt, nt, z);
         const int kb0 = p.split_k ? z * p.kb_per_slice : 0;
         const int kb1 = p.split_k ? min(kb0 + p.kb_per_slice, p.kb_total) : p.kb_total;
         const int zA0 = ((z / p.am.z_div) % p.am.z_mod) * p.am.z_mul;
@@ -285,7 +308,8 @@ __global__ void __launch_bounds__(kThreads1, 1) contract_kernel(const __grid_con
       tc_fence_after();
     }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int z = (t / p.MT) / p.NT;
+      int mt_, nt_, z;
+      decode_tile(p, t, mt_, nt_, z);
       const int kb0 = p.split_k ? z * p.kb_per_slice : 0;
       const int kb1 = p.split_k ? min(kb0 + p.kb_per_slice, p.kb_total) : p.kb_total;
       mbar_wait(&tempty[acc], acc_phase ^ 1u);
@@ -324,10 +348,8 @@ __global__ void __launch_bounds__(kThreads1, 1) contract_kernel(const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int mt = t % p.MT;
-      const int rest = t / p.MT;
-      const int nt = rest % p.NT;
-      const int z = rest / p.NT;
+      int mt, nt, z;
+      decode_tile(p, t, mt, nt, z);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int i = mt * 128 + quarter * 32 + lane;
@@ -464,8 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
         int mt, nt, z;
-        if (p.nt_fastest) { nt = t % p.NT; const int rest = t / p.NT; mt = rest % p.MT; z = rest / p.MT; }
-        else { mt = t % p.MT; const int rest = t / p.MT; nt = rest % p.NT; z = rest / p.NT; }
+        decode_tile(p, t, mt, nt, z);
         const int m0 = mt * 256 + (int)rank * 128;
         const int zA0 = ((z / p.am.z_div) % p.am.z_mod) * p.am.z_mul;
         const int zB0 = ((z / p.bm.z_div) % p.bm.z_mod) * p.bm.z_mul;
@@ -552,8 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
     uint32_t acc_phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       int mt, nt, z;
-      if (p.nt_fastest) { nt = t % p.NT; const int rest = t / p.NT; mt = rest % p.MT; z = rest / p.MT; }
-      else { mt = t % p.MT; const int rest = t / p.MT; nt = rest % p.NT; z = rest / p.NT; }
+      decode_tile(p, t, mt, nt, z);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int i = mt * 256 + (int)rank * 128 + quarter * 32 + lane;

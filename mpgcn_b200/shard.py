@@ -1,0 +1,372 @@
+"""Model-parallel shards of the hot path over the GPUs of one node, one process per GPU.
+
+The reference has no distributed code; this is the B200-native addition behind the same math
+(`BDGCN.forward`, reference MPGCN.py:24-50; model glue MPGCN.py:89-112).  Both shards split ONE sample's work, so they
+scale a fixed batch ("strong" scaling) -- the batch shard of `mpgcn_b200.dist` scales the number of samples instead.
+
+origin-row shard (`kind="row"`, 8(e) row 1).  Rank j owns the origin rows n in slab_j of every activation: the LSTM, the
+    destination contraction Z = X x_2 G_d, the channel mix and the FC head are row-local.  The origin contraction sums over n,
+    so rank j produces the PARTIAL pre-activation sum_o G_o[slab_j, :]^T U_o[slab_j] for every output row m and the ranks
+    exchange it with ONE reduce-scatter over m per layer (sample by sample, so that the slabs stay in the reference's
+    [B, rows, N, C] layout); bias + ReLU (MPGCN.py:47-49) run after the exchange on the rank's own rows.  Backward: the masked
+    dPre of the rank's rows is all-gathered (same size), everything after that is local; the parameter gradients are partial
+    sums over the rank's cells and are summed once per step with the LSTM / head gradients (< 200 KB).
+K shard (`kind="k"`, 8(e) row 2, the partition north_star names).  Rank j owns the destination supports d in D_j: it
+    evaluates Z_d and U_o^(j) = sum_{d in D_j} Z_d W[o,d] for all o and the origin contraction of that partial U; ONE all-reduce
+    of the pre-activation per layer forward and of dX per layer backward.  The origin contraction (and V = G_o x_1 dPre) is
+    replicated, which bounds the speed-up by 2K / (K/g + K) < 2; the LSTM is row-sharded (its cells are
+    independent) with an all-gather of h_T, the head is replicated.
+
+All arithmetic is in libmpgcn_b200.so (`mpgcn_bdgcn_forward_part` / `_backward_part`, `mpgcn_bias_act`,
+`mpgcn_relu_backward`); torch.distributed (NCCL over NVLink / NVSwitch) moves the partial sums.  `_ENGINE` is the compute
+back end; tests swap in a CPU stand-in to run the exchange logic under gloo (tests/test_shard_gloo.py).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .dist import shard_range
+
+
+class ShardPlan:
+    """Who owns what.  kind "row": origin rows [row_lo, row_hi) (N must divide evenly: the reduce-scatter needs equal slabs);
+    kind "k": destination supports [d_lo, d_hi) (may be empty when world > K) plus the same row slab for the LSTM."""
+
+    def __init__(self, kind: str, rank: int, world: int, N: int, K: int, group=None):
+        if kind not in ("row", "k"):
+            raise ValueError(f"unknown shard kind {kind!r}")
+        if N % world != 0:
+            raise ValueError(f"the {kind} shard needs N ({N}) to be a multiple of the number of ranks ({world})")
+        self.kind, self.rank, self.world, self.N, self.K, self.group = kind, rank, world, N, K, group
+        self.row_lo, self.row_hi = shard_range(N, rank, world)
+        self.rows = self.row_hi - self.row_lo
+        self.d_lo, self.d_hi = shard_range(K, rank, world) if kind == "k" else (0, K)
+        self.Kd = self.d_hi - self.d_lo
+
+    def describe(self) -> dict:
+        d = {"kind": self.kind, "world": self.world, "rows_per_rank": self.rows,
+             "collective_per_layer": ("reduce-scatter of pre [B,N,N,H] fp32 forward, all-gather of dPre backward" if self.kind == "row"
+                                      else "all-reduce of pre [B,N,N,H] fp32 forward, all-reduce of dX backward; all-gather of h_T once per branch")}
+        if self.kind == "k":
+            d["supports_per_rank"] = [shard_range(self.K, r, self.world)[1] - shard_range(self.K, r, self.world)[0] for r in range(self.world)]
+        return d
+
+
+# ------------------------------------------------------------------------------------------------
+# compute back end (the C ABI); tests replace it by a CPU stand-in to exercise the exchange logic under gloo
+# ------------------------------------------------------------------------------------------------
+class CudaEngine:
+    def _part(self, row0, rows, Ko, Kd):
+        return _lib.BdgcnPart(row0, rows, Ko, Kd)
+
+    def forward_part(self, X, Go, Gd, dynamic, W, N, row0, Ko, Kd, prec, keep):
+        """X [B,rows,N,C] -> (raw partial pre-activation [B,N,N,H], Z stash or None)"""
+        lib = _lib.load()
+        ops._require_cuda(X, "X")
+        B, rows, _, C = X.shape
+        H = W.shape[1]
+        part = self._part(row0, rows, Ko, Kd)
+        pp = ctypes.addressof(part)
+        pre = torch.empty((B, N, N, H), dtype=torch.float32, device=X.device)
+        saved = ops._scratch(lib.mpgcn_bdgcn_part_saved_bytes(B, N, C, H, prec, pp), X.device) if keep else None
+        ws = ops._scratch(lib.mpgcn_bdgcn_part_fwd_workspace_bytes(B, N, C, H, int(dynamic), prec, pp), X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(lib.mpgcn_bdgcn_forward_part(X.data_ptr(), Go.data_ptr(), Gd.data_ptr(), int(dynamic), W.data_ptr(), pre.data_ptr(),
+                                                    ops._ptr(saved), ws.data_ptr(), ws.numel(), B, N, C, H, prec, pp, ops._stream()),
+                       "bdgcn_forward_part")
+        return pre, saved
+
+    def backward_part(self, d_pre, Go, Gd, dynamic, W, saved, N, row0, rows, Ko, Kd, C, prec, need_dx):
+        """d_pre [B,N,N,H] (every origin row, masked) -> (dX [B,rows,N,C] or None, dW [Ko*Kd*C, H])"""
+        lib = _lib.load()
+        B, H = d_pre.shape[0], d_pre.shape[-1]
+        part = self._part(row0, rows, Ko, Kd)
+        pp = ctypes.addressof(part)
+        dX = torch.empty((B, rows, N, C), dtype=torch.float32, device=d_pre.device) if need_dx else None
+        dW = torch.empty((Ko * Kd * C, H), dtype=torch.float32, device=d_pre.device)
+        ws = ops._scratch(lib.mpgcn_bdgcn_part_bwd_workspace_bytes(B, N, C, H, int(dynamic), prec, pp), d_pre.device)
+        with torch.cuda.device(d_pre.device):
+            _lib.check(lib.mpgcn_bdgcn_backward_part(d_pre.data_ptr(), Go.data_ptr(), Gd.data_ptr(), int(dynamic), W.data_ptr(), saved.data_ptr(),
+                                                     ops._ptr(dX), dW.data_ptr(), ws.data_ptr(), ws.numel(), B, N, C, H, prec, pp, None,
+                                                     ops._stream()), "bdgcn_backward_part")
+        return dX, dW
+
+    def bias_act(self, pre, bias, act):
+        """in place: pre = act(pre + bias)"""
+        lib = _lib.load()
+        with torch.cuda.device(pre.device):
+            _lib.check(lib.mpgcn_bias_act(pre.data_ptr(), ops._ptr(bias), int(act), pre.numel(), pre.shape[-1], ops._stream()), "bias_act")
+        return pre
+
+    def relu_backward(self, d_out, out, act, want_db):
+        lib = _lib.load()
+        d_pre = torch.empty_like(d_out)
+        db = torch.empty(d_out.shape[-1], dtype=torch.float32, device=d_out.device) if want_db else None
+        with torch.cuda.device(d_out.device):
+            _lib.check(lib.mpgcn_relu_backward(d_out.data_ptr(), out.data_ptr(), int(act), d_pre.data_ptr(), ops._ptr(db), d_out.numel(),
+                                               d_out.shape[-1], ops._stream()), "relu_backward")
+        return d_pre, db
+
+    def lstm_last(self, x_seq, lstm, precision):
+        return ops.lstm_last(x_seq, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0, precision=precision)
+
+    def head(self, feats, w, b):
+        return ops.fc_relu_mean(feats, w, b)
+
+    def resolve_precision(self, name, B, N, K, C, H):
+        return ops.resolve_precision(name, B, N, K, C, H)
+
+
+_ENGINE = CudaEngine()
+
+
+# ------------------------------------------------------------------------------------------------
+# exchange steps
+# ------------------------------------------------------------------------------------------------
+def _backend(group=None) -> str:
+    return dist.get_backend(group)
+
+
+def reduce_scatter_rows(partial: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
+    """partial [B, N(m), N, H] (this rank's partial sum for every origin row m) -> [B, rows, N, H]: the sum over the ranks of the
+    rows this rank owns.  One collective per sample keeps the slab in [B, rows, ...] layout with no transpose pass."""
+    B = partial.shape[0]
+    out = partial.new_empty((B, plan.rows) + tuple(partial.shape[2:]))
+    if _backend(plan.group) == "nccl":
+        works = [dist.reduce_scatter_tensor(out[b], partial[b], group=plan.group, async_op=True) for b in range(B)]
+        for w in works:
+            w.wait()
+    else:   # gloo (CPU tests) has no reduce-scatter: all-reduce, keep the own rows
+        dist.all_reduce(partial, group=plan.group)
+        out.copy_(partial[:, plan.row_lo:plan.row_hi])
+    return out
+
+
+def all_gather_rows(slab: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
+    """slab [B, rows, N, H] -> [B, N, N, H] (rank r's rows at r*rows ..)"""
+    B = slab.shape[0]
+    full = slab.new_empty((B, plan.N) + tuple(slab.shape[2:]))
+    slab = slab.contiguous()
+    if _backend(plan.group) == "nccl":
+        works = [dist.all_gather_into_tensor(full[b], slab[b], group=plan.group, async_op=True) for b in range(B)]
+        for w in works:
+            w.wait()
+    else:
+        parts = [torch.empty_like(slab) for _ in range(plan.world)]
+        dist.all_gather(parts, slab, group=plan.group)
+        for r, p in enumerate(parts):
+            full[:, r * plan.rows:(r + 1) * plan.rows] = p
+    return full
+
+
+class _AllGatherRowsFn(torch.autograd.Function):
+    """forward: all-gather the row slabs; backward: the incoming gradient is already complete on every rank (it comes out of an
+    all-reduce), so each rank keeps the rows it owns."""
+
+    @staticmethod
+    def forward(ctx, slab, plan):
+        ctx.plan = plan
+        return all_gather_rows(slab, plan)
+
+    @staticmethod
+    def backward(ctx, d_full):
+        p = ctx.plan
+        return d_full[:, p.row_lo:p.row_hi].contiguous(), None
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded BDGCN layers
+# ------------------------------------------------------------------------------------------------
+def _f32c(t):
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+class _RowShardLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, G_o, G_d, W, b, dynamic, act, precision, plan, grad_mode):
+        B, rows, N, C = X.shape
+        K, H = G_o.shape[-3], W.shape[1]
+        prec = _ENGINE.resolve_precision(precision, B, N, K, C, H)
+        Xc, Goc, Wc = _f32c(X), _f32c(G_o), _f32c(W)
+        Gdc = Goc if G_d is G_o else _f32c(G_d)
+        keep = grad_mode and any(ctx.needs_input_grad)
+        partial, saved = _ENGINE.forward_part(Xc, Goc, Gdc, dynamic, Wc, N, plan.row_lo, K, K, prec, keep)
+        out = reduce_scatter_rows(partial, plan)                 # the ONE exchange step of the layer forward
+        del partial
+        _ENGINE.bias_act(out, None if b is None else _f32c(b), act)
+        ctx.meta = (dynamic, act, prec, b is not None, N, K, C)
+        ctx.plan = plan
+        ctx.save_for_backward(out, Goc, Gdc, Wc, saved if saved is not None else torch.empty(0, device=X.device))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        out, Goc, Gdc, Wc, saved = ctx.saved_tensors
+        dynamic, act, prec, has_bias, N, K, C = ctx.meta
+        plan = ctx.plan
+        if saved.numel() == 0:
+            raise RuntimeError("mpgcn_b200.shard: backward called but forward ran without requires_grad inputs")
+        d_pre_slab, db = _ENGINE.relu_backward(_f32c(d_out), out, act, has_bias)       # mask + bias gradient of the rank's own rows
+        d_pre = all_gather_rows(d_pre_slab, plan)                                      # the ONE exchange step of the layer backward
+        dX, dW = _ENGINE.backward_part(d_pre, Goc, Gdc, dynamic, Wc, saved, N, plan.row_lo, plan.rows, K, K, C, prec, ctx.needs_input_grad[0])
+        return dX, None, None, dW, db, None, None, None, None, None
+
+
+class _KShardLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, G_o, G_d_local, W, b, dynamic, act, precision, plan, grad_mode):
+        B, N, _, C = X.shape
+        K, H = G_o.shape[-3], W.shape[1]
+        Kd = plan.Kd
+        prec = _ENGINE.resolve_precision(precision, B, N, K, C, H)
+        Xc, Goc = _f32c(X), _f32c(G_o)
+        keep = grad_mode and any(ctx.needs_input_grad)
+        saved = Wl = Gdc = None
+        if Kd > 0:
+            Gdc = _f32c(G_d_local)
+            Wl = W.detach().view(K, K, C, H)[:, plan.d_lo:plan.d_hi].reshape(K * Kd * C, H).to(torch.float32).contiguous()
+            pre, saved = _ENGINE.forward_part(Xc, Goc, Gdc, dynamic, Wl, N, 0, K, Kd, prec, keep)
+        else:               # more ranks than supports: this rank only takes part in the exchange
+            pre = torch.zeros((B, N, N, H), dtype=torch.float32, device=X.device)
+        dist.all_reduce(pre, group=plan.group)                   # the ONE exchange step of the layer forward
+        _ENGINE.bias_act(pre, None if b is None else _f32c(b), act)
+        ctx.meta = (dynamic, act, prec, b is not None, N, K, C, H, keep)
+        ctx.plan = plan
+        ctx.save_for_backward(pre, Goc, Gdc if Gdc is not None else torch.empty(0, device=X.device),
+                              Wl if Wl is not None else torch.empty(0, device=X.device),
+                              saved if saved is not None else torch.empty(0, device=X.device))
+        return pre
+
+    @staticmethod
+    def backward(ctx, d_out):
+        out, Goc, Gdc, Wl, saved = ctx.saved_tensors
+        dynamic, act, prec, has_bias, N, K, C, H, keep = ctx.meta
+        plan = ctx.plan
+        if not keep:
+            raise RuntimeError("mpgcn_b200.shard: backward called but forward ran without requires_grad inputs")
+        d_pre, db = _ENGINE.relu_backward(_f32c(d_out), out, act, has_bias)            # replicated: identical on every rank
+        dW = torch.zeros((K, K, C, H), dtype=torch.float32, device=d_out.device)
+        need_dx = ctx.needs_input_grad[0]
+        if plan.Kd > 0:
+            dX, dWl = _ENGINE.backward_part(d_pre, Goc, Gdc, dynamic, Wl, saved, N, 0, N, K, plan.Kd, C, prec, need_dx)
+            dW[:, plan.d_lo:plan.d_hi] = dWl.view(K, plan.Kd, C, H)
+        else:
+            dX = torch.zeros((d_out.shape[0], N, N, C), dtype=torch.float32, device=d_out.device) if need_dx else None
+        if need_dx:
+            dist.all_reduce(dX, group=plan.group)                # the ONE exchange step of the layer backward
+        if db is not None:
+            db = db / plan.world          # replicated quantity: the parameter-gradient exchange SUMS over the ranks
+        return dX, None, None, dW.view(K * K * C, H), db, None, None, None, None, None
+
+
+def sharded_bdgcn(layer, X, G, plan: ShardPlan):
+    """One BDGCN layer (mpgcn_b200.MPGCN.BDGCN: parameters W, b; activation None or ReLU) on this rank's shard.
+    row: X [B,rows,N,C] -> [B,rows,N,H];  k: X [B,N,N,C] -> [B,N,N,H] (replicated), G_d already sliced to the rank's supports."""
+    from torch import nn
+    dynamic = not isinstance(G, torch.Tensor)
+    G_o, G_d = (G if dynamic else (G, G))
+    relu = isinstance(layer.activation, nn.ReLU)
+    if layer.activation is not None and not relu:
+        raise NotImplementedError("sharded layers fuse None / ReLU only")
+    fn = _RowShardLayerFn if plan.kind == "row" else _KShardLayerFn
+    return fn.apply(X, G_o, G_d, layer.W, layer.b if layer.use_bias else None, dynamic, 1 if relu else 0, layer.precision, plan,
+                    torch.is_grad_enabled())
+
+
+# ------------------------------------------------------------------------------------------------
+# the model on a shard  (reference MPGCN.forward, MPGCN.py:89-112)
+# ------------------------------------------------------------------------------------------------
+def shard_host_inputs(plan: ShardPlan, x_seq, y_true, g_o, g_d):
+    """This rank's slices of the step inputs (host side; pinned like their sources).
+    x_seq [B,T,N,N,1] -> its origin rows (the LSTM is row-local in both shards); y [B,1,N,N,1] -> its rows (row shard; the K
+    shard's head is replicated and keeps all of y); dynamic G_o stays whole (every rank contracts over its own rows of every
+    support / over all of them); G_d [B,K,N,N] -> the rank's destination supports (K shard)."""
+    def pin(t):
+        t = t.contiguous()
+        return t.pin_memory() if torch.cuda.is_available() else t
+    lo, hi = plan.row_lo, plan.row_hi
+    x = pin(x_seq[:, :, lo:hi])
+    if plan.kind == "row":
+        return x, pin(y_true[:, :, lo:hi]), g_o, g_d
+    return x, y_true, g_o, pin(g_d[:, plan.d_lo:plan.d_hi])
+
+
+def sharded_forward(model, plan: ShardPlan, x_slab, G_static, G_dyn):
+    """model: mpgcn_b200.MPGCN.MPGCN.  x_slab [B,T,rows,N,1] (shard_host_inputs).  G_static [K,N,N] (whole, on every rank);
+    G_dyn = (G_o [B,K,N,N], G_d) with G_d whole (row shard) or the rank's slice [B,Kd,N,N] (K shard).
+    -> row shard: y of the rank's rows [B,1,rows,N,1];  K shard: the whole y [B,1,N,N,1] on every rank."""
+    assert len(model.branch_models) == 2 == model.M, "the trainer's M = 2 layout: static branch, dynamic branch"
+    B, T, rows, N, _ = x_slab.shape
+    C = model.lstm_hidden_dim
+    if plan.kind == "k":
+        G_list = [(G_static, G_static[plan.d_lo:plan.d_hi]), G_dyn]       # static supports: origin side whole, destination side sliced
+    else:
+        G_list = [G_static, G_dyn]
+    feats = []
+    for m in range(model.M):
+        branch = model.branch_models[m]
+        h = _ENGINE.lstm_last(x_slab, branch['temporal'], model.lstm_precision).reshape(B, rows, N, C)
+        g = h if plan.kind == "row" else _AllGatherRowsFn.apply(h, plan)
+        Gm = G_list[m]
+        for layer in branch['spatial']:
+            if plan.kind == "k" and isinstance(Gm, tuple) and Gm[0].dim() == 3:
+                g = _static_k_layer(layer, g, Gm, plan)
+            else:
+                g = sharded_bdgcn(layer, g, Gm, plan)
+        feats.append(g)
+    fcs = [model.branch_models[m]['fc'][0] for m in range(model.M)]
+    w = torch.cat([fc.weight for fc in fcs], dim=0)
+    b = torch.cat([fc.bias for fc in fcs], dim=0)
+    return _ENGINE.head(feats, w, b).unsqueeze(dim=1)
+
+
+def _static_k_layer(layer, X, G_pair, plan):
+    """K shard with STATIC supports: G_o = the whole [K,N,N] stack, G_d = the rank's [Kd,N,N] slice of the same stack."""
+    from torch import nn
+    relu = isinstance(layer.activation, nn.ReLU)
+    return _KShardLayerFn.apply(X, G_pair[0], G_pair[1], layer.W, layer.b if layer.use_bias else None, False, 1 if relu else 0, layer.precision,
+                                plan, torch.is_grad_enabled())
+
+
+def sharded_mse_loss(plan: ShardPlan, y_pred, y_true):
+    """nn.MSELoss(reduction='mean') (Model_Trainer.py:64,108) of the WHOLE prediction.  Row shard: each rank holds its rows; the value
+    returned is the rank's share sum((y - t)^2) / (B*N*N), whose gradients are exactly the rank's part of the global gradient
+    (sum the returned values over the ranks for the loss itself).  K shard: y is replicated, plain MSE."""
+    if plan.kind == "row":
+        total = y_pred.shape[0] * plan.N * plan.N * y_pred.shape[-1]
+        return ((y_pred - y_true) ** 2).sum() / total
+    return torch.nn.functional.mse_loss(y_pred, y_true)
+
+
+def allreduce_sum_gradients(params, plan: ShardPlan = None, model=None) -> int:
+    """ONE all-reduce (sum) of every parameter gradient on a flat buffer.  Row shard: all gradients are partial sums over the
+    rank's cells.  K shard: dW slices are disjoint (zeros elsewhere), db was pre-divided, the LSTM is row-sharded; only the
+    replicated head's gradients must be divided by the number of ranks first (pass `model`)."""
+    params = list(params)
+    if not (dist.is_available() and dist.is_initialized()) or not params:
+        return 0
+    group = plan.group if plan is not None else None
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 0
+    if plan is not None and plan.kind == "k" and model is not None:
+        for m in range(model.M):
+            for p in model.branch_models[m]['fc'].parameters():
+                if p.grad is not None:
+                    p.grad.div_(world)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return off

@@ -1,0 +1,74 @@
+"""torchrun worker of tests/test_gpu_shard.py::test_sharded_model_nccl_world2 (one rank per GPU, NCCL)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import MPGCN as shim  # noqa: E402
+from mpgcn_b200 import dist as mdist, shard  # noqa: E402
+from oracle import mpgcn_oracle as orc  # noqa: E402
+
+
+def main(kind, out_path):
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rank, world = mdist.init_from_env("nccl", device=dev)
+    N, K, T, B, hid = 260, 3 if kind == "row" else 4, 5, 2, 32
+    torch.manual_seed(0)
+    model = shim.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=hid, lstm_num_layers=1, gcn_hidden_dim=hid, gcn_num_layers=3,
+                       num_nodes=N, user_bias=True, activation=nn.ReLU).to(dev)
+    rng = np.random.default_rng(1)
+    x = torch.from_numpy((rng.random((B, T, N, N, 1)) * 6).astype(np.float32))
+    y = torch.from_numpy((rng.random((B, 1, N, N, 1)) * 2).astype(np.float32))
+    G = torch.from_numpy((rng.standard_normal((K, N, N)) / N ** 0.5).astype(np.float32)).to(dev)
+    go = torch.from_numpy((rng.standard_normal((B, K, N, N)) / N ** 0.5).astype(np.float32))
+    gd = torch.from_numpy((rng.standard_normal((B, K, N, N)) / N ** 0.5).astype(np.float32))
+    plan = shard.ShardPlan(kind, rank, world, N, K)
+    xs, ys, gos, gds = (t.to(dev) for t in shard.shard_host_inputs(plan, x, y, go, gd))
+    rows = []
+    for prec, tol_f, tol_g in (("fp32", 1e-5, 2e-4), ("fp16", 1e-3, 8e-2)):
+        model.lstm_precision = prec
+        for mod in model.modules():
+            if isinstance(mod, shim.BDGCN):
+                mod.precision = prec
+        # whole model on this GPU (fp32 engine = the yardstick for both precisions)
+        model.lstm_precision = "fp32"
+        for mod in model.modules():
+            if isinstance(mod, shim.BDGCN):
+                mod.precision = "fp32"
+        model.zero_grad(set_to_none=True)
+        pred_w = model(x_seq=x.to(dev), G_list=[G, (go.to(dev), gd.to(dev))])
+        nn.functional.mse_loss(pred_w, y.to(dev)).backward()
+        want = {k: p.grad.clone() for k, p in model.named_parameters()}
+        model.lstm_precision = prec
+        for mod in model.modules():
+            if isinstance(mod, shim.BDGCN):
+                mod.precision = prec
+        model.zero_grad(set_to_none=True)
+        pred = shard.sharded_forward(model, plan, xs, G, (gos, gds))
+        loss = shard.sharded_mse_loss(plan, pred, ys)
+        loss.backward()
+        shard.allreduce_sum_gradients(list(model.parameters()), plan, model)
+        torch.cuda.synchronize()
+        ref_pred = pred_w[:, :, plan.row_lo:plan.row_hi] if kind == "row" else pred_w
+        linf, l2 = orc.rel_errors(pred.detach().cpu().numpy(), ref_pred.detach().cpu().numpy())
+        rows.append(dict(what=f"nccl world-{world} {kind} shard {prec}: y (rank {rank})", linf=linf, l2=l2, tol=tol_f))
+        for k, p in model.named_parameters():
+            linf, l2 = orc.rel_errors(p.grad.cpu().numpy(), want[k].cpu().numpy())
+            rows.append(dict(what=f"nccl world-{world} {kind} shard {prec}: grad {k} (rank {rank})", linf=l2, l2=l2, tol=tol_g))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, rows)
+    if rank == 0:
+        json.dump({"rows": [r for part in gathered for r in part]}, open(out_path, "w"))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])

@@ -49,7 +49,7 @@ def _precisions(C, H, K):
 
 def test_library_is_the_cuda_one(cuda_device):
     lib = _lib.load()
-    assert lib.mpgcn_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.mpgcn_abi_version() == _lib.ABI_VERSION == 3
     assert torch.cuda.get_device_capability(cuda_device)[0] == 10, "tests expect a Blackwell (sm_100) device"
 
 

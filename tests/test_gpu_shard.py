@@ -1,0 +1,121 @@
+"""Layer PARTS on the GPU (`mpgcn_bdgcn_forward_part` / `_backward_part`, include/mpgcn_b200.h) -- what one rank of an origin-row
+shard or of a K shard evaluates -- against an independent float64 evaluation of the same part
+(tests/shard_standin.py), rank by rank on ONE GPU, and the parts of all ranks summed against the whole layer.  The NCCL run of the
+sharded model over 2 GPUs is `test_sharded_model_nccl_world2` (skipped on a 1-GPU box)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import abi
+from conftest import record_parity
+from oracle import mpgcn_oracle as orc
+from shard_standin import TorchEngine
+
+from mpgcn_b200 import shard
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = {"fp32": (2e-5, 1e-4), "fp16": (1e-3, 2e-3)}
+
+
+def _check(a, ref, tol, what):
+    linf, l2 = orc.rel_errors(a.detach().cpu().numpy(), ref.detach().cpu().numpy())
+    record_parity(what, linf, l2, tol)
+    assert np.isfinite(linf) and linf <= tol and l2 <= tol, f"{what}: rel_Linf={linf:.3e} rel_L2={l2:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("kind,N,world,K,dyn", [("row", 130, 2, 3, False), ("row", 256, 4, 3, True), ("row", 300, 2, 3, False),
+                                                 ("row", 1000, 8, 3, True), ("k", 130, 2, 3, True), ("k", 201, 3, 3, False),
+                                                 ("k", 300, 4, 6, False), ("k", 132, 4, 3, False)])
+def test_layer_parts_match_standin_and_sum_to_the_whole_layer(kind, N, world, K, dyn, cuda_device):
+    dev = cuda_device
+    torch.manual_seed(N + world)
+    B, C = 2 if N <= 300 else 1, 32
+    X = torch.tanh(torch.randn(B, N, N, C, device=dev))
+    mk = (lambda: torch.randn(B, K, N, N, device=dev) / N ** 0.5) if dyn else (lambda: torch.randn(K, N, N, device=dev) / N ** 0.5)
+    Go = mk()
+    Gd = mk() if dyn else Go
+    W = torch.randn(K * K * C, C, device=dev) * (2.0 / (K * K * C + C)) ** 0.5
+    bias = torch.randn(C, device=dev) * 0.1
+    d_pre = torch.randn(B, N, N, C, device=dev) * 1e-4
+    cuda, ref = shard.CudaEngine(), TorchEngine()
+    for prec_name, prec in (("fp32", 0), ("fp16", 1)):
+        tf, tb = TOL[prec_name]
+        total = torch.zeros(B, N, N, C, device=dev)
+        dX_all = torch.zeros(B, N, N, C, device=dev)
+        dW_all = torch.zeros(K, K, C, C, device=dev)
+        for r in range(world):
+            plan = shard.ShardPlan(kind, r, world, N, K)
+            if kind == "row":
+                Xp, row0, rows, Kd, Gdp, Wp = X[:, plan.row_lo:plan.row_hi].contiguous(), plan.row_lo, plan.rows, K, Gd, W
+            else:
+                if plan.Kd == 0:
+                    continue
+                Xp, row0, rows, Kd = X, 0, N, plan.Kd
+                Gdp = (Gd[:, plan.d_lo:plan.d_hi] if dyn else Gd[plan.d_lo:plan.d_hi]).contiguous()
+                Wp = W.view(K, K, C, C)[:, plan.d_lo:plan.d_hi].reshape(K * Kd * C, C).contiguous()
+            pre, saved = cuda.forward_part(Xp, Go, Gdp, dyn, Wp, N, row0, K, Kd, prec, True)
+            pre_r, Z_r = ref.forward_part(Xp, Go, Gdp, dyn, Wp, N, row0, K, Kd, 0, True)
+            _check(pre, pre_r, tf, f"part {kind} N={N} rank {r}/{world} {prec_name} partial pre")
+            total += pre
+            dX, dW = cuda.backward_part(d_pre, Go, Gdp, dyn, Wp, saved, N, row0, rows, K, Kd, C, prec, True)
+            dX_r, dW_r = ref.backward_part(d_pre, Go, Gdp, dyn, Wp, Z_r, N, row0, rows, K, Kd, C, 0, True)
+            _check(dX, dX_r, tb, f"part {kind} N={N} rank {r}/{world} {prec_name} dX")
+            _check(dW, dW_r, tb, f"part {kind} N={N} rank {r}/{world} {prec_name} dW")
+            if kind == "row":
+                dX_all[:, plan.row_lo:plan.row_hi] = dX
+                dW_all += dW.view(K, K, C, C)
+            else:
+                dX_all += dX
+                dW_all[:, plan.d_lo:plan.d_hi] = dW.view(K, Kd, C, C)
+        # the parts of all ranks, exchanged (= summed) and finished with bias + ReLU, are the whole layer
+        cuda.bias_act(total, bias, 1)
+        Go_, Gd_ = (Go, Gd) if dyn else (Go, Go)
+        whole, saved_w = abi.forward(X, Go_, Gd_, W, bias, True, "fp32")
+        _check(total, whole, tf, f"parts {kind} N={N} x{world} {prec_name}: sum of partials == whole layer")
+        # ... and so are their gradients (whole layer fed d_pre through a linear epilogue: act = None)
+        lin, saved_l = abi.forward(X, Go_, Gd_, W, bias, False, "fp32")
+        dXw, dWw, _ = abi.backward(d_pre, lin, Go_, Gd_, W, False, saved_l, "fp32")
+        _check(dX_all, dXw, tb, f"parts {kind} N={N} x{world} {prec_name}: dX")
+        _check(dW_all.view(K * K * C, C), dWw, tb, f"parts {kind} N={N} x{world} {prec_name}: dW")
+
+
+def test_bias_act_and_relu_backward_kernels(cuda_device):
+    torch.manual_seed(0)
+    x = torch.randn(3, 17, 19, 32, device=cuda_device)
+    b = torch.randn(32, device=cuda_device)
+    eng = shard.CudaEngine()
+    want = torch.relu(x + b)
+    got = eng.bias_act(x.clone(), b, 1)
+    assert torch.equal(got, want)
+    assert torch.equal(eng.bias_act(x.clone(), None, 0), x)
+    d = torch.randn_like(x)
+    d_pre, db = eng.relu_backward(d, want, 1, True)
+    assert torch.equal(d_pre, d * (want > 0))
+    torch.testing.assert_close(db, (d * (want > 0)).reshape(-1, 32).sum(0), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("kind", ["row", "k"])
+def test_sharded_model_nccl_world2(kind, tmp_path):
+    """The sharded model on 2 GPUs over NCCL vs the whole model on one GPU: fp32 engine <= 1e-5 forward (2e-4 gradients:
+    summation order), fp16 engine <= 1e-3 forward."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "res.json"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(HERE, "_shard_nccl_worker.py"), kind, str(out)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import json
+    res = json.load(open(out))
+    for row in res["rows"]:
+        record_parity(row["what"], row["linf"], row["l2"], row["tol"])
+        assert row["linf"] <= row["tol"] and row["l2"] <= row["tol"], row
