@@ -283,3 +283,49 @@ def test_two_devices_in_one_process(cuda_device):
             torch.cuda.synchronize(dev)
         outs.append(y.detach().cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("N", [47, 200])
+def test_graphed_training_step_equals_eager_training(N, cuda_device):
+    """mpgcn_b200.graph_step: 6 Adam steps through the captured graph (new batch copied in every step) == the same 6 steps
+    eagerly, bit for bit (same kernels, same buffers' contents), at the reference's N = 47 and at N = 200."""
+    from mpgcn_b200.graph_step import GraphedTrainStep
+    K, T, B = 3, 7, 4
+    rng = np.random.default_rng(N)
+    G = _t(_supports(rng, "rw", K, N, 0), cuda_device)
+    batches = [(_t((rng.random((B, T, N, N, 1)) * 6).astype(np.float32), cuda_device), _t((rng.random((B, 1, N, N, 1)) * 6).astype(np.float32), cuda_device),
+                _t(_supports(rng, "rw", K, N, B), cuda_device), _t(_supports(rng, "rw", K, N, B), cuda_device)) for _ in range(3)]
+    losses = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(5)
+        model = shim.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=32, lstm_num_layers=1, gcn_hidden_dim=32, gcn_num_layers=3,
+                           num_nodes=N, user_bias=True, activation=nn.ReLU).to(cuda_device)
+        _set_precision(model, "fp16")
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+        crit = nn.MSELoss()
+        out = []
+        if mode == "graph":
+            state = {k: v.clone() for k, v in model.state_dict().items()}
+            step = GraphedTrainStep(model, crit, opt, example=(batches[0][0], batches[0][1], G, (batches[0][2], batches[0][3])), warmup=2)
+            with torch.no_grad():                           # undo the warm-up / capture updates IN PLACE (the graph holds these buffers)
+                for k, v in model.state_dict().items():
+                    v.copy_(state[k])
+                for st in opt.state.values():               # ... and restart Adam from zero moments / step 0
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+        for i in range(6):
+            x, y, go, gd = batches[i % 3]
+            if mode == "eager":
+                loss = crit(model(x_seq=x, G_list=[G, (go, gd)]), y)
+                opt.zero_grad(set_to_none=False)
+                loss.backward()
+                opt.step()
+            else:
+                loss = step(x, y, go, gd)
+            out.append(float(loss))
+        losses[mode] = out
+        if mode == "graph":
+            assert step.replays == 6
+    assert np.allclose(losses["graph"], losses["eager"], rtol=1e-5), losses
+    assert losses["eager"][-1] < losses["eager"][0]
