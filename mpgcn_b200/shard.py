@@ -131,35 +131,50 @@ def _backend(group=None) -> str:
     return dist.get_backend(group)
 
 
-def reduce_scatter_rows(partial: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
-    """partial [B, N(m), N, H] (this rank's partial sum for every origin row m) -> [B, rows, N, H]: the sum over the ranks of the
-    rows this rank owns.  One collective per sample keeps the slab in [B, rows, ...] layout with no transpose pass."""
-    B = partial.shape[0]
-    out = partial.new_empty((B, plan.rows) + tuple(partial.shape[2:]))
+class _Pending:
+    """An exchange in flight: `wait()` makes the current stream wait for it (NCCL: the collective runs on NCCL's own stream and
+    overlaps whatever the compute stream does in between) and finishes the gloo emulation."""
+
+    def __init__(self, work=None, finish=None):
+        self.work, self.finish = work, finish
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+        if self.finish is not None:
+            self.finish()
+
+
+def reduce_scatter_rows_begin(partial: torch.Tensor, out: torch.Tensor, plan: ShardPlan) -> _Pending:
+    """partial [N(m), N, H] (ONE sample: this rank's partial sum for every origin row m) -> out [rows, N, H]: the sum over the
+    ranks of the rows this rank owns.  Asynchronous: the next sample's contractions run while this one is exchanged."""
     if _backend(plan.group) == "nccl":
-        works = [dist.reduce_scatter_tensor(out[b], partial[b], group=plan.group, async_op=True) for b in range(B)]
-        for w in works:
-            w.wait()
-    else:   # gloo (CPU tests) has no reduce-scatter: all-reduce, keep the own rows
-        dist.all_reduce(partial, group=plan.group)
-        out.copy_(partial[:, plan.row_lo:plan.row_hi])
-    return out
+        return _Pending(dist.reduce_scatter_tensor(out, partial, group=plan.group, async_op=True))
+    # gloo (CPU tests) has no reduce-scatter: all-reduce, keep the own rows
+    work = dist.all_reduce(partial, group=plan.group, async_op=True)
+    return _Pending(work, lambda: out.copy_(partial[plan.row_lo:plan.row_hi]))
+
+
+def all_gather_rows_begin(slab: torch.Tensor, full: torch.Tensor, plan: ShardPlan) -> _Pending:
+    """slab [rows, N, H] of ONE sample -> full [N, N, H] (rank r's rows at r*rows ..), asynchronously."""
+    if _backend(plan.group) == "nccl":
+        return _Pending(dist.all_gather_into_tensor(full, slab, group=plan.group, async_op=True))
+    parts = [torch.empty_like(slab) for _ in range(plan.world)]
+    work = dist.all_gather(parts, slab, group=plan.group, async_op=True)
+
+    def finish():
+        for r, p in enumerate(parts):
+            full[r * plan.rows:(r + 1) * plan.rows] = p
+    return _Pending(work, finish)
 
 
 def all_gather_rows(slab: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
-    """slab [B, rows, N, H] -> [B, N, N, H] (rank r's rows at r*rows ..)"""
+    """slab [B, rows, N, H] -> [B, N, N, H]; one collective per sample keeps the [B, rows, ...] layout with no transpose pass"""
     B = slab.shape[0]
     full = slab.new_empty((B, plan.N) + tuple(slab.shape[2:]))
     slab = slab.contiguous()
-    if _backend(plan.group) == "nccl":
-        works = [dist.all_gather_into_tensor(full[b], slab[b], group=plan.group, async_op=True) for b in range(B)]
-        for w in works:
-            w.wait()
-    else:
-        parts = [torch.empty_like(slab) for _ in range(plan.world)]
-        dist.all_gather(parts, slab, group=plan.group)
-        for r, p in enumerate(parts):
-            full[:, r * plan.rows:(r + 1) * plan.rows] = p
+    for p in [all_gather_rows_begin(slab[b], full[b], plan) for b in range(B)]:
+        p.wait()
     return full
 
 
@@ -186,33 +201,57 @@ def _f32c(t):
 
 
 class _RowShardLayerFn(torch.autograd.Function):
+    """Sample by sample, so that the exchange of sample b overlaps the contractions of sample b + 1 (forward: partial pre of b is
+    reduce-scattered while b + 1 is computed; backward: every dPre slab is put on the wire up front and the gradient
+    contractions of sample b start as soon as ITS rows have arrived)."""
+
     @staticmethod
     def forward(ctx, X, G_o, G_d, W, b, dynamic, act, precision, plan, grad_mode):
         B, rows, N, C = X.shape
         K, H = G_o.shape[-3], W.shape[1]
-        prec = _ENGINE.resolve_precision(precision, B, N, K, C, H)
+        prec = _ENGINE.resolve_precision(precision, 1, N, K, C, H)
         Xc, Goc, Wc = _f32c(X), _f32c(G_o), _f32c(W)
         Gdc = Goc if G_d is G_o else _f32c(G_d)
         keep = grad_mode and any(ctx.needs_input_grad)
-        partial, saved = _ENGINE.forward_part(Xc, Goc, Gdc, dynamic, Wc, N, plan.row_lo, K, K, prec, keep)
-        out = reduce_scatter_rows(partial, plan)                 # the ONE exchange step of the layer forward
-        del partial
+        out = torch.empty((B, rows, N, H), dtype=torch.float32, device=X.device)
+        pending, stash = [], []
+        for s in range(B):
+            go_s, gd_s = (Goc[s:s + 1], Gdc[s:s + 1]) if dynamic else (Goc, Gdc)
+            partial, saved = _ENGINE.forward_part(Xc[s:s + 1], go_s, gd_s, dynamic, Wc, N, plan.row_lo, K, K, prec, keep)
+            pending.append((reduce_scatter_rows_begin(partial[0], out[s], plan), partial))      # the ONE exchange step of the layer forward
+            stash.append(saved)
+        for p, _ in pending:
+            p.wait()
+        del pending
         _ENGINE.bias_act(out, None if b is None else _f32c(b), act)
-        ctx.meta = (dynamic, act, prec, b is not None, N, K, C)
+        ctx.meta = (dynamic, act, prec, b is not None, N, K, C, keep)
         ctx.plan = plan
-        ctx.save_for_backward(out, Goc, Gdc, Wc, saved if saved is not None else torch.empty(0, device=X.device))
+        ctx.stash = stash
+        ctx.save_for_backward(out, Goc, Gdc, Wc)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        out, Goc, Gdc, Wc, saved = ctx.saved_tensors
-        dynamic, act, prec, has_bias, N, K, C = ctx.meta
+        out, Goc, Gdc, Wc = ctx.saved_tensors
+        dynamic, act, prec, has_bias, N, K, C, keep = ctx.meta
         plan = ctx.plan
-        if saved.numel() == 0:
+        if not keep:
             raise RuntimeError("mpgcn_b200.shard: backward called but forward ran without requires_grad inputs")
+        B, H = d_out.shape[0], d_out.shape[-1]
         d_pre_slab, db = _ENGINE.relu_backward(_f32c(d_out), out, act, has_bias)       # mask + bias gradient of the rank's own rows
-        d_pre = all_gather_rows(d_pre_slab, plan)                                      # the ONE exchange step of the layer backward
-        dX, dW = _ENGINE.backward_part(d_pre, Goc, Gdc, dynamic, Wc, saved, N, plan.row_lo, plan.rows, K, K, C, prec, ctx.needs_input_grad[0])
+        d_pre = d_pre_slab.new_empty((B, N, N, H))
+        pending = [all_gather_rows_begin(d_pre_slab[s], d_pre[s], plan) for s in range(B)]     # the ONE exchange step of the layer backward
+        need_dx = ctx.needs_input_grad[0]
+        dX = torch.empty((B, plan.rows, N, C), dtype=torch.float32, device=d_out.device) if need_dx else None
+        dW = None
+        for s in range(B):
+            pending[s].wait()
+            go_s, gd_s = (Goc[s:s + 1], Gdc[s:s + 1]) if dynamic else (Goc, Gdc)
+            dx_s, dw_s = _ENGINE.backward_part(d_pre[s:s + 1], go_s, gd_s, dynamic, Wc, ctx.stash[s], N, plan.row_lo, plan.rows, K, K, C, prec, need_dx)
+            if need_dx:
+                dX[s:s + 1] = dx_s
+            dW = dw_s if dW is None else dW + dw_s
+        ctx.stash = None
         return dX, None, None, dW, db, None, None, None, None, None
 
 
