@@ -53,7 +53,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--impl", choices=["ours", "reference", "library"], default="ours",
+                    help="ours: the engine; reference: the reference's CPU path (bounded sample); library: (internal) the reference model on the "
+                         "GPU through cuBLAS / cuDNN, printed as gpu_library_baseline by the default arm")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="headline")
     ap.add_argument("--nodes", type=int, default=None, help="N (OD zones); overrides --workload")
     ap.add_argument("--supports", type=int, default=None, help="K")
@@ -503,11 +505,21 @@ def run_ours(a):
                         "sample_ms": 1e3 * best, "lstm_threads": arm.lstm_threads}
     lib_baseline = None
     if world == 1 and not (a.no_gpu_baseline or a.profile):
+        # in a child process: the reference's library path needs ~2 K^2 N^2 C 4 B of autograd state per layer (56 GB at the
+        # headline size) and at cfg5 (N=2000: 4e6 LSTM sequences) it dies inside the libraries with an illegal memory access --
+        # neither may take this process (or its GPU memory) with it
         del model
         torch.cuda.empty_cache()
-        lib_baseline = gpu_library_baseline(a, dev)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "library", "--nodes", str(N), "--supports", str(K), "--obs", str(T),
+               "--hidden", str(hid), "--gpus", "1"]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local))))
+            lib_baseline = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 and r.stdout.strip() else \
+                {"error": f"child exited with {r.returncode}: {r.stderr.strip().splitlines()[-1][:200] if r.stderr.strip() else ''}"}
+        except Exception as e:
+            lib_baseline = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
         for mode in ("fp32", "tf32"):
-            if mode in lib_baseline:
+            if isinstance(lib_baseline.get(mode), dict):
                 lib_baseline[mode]["ours_over_library"] = value / world / lib_baseline[mode]["value"]
 
     line = {
@@ -532,7 +544,11 @@ def main():
     os.dup2(2, 1)
     sys.stdout = sys.stderr
     try:
-        line = run_reference(a) if a.impl == "reference" else run_ours(a)
+        if a.impl == "library":
+            import torch
+            line = gpu_library_baseline(a, torch.device("cuda", 0))
+        else:
+            line = run_reference(a) if a.impl == "reference" else run_ours(a)
     finally:
         sys.stdout = real_stdout
     if line is not None:

@@ -9,7 +9,7 @@ through the C ABI, for BOTH kernel families: fp32 CUDA cores and fp16-operand tc
 accumulation, SWIZZLE_128B flat boxes, ragged 256-row tiles -- the kernels bench.py times).
 
 Tolerances (same definitions as tests/test_gpu_parity.py): forward <= 1e-3 (fp16) / 5e-5 (fp32) rel_Linf and rel_L2;
-gradients <= 2e-3 (fp16, oracle evaluated with the engine's ReLU mask) / 2e-4 (fp32, oracle's own mask).
+gradients <= 2e-3 (fp16) / 2e-4 (fp32) against the oracle evaluated with the engine's ReLU mask (see the layer test).
 """
 import time
 
@@ -120,13 +120,16 @@ def test_layer_matches_oracle_at_size(N, K, B, dyn, kind, cuda_device):
     for prec in ("fp32", "fp16"):
         out, dX, dW, db = _run_layer(X, G, W, b, d_out, prec, cuda_device)
         _check(out, out_o, FWD_TOL[prec], f"{tag}/{prec}/out vs oracle")
-        if prec == "fp32":
-            refs = (dX_o, dW_o, db_o)
-        else:
-            _check(dX, dX_o, LOOSE_FP16_GRAD, f"{tag}/{prec}/dX vs oracle (own mask)", l2_only=True)
-            refs = orc.bdgcn_backward_factored(cast(X), Gc, cast(W), cast(b), "relu", cast(d_out), mask_from=out)[1:]
+        # Gradients are compared with the oracle evaluated on the ENGINE's ReLU mask, for both kernel families: even the fp32
+        # kernels (summation-order noise ~1e-6) flip the sign of the handful of pre-activations that lie within that noise of
+        # zero, and with an i.i.d. d_out every flipped element moves dX by O(|d_out|) (measured: 3 flips in 2.5e6 -> rel_L2
+        # 3e-4, rel_Linf up to 0.16).  Against the oracle's own mask only the norm is bounded.
+        _check(dX, dX_o, LOOSE_FP16_GRAD if prec == "fp16" else 5e-3, f"{tag}/{prec}/dX vs oracle (own mask)", l2_only=True)
+        refs = orc.bdgcn_backward_factored(cast(X), Gc, cast(W), cast(b), "relu", cast(d_out), mask_from=out)[1:]
         for a, r, what in zip((dX, dW, db), refs, ("dX", "dW", "db")):
-            _check(a, r, BWD_TOL[prec], f"{tag}/{prec}/{what}" + (" (engine mask)" if prec == "fp16" else ""))
+            _check(a, r, BWD_TOL[prec], f"{tag}/{prec}/{what} (engine mask)")
+        flips = float(((out > 0) != (out_o > 0)).mean())
+        assert flips <= (1e-5 if prec == "fp32" else 2e-3), f"{tag}/{prec}: ReLU mask flips {flips:.2e}"
     print(f"{tag}: oracle {t_oracle:.1f} s")
 
 
