@@ -34,6 +34,26 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return (uint
 __device__ __forceinline__ float ex2_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// 2^x WITHOUT the SFU, for x <= 40: round-to-nearest split x = n + f through the 1.5 * 2^23 trick, degree-6 polynomial of 2^f on
+// [-0.5, 0.5] (Cephes exp2f coefficients; measured max relative error 1.0e-7, the SFU's ex2.approx is 2 ulp = 2.4e-7), 2^n added into
+// the exponent field.  11 FMA / ALU-pipe instructions instead of one of the 7 SFU operations per unit and step: the forward kernel
+// is SFU-bound (MIO throttle, 72 % XU) with half of its issue slots free (profiles/ncu_lstm_r2.txt).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = 1.535336188319500e-4f;
+  p = fmaf(p, f, 1.339887440266574e-3f);
+  p = fmaf(p, f, 9.618437357674640e-3f);
+  p = fmaf(p, f, 5.550332471162809e-2f);
+  p = fmaf(p, f, 2.402264791363012e-1f);
+  p = fmaf(p, f, 6.931472028550421e-1f);
+  p = fmaf(p, f, 1.f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// POLY = how many of the five exponentials per unit and step take the polynomial (0: none; 1: tanh(c); 2: tanh(c) and the o gate)
+template <int POLY, int WHICH> __device__ __forceinline__ float ex2_sel(float x) { return (WHICH < POLY) ? ex2_poly(x) : ex2_(x); }
+
 // x enters the gate MMA as fp16 hi + lo (exact to ~22 bits for |x| < 65504); both parts saturate instead of overflowing to inf,
 // so larger inputs give finite (saturated-gate) results rather than NaN
 __device__ __forceinline__ float x_split_hi(float x) { return __half2float(__float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f))); }
@@ -141,7 +161,7 @@ __device__ void load_weights_ext(uint8_t* sWx, const float* w_ih, const float* w
 
 constexpr int FWD_THREADS = 256;
 
-template <bool SAVE>
+template <bool SAVE, int POLY>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ hT, __half* __restrict__ saved,
@@ -239,11 +259,11 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           const float gg = fmaf(r + r, ai[u] * af, -1.f);       // tanh(g)
           const float gf = r * pig;                             // sigmoid(f)
           c[u] = fmaf(gf, c[u], gi * gg);
-          p[u] = 1.f + ex2_(fminf(__uint_as_float(rb[u]), 40.f));
+          p[u] = 1.f + ex2_sel<POLY, 1>(fminf(__uint_as_float(rb[u]), 40.f));
         }
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-          const float ac = 1.f + ex2_(fminf(-2.8853900817779268f * c[u], 40.f));
+          const float ac = 1.f + ex2_sel<POLY, 0>(fminf(-2.8853900817779268f * c[u], 40.f));
           const float r = rcp_(p[u] * ac);
           h[u] = (r * ac) * fmaf(r + r, p[u], -1.f);            // sigmoid(o) * tanh(c)
         }
@@ -303,7 +323,7 @@ template <> __device__ __forceinline__ void tmem_st_w<4>(uint32_t taddr, const u
 // No dedicated MMA warp: with 9 warps per CTA the register file only holds ONE CTA per SM at > 102 registers per thread
 // (18 warps -> 5 on one scheduler partition).  Every step ends in one CTA-wide barrier, after which lane 0 of warp 0 issues
 // the step's three MMA groups while everybody moves on.
-template <int TPC>
+template <int TPC, int POLY>
 __global__ void __launch_bounds__(128 * TPC, 2)
 lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                          const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ d_hT,
@@ -477,8 +497,8 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
           const float ai = 1.f + ex2_(fminf(__uint_as_float(ri[e]), 40.f));
           const float ag = 1.f + ex2_(fminf(__uint_as_float(rg[e]), 40.f));
           const float af = 1.f + ex2_(fminf(__uint_as_float(rf[e]), 40.f));
-          const float ao = 1.f + ex2_(fminf(__uint_as_float(ro[e]), 40.f));
-          const float ac = 1.f + ex2_(fminf(-2.8853900817779268f * fc[e], 40.f));
+          const float ao = 1.f + ex2_sel<POLY, 1>(fminf(__uint_as_float(ro[e]), 40.f));
+          const float ac = 1.f + ex2_sel<POLY, 0>(fminf(-2.8853900817779268f * fc[e], 40.f));
           const float pig = ai * ag;
           const float r1 = rcp_(pig * af), r2 = rcp_(ao * ac);      // 7 SFU ops per unit: see the forward kernel
           const float gi = r1 * (ag * af), gg = fmaf(r1 + r1, ai * af, -1.f), gf = r1 * pig;
@@ -582,6 +602,17 @@ __global__ void copy_vec_kernel(const float* src, float* dst, int n) {
 // ---------------------------------------------------------------------------------------
 bool lstm_tc_supported(int T, int C) { return C == 32 && T >= 1 && T <= 256; }
 
+// MPGCN_B200_LSTM_POLY = 0 | 1 | 2: exponentials per unit and step evaluated by ex2_poly (FMA pipe) instead of the SFU
+static int lstm_poly_knob() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MPGCN_B200_LSTM_POLY");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
+  }
+  return v;
+}
+
 static int lstm_grid(long long cells) {
   const long long tiles = (cells + lstm_tc::CELLS - 1) / lstm_tc::CELLS;
   static int per_sm = 0;
@@ -617,15 +648,15 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
     fwd_smem = e ? atoi(e) * 1024 : kLstmFwdSmem;
     if (fwd_smem < kLstmFwdSmem) fwd_smem = kLstmFwdSmem;
   }
-  static DynSmemAttr attr_f = {}, attr_t = {};
-  if (int e = ensure_dyn_smem(lstm_fwd_tc_kernel<false>, fwd_smem, attr_f)) return e;
-  if (int e = ensure_dyn_smem(lstm_fwd_tc_kernel<true>, fwd_smem, attr_t)) return e;
+  const int poly = lstm_poly_knob();
+  using Kern = void (*)(const float*, const float*, const float*, const float*, const float*, float*, __half*, long long, int, long long);
+  static const Kern kerns[2][3] = {{lstm_fwd_tc_kernel<false, 0>, lstm_fwd_tc_kernel<false, 1>, lstm_fwd_tc_kernel<false, 2>},
+                                   {lstm_fwd_tc_kernel<true, 0>, lstm_fwd_tc_kernel<true, 1>, lstm_fwd_tc_kernel<true, 2>}};
+  static DynSmemAttr attrs[2][3] = {};
+  const int sv = saved ? 1 : 0;
+  if (int e = ensure_dyn_smem(kerns[sv][poly], fwd_smem, attrs[sv][poly])) return e;
   prof_begin(PROF_LSTM_FWD, 8.0 * C * (C + 1) * (double)cells * T, st);
-  if (saved)
-    lstm_fwd_tc_kernel<true><<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, static_cast<__half*>(saved),
-                                                                          cells, T, NN);
-  else
-    lstm_fwd_tc_kernel<false><<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, nullptr, cells, T, NN);
+  kerns[sv][poly]<<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, static_cast<__half*>(saved), cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
@@ -651,12 +682,16 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   MPGCN_CUDA(cudaMemsetAsync(d_w_hh, 0, sizeof(float) * G4 * C, st));
   MPGCN_CUDA(cudaMemsetAsync(d_b_ih, 0, sizeof(float) * G4, st));
   if (d_x) MPGCN_CUDA(cudaMemsetAsync(d_x, 0, sizeof(float) * (size_t)cells * T, st));
-  static DynSmemAttr attr = {};
-  if (int e = ensure_dyn_smem(lstm_bwd_saved_tc_kernel<2>, kLstmSavedSmem, attr)) return e;
+  const int poly = lstm_poly_knob();
+  using KernB = void (*)(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
+                         const __half*, const float*, long long, int, long long);
+  static const KernB kernb[3] = {lstm_bwd_saved_tc_kernel<2, 0>, lstm_bwd_saved_tc_kernel<2, 1>, lstm_bwd_saved_tc_kernel<2, 2>};
+  static DynSmemAttr attr_b[3] = {};
+  if (int e = ensure_dyn_smem(kernb[poly], kLstmSavedSmem, attr_b[poly])) return e;
   static_assert(1024 + DA_BYTES + 3 * HX_BYTES + WX_BYTES + 8192 + 2 * G4 * sizeof(float) + 256 <= (size_t)kLstmSavedSmem, "smem");
   prof_begin(PROF_LSTM_BWD, 12.0 * C * (C + 1) * (double)cells * T, st);
-  lstm_bwd_saved_tc_kernel<2><<<lstm_grid(cells), 256, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
-                                                                             static_cast<const __half*>(saved), scale2, cells, T, NN);
+  kernb[poly]<<<lstm_grid(cells), 256, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
+                                                            static_cast<const __half*>(saved), scale2, cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
   prof_count(PROF_ELEMENTWISE);
