@@ -344,6 +344,7 @@ def run_ours(a):
     if sharded:
         from mpgcn_b200 import shard as mshard
         plan = mshard.ShardPlan(a.shard, rank, world, N, K)
+        mshard.enable_peer_exchange(plan, dev)          # row shard: exchange inside our own kernels over NVLink peer memory, if available
         hosts = mshard.shard_host_inputs(plan, x_host, y_host, go_host, gd_host)       # this rank's slices (pinned)
         fwd = lambda x, go, gd: mshard.sharded_forward(model, plan, x, G_static, (go, gd))
     else:

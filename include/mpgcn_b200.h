@@ -140,6 +140,18 @@ MPGCN_API int mpgcn_bias_act(float* x, const float* bias, int act, long long n, 
 /* d_pre = d_out * [out > 0] (act 1) or d_out (act 0); db[h] = sum d_pre (nullable) -- the head of the backward, BEFORE the exchange */
 MPGCN_API int mpgcn_relu_backward(const float* d_out, const float* out, int act, float* d_pre, float* db, long long n, int H, void* stream);
 
+/* The two exchange steps of the origin-row shard, fused into this library's own kernels over PEER memory (NVLink P2P): no separate
+ * collective.  `partials` / `dsts` are HOST arrays of g <= 8 DEVICE pointers to [B,N,N,H] fp32 buffers -- the rank's own and its peers'
+ * buffers mapped into this process (symmetric memory / CUDA IPC); the caller places a barrier between the producers and these calls.
+ *   rows_reduce_bias_act:  out[b,r,e,h] = act( sum_j partials[j][b, row0 + r, e, h] + bias[h] )   out [B,rows,N,H]
+ *        = reduce-scatter of the partial pre-activations (each rank reads ITS rows from every rank) + MPGCN.py:47-49;
+ *   relu_backward_scatter: d_pre = d_out * [out > 0] (d_out, out [B,rows,N,H]) stored to rows [row0, row0 + rows) of EVERY dsts[j];
+ *        db[h] = sum d_pre (nullable)   = ReLU mask + all-gather of dPre. */
+MPGCN_API int mpgcn_rows_reduce_bias_act(float* out, const float* const* partials, int g, const float* bias, int act, int B, int N, int row0,
+                               int rows, int H, void* stream);
+MPGCN_API int mpgcn_relu_backward_scatter(const float* d_out, const float* out, int act, float* const* dsts, int g, float* db, int B, int N,
+                                int row0, int rows, int H, void* stream);
+
 /* nn.LSTM(input_size=1, hidden=C, layers=1, batch_first) over the B*NN OD cells with zero initial
  * state, returning only the last hidden state (reference MPGCN.py:69,80-87,100-104).
  *   x_seq [B,T,NN] (= the model input [B,T,N,N,1] unchanged, NN = N*N)

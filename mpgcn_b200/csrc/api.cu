@@ -196,6 +196,18 @@ int mpgcn_bias_act(float* x, const float* bias, int act, long long n, int H, voi
   return bias_act_inplace(x, bias, act, (size_t)n, H, static_cast<cudaStream_t>(stream));
 }
 
+int mpgcn_rows_reduce_bias_act(float* out, const float* const* partials, int g, const float* bias, int act, int B, int N, int row0, int rows, int H,
+                               void* stream) {
+  MPGCN_CHECK(out && partials && B >= 1 && (act == 0 || act == 1), "mpgcn_rows_reduce_bias_act: bad argument");
+  return rows_reduce_bias_act(out, partials, g, bias, act, B, N, row0, rows, H, static_cast<cudaStream_t>(stream));
+}
+
+int mpgcn_relu_backward_scatter(const float* d_out, const float* out, int act, float* const* dsts, int g, float* db, int B, int N, int row0,
+                                int rows, int H, void* stream) {
+  MPGCN_CHECK(d_out && dsts && B >= 1 && (act == 0 || (act == 1 && out)), "mpgcn_relu_backward_scatter: bad argument");
+  return relu_backward_scatter(d_out, out, act, dsts, g, db, B, N, row0, rows, H, static_cast<cudaStream_t>(stream));
+}
+
 int mpgcn_relu_backward(const float* d_out, const float* out, int act, float* d_pre, float* db, long long n, int H, void* stream) {
   MPGCN_CHECK(d_out && d_pre && n >= 1 && (act == 0 || (act == 1 && out)), "mpgcn_relu_backward: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

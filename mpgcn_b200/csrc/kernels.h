@@ -61,6 +61,12 @@ int reduce_dw_partials(const float* P, float* dW, int slices, int MT, int Ko, in
 int mask_delta_rows(const float* delta, float* out, size_t planes, int N, int row0, int rows, cudaStream_t s);
 // x[i] = act(x[i] + bias[i % H]) in place (bias nullable; act 0 none / 1 ReLU): the epilogue a partial layer call leaves out
 int bias_act_inplace(float* x, const float* bias, int act, size_t n, int H, cudaStream_t s);
+// exchange steps of the origin-row shard fused into elementwise kernels over peer memory (parts / dsts: HOST arrays of g <= 8 DEVICE
+// pointers to [B][N][N][H] buffers, the rank's own and its peers' NVLink-mapped ones)
+int rows_reduce_bias_act(float* out, const float* const* parts, int g, const float* bias, int act, int B, int N, int row0, int rows, int H,
+                         cudaStream_t s);
+int relu_backward_scatter(const float* d_out, const float* out, int act, float* const* dsts, int g, float* db, int B, int N, int row0, int rows,
+                          int H, cudaStream_t s);
 
 // ---- per-cell LSTM, last hidden state (lstm_kernels.cu) ------------------------------------
 int lstm_last_forward(const float* x_seq, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hT,

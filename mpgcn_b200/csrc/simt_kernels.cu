@@ -490,6 +490,100 @@ __global__ void bias_act_kernel(float* __restrict__ x, const float* __restrict__
     x[i] = act ? fmaxf(v, 0.f) : v;
   }
 }
+// ---- exchange steps of the origin-row shard, fused into elementwise kernels over PEER memory (NVLink P2P loads / stores) ----
+struct PeerPtrs { float* p[8]; };
+
+// out[b][r][e][h] = act( sum_j part[j][b][row0 + r][e][h] + bias[h] ): the reduce-scatter of the partial pre-activations -- every rank
+// reads ITS rows out of all g partial buffers (its own and, over NVLink, the peers') -- fused with the bias / activation epilogue
+// (reference MPGCN.py:47-49).  grid.y = sample; x4 = float4 index inside the sample's slab.
+__global__ void rows_reduce_bias_act_kernel(float4* __restrict__ out, PeerPtrs parts, int g, const float* __restrict__ bias, int act,
+                                            size_t slab4 /*rows*N*H/4*/, size_t full4 /*N*N*H/4*/, size_t off4 /*row0*N*H/4*/, int H4) {
+  const size_t b = blockIdx.y;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slab4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < g) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(parts.p[j]) + b * full4 + off4 + i);      // read once: streaming
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    if (bias) {
+      const float4 bb = reinterpret_cast<const float4*>(bias)[i % H4];
+      acc.x += bb.x; acc.y += bb.y; acc.z += bb.z; acc.w += bb.w;
+    }
+    if (act) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    out[b * slab4 + i] = acc;
+  }
+}
+int rows_reduce_bias_act(float* out, const float* const* parts, int g, const float* bias, int act, int B, int N, int row0, int rows, int H,
+                         cudaStream_t s) {
+  MPGCN_CHECK(g >= 1 && g <= 8, "rows_reduce: %d ranks unsupported (1..8)", g);
+  MPGCN_CHECK(H % 4 == 0 && row0 >= 0 && rows >= 1 && row0 + rows <= N, "rows_reduce: bad slab rows [%d, %d) of %d, H=%d", row0, row0 + rows, N, H);
+  PeerPtrs pp{};
+  for (int j = 0; j < g; ++j) {
+    MPGCN_CHECK(parts[j] != nullptr && (reinterpret_cast<uintptr_t>(parts[j]) & 15) == 0, "rows_reduce: partial buffer %d null or misaligned", j);
+    pp.p[j] = const_cast<float*>(parts[j]);
+  }
+  const size_t slab4 = (size_t)rows * N * H / 4, full4 = (size_t)N * N * H / 4, off4 = (size_t)row0 * N * H / 4;
+  prof_count(PROF_ELEMENTWISE);
+  dim3 grid(grid_for(slab4, 256), (unsigned)B);
+  rows_reduce_bias_act_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(out), pp, g, bias, act, slab4, full4, off4, H / 4);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// d_pre = d_out * [out > 0] (or d_out), written to rows [row0, row0 + rows) of EVERY destination buffer [B][N][N][H] -- the rank's own
+// and, over NVLink, the peers': the all-gather of dPre fused with the ReLU mask; db[h] += sum d_pre.  H4 divides the block size,
+// so a thread keeps its four channels.
+__global__ void relu_backward_scatter_kernel(const float4* __restrict__ d_out, const float4* __restrict__ out, int act, PeerPtrs dst, int g,
+                                             float* __restrict__ db, size_t slab4, size_t full4, size_t off4, int H4) {
+  extern __shared__ float s_db[];   // [4][blockDim.x]
+  const size_t b = blockIdx.y;
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slab4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 gq = d_out[b * slab4 + i];
+    if (act) {
+      const float4 o = out[b * slab4 + i];
+      gq.x = o.x > 0.f ? gq.x : 0.f; gq.y = o.y > 0.f ? gq.y : 0.f; gq.z = o.z > 0.f ? gq.z : 0.f; gq.w = o.w > 0.f ? gq.w : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < g) reinterpret_cast<float4*>(dst.p[j])[b * full4 + off4 + i] = gq;
+    l0 += gq.x; l1 += gq.y; l2 += gq.z; l3 += gq.w;
+  }
+  if (db) {
+    const int nt = blockDim.x;
+    s_db[threadIdx.x] = l0; s_db[nt + threadIdx.x] = l1; s_db[2 * nt + threadIdx.x] = l2; s_db[3 * nt + threadIdx.x] = l3;
+    __syncthreads();
+    if ((int)threadIdx.x < 4 * H4) {       // one thread per channel: quad q = channel / 4, component e = channel % 4
+      const int q = threadIdx.x >> 2, e = threadIdx.x & 3;
+      float sum = 0.f;
+      for (int t = q; t < nt; t += H4) sum += s_db[e * nt + t];      // threads t = q (mod H4) own quad q (the grid stride is a multiple of H4)
+      atomicAdd(&db[q * 4 + e], sum);
+    }
+  }
+}
+int relu_backward_scatter(const float* d_out, const float* out, int act, float* const* dsts, int g, float* db, int B, int N, int row0, int rows,
+                          int H, cudaStream_t s) {
+  MPGCN_CHECK(g >= 1 && g <= 8, "relu_backward_scatter: %d ranks unsupported (1..8)", g);
+  MPGCN_CHECK(H % 4 == 0 && 256 % (H / 4) == 0 && 4 * (H / 4) <= 256, "relu_backward_scatter: H=%d unsupported", H);
+  MPGCN_CHECK(row0 >= 0 && rows >= 1 && row0 + rows <= N, "relu_backward_scatter: bad slab rows [%d, %d) of %d", row0, row0 + rows, N);
+  PeerPtrs pp{};
+  for (int j = 0; j < g; ++j) {
+    MPGCN_CHECK(dsts[j] != nullptr && (reinterpret_cast<uintptr_t>(dsts[j]) & 15) == 0, "relu_backward_scatter: destination %d null or misaligned", j);
+    pp.p[j] = dsts[j];
+  }
+  if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * H, s));
+  const size_t slab4 = (size_t)rows * N * H / 4, full4 = (size_t)N * N * H / 4, off4 = (size_t)row0 * N * H / 4;
+  prof_count(PROF_ELEMENTWISE);
+  dim3 grid(grid_for(slab4, 256), (unsigned)B);
+  relu_backward_scatter_kernel<<<grid, 256, 4 * 256 * sizeof(float), s>>>(reinterpret_cast<const float4*>(d_out), reinterpret_cast<const float4*>(out),
+                                                                         act, pp, g, db, slab4, full4, off4, H / 4);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int bias_act_inplace(float* x, const float* bias, int act, size_t n, int H, cudaStream_t s) {
   MPGCN_CHECK(H >= 1, "bias_act: H=%d", H);
   prof_count(PROF_ELEMENTWISE);

@@ -46,9 +46,12 @@ class ShardPlan:
         self.rows = self.row_hi - self.row_lo
         self.d_lo, self.d_hi = shard_range(K, rank, world) if kind == "k" else (0, K)
         self.Kd = self.d_hi - self.d_lo
+        self.peer = None          # PeerExchange once enable_peer_exchange() succeeded (row shard over NVLink peer memory)
 
     def describe(self) -> dict:
         d = {"kind": self.kind, "world": self.world, "rows_per_rank": self.rows,
+             "exchange": ("peer memory: P2P loads / stores inside mpgcn_rows_reduce_bias_act / mpgcn_relu_backward_scatter" if self.peer is not None
+                          else "NCCL collectives"),
              "collective_per_layer": ("reduce-scatter of pre [B,N,N,H] fp32 forward, all-gather of dPre backward" if self.kind == "row"
                                       else "all-reduce of pre [B,N,N,H] fp32 forward, all-reduce of dX backward; all-gather of h_T once per branch")}
         if self.kind == "k":
@@ -63,15 +66,15 @@ class CudaEngine:
     def _part(self, row0, rows, Ko, Kd):
         return _lib.BdgcnPart(row0, rows, Ko, Kd)
 
-    def forward_part(self, X, Go, Gd, dynamic, W, N, row0, Ko, Kd, prec, keep):
-        """X [B,rows,N,C] -> (raw partial pre-activation [B,N,N,H], Z stash or None)"""
+    def forward_part(self, X, Go, Gd, dynamic, W, N, row0, Ko, Kd, prec, keep, out=None):
+        """X [B,rows,N,C] -> (raw partial pre-activation [B,N,N,H] (written into `out` if given), Z stash or None)"""
         lib = _lib.load()
         ops._require_cuda(X, "X")
         B, rows, _, C = X.shape
         H = W.shape[1]
         part = self._part(row0, rows, Ko, Kd)
         pp = ctypes.addressof(part)
-        pre = torch.empty((B, N, N, H), dtype=torch.float32, device=X.device)
+        pre = out if out is not None else torch.empty((B, N, N, H), dtype=torch.float32, device=X.device)
         saved = ops._scratch(lib.mpgcn_bdgcn_part_saved_bytes(B, N, C, H, prec, pp), X.device) if keep else None
         ws = ops._scratch(lib.mpgcn_bdgcn_part_fwd_workspace_bytes(B, N, C, H, int(dynamic), prec, pp), X.device)
         with torch.cuda.device(X.device):
@@ -111,6 +114,27 @@ class CudaEngine:
                                                d_out.shape[-1], ops._stream()), "relu_backward")
         return d_pre, db
 
+    def rows_reduce_bias_act(self, ptrs, B, N, row0, rows, H, bias, act, device):
+        """out [B,rows,N,H] = act(sum over the g buffers at `ptrs` (own + peers', [B,N,N,H]) of the rank's rows + bias)"""
+        lib = _lib.load()
+        out = torch.empty((B, rows, N, H), dtype=torch.float32, device=device)
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        with torch.cuda.device(device):
+            _lib.check(lib.mpgcn_rows_reduce_bias_act(out.data_ptr(), arr, len(ptrs), ops._ptr(bias), int(act), B, N, row0, rows, H, ops._stream()),
+                       "rows_reduce_bias_act")
+        return out
+
+    def relu_backward_scatter(self, d_out, out, act, ptrs, N, row0, want_db):
+        """mask the rank's rows of d_out and store them into rows [row0, ..) of every buffer at `ptrs`; -> db or None"""
+        lib = _lib.load()
+        B, rows, _, H = d_out.shape
+        db = torch.empty(H, dtype=torch.float32, device=d_out.device) if want_db else None
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        with torch.cuda.device(d_out.device):
+            _lib.check(lib.mpgcn_relu_backward_scatter(d_out.data_ptr(), out.data_ptr(), int(act), arr, len(ptrs), ops._ptr(db), B, N, row0, rows, H,
+                                                       ops._stream()), "relu_backward_scatter")
+        return db
+
     def lstm_last(self, x_seq, lstm, precision):
         return ops.lstm_last(x_seq, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0, precision=precision)
 
@@ -122,6 +146,68 @@ class CudaEngine:
 
 
 _ENGINE = CudaEngine()
+
+
+class PeerExchange:
+    """Symmetric [B,N,N,H] fp32 buffers of the row shard, mapped into every rank (torch.distributed._symmetric_memory: cuMem
+    allocations exchanged once at rendezvous; `buffer_ptrs[r]` is rank r's buffer as a device pointer valid in THIS process).
+    With them the two exchange steps of a layer run inside this library's own kernels -- P2P loads / stores over NVLink --
+    instead of a separate NCCL collective whose kernels compete with the persistent contraction kernels for SMs:
+        forward   every rank writes its partial pre-activation into ITS buffer, barrier, `mpgcn_rows_reduce_bias_act` reads the
+                  rank's rows out of all g buffers (reduce-scatter + bias + ReLU in one pass);
+        backward  `mpgcn_relu_backward_scatter` masks the rank's dOut rows and stores them into ALL g buffers (all-gather fused
+                  with the mask), barrier, `mpgcn_bdgcn_backward_part` reads the local copy.
+    Two buffers per direction alternate from layer to layer; with ONE barrier per exchange that is enough: a rank re-uses
+    buffer X two layers later, after a barrier that every rank enters only when it is done with the previous use of X."""
+
+    def __init__(self, plan, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem, self.plan, self.device = symm_mem, plan, device
+        self.group = plan.group if plan.group is not None else dist.group.WORLD
+        self.bufs = {}            # (direction, parity, numel) -> (tensor, handle)
+        self.count = {"fwd": 0, "bwd": 0}
+
+    def next(self, direction, shape):
+        """-> (tensor [shape] in this rank's symmetric buffer, handle); alternates between two buffers per direction"""
+        numel = 1
+        for d in shape:
+            numel *= d
+        key = (direction, self.count[direction] & 1, numel)
+        self.count[direction] += 1
+        if key not in self.bufs:
+            t = self.symm_mem.empty(numel, dtype=torch.float32, device=self.device)
+            hdl = self.symm_mem.rendezvous(t, self.group)            # collective: every rank allocates in the same order
+            self.bufs[key] = (t, hdl)
+        t, hdl = self.bufs[key]
+        return t.view(shape), hdl
+
+
+def enable_peer_exchange(plan, device) -> bool:
+    """Try to switch the row shard of `plan` to the peer-memory exchange (NCCL backend, CUDA symmetric memory available on every
+    rank).  Collective.  Returns whether it is on; on failure anywhere every rank stays on the NCCL collectives."""
+    import os
+    ok = 0
+    if plan.kind == "row" and _backend(plan.group) == "nccl" and os.environ.get("MPGCN_B200_SHARD_EXCHANGE", "peer") == "peer":
+        try:
+            px = PeerExchange(plan, device)
+            ok = 1
+        except Exception:
+            ok = 0
+    flag = torch.tensor([ok], device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=plan.group)
+    if int(flag.item()) == 1:
+        try:
+            px.next("fwd", (1,))                       # smoke: one tiny rendezvous + barrier, so that a failure shows up here
+            px.bufs[("fwd", 0, 1)][1].barrier()
+            px.count["fwd"] = 0
+            plan.peer = px
+        except Exception as e:
+            plan.peer = None
+            flag.zero_()
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=plan.group)
+        if int(flag.item()) != 1:
+            plan.peer = None
+    return plan.peer is not None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -213,6 +299,18 @@ class _RowShardLayerFn(torch.autograd.Function):
         Xc, Goc, Wc = _f32c(X), _f32c(G_o), _f32c(W)
         Gdc = Goc if G_d is G_o else _f32c(G_d)
         keep = grad_mode and any(ctx.needs_input_grad)
+        if plan.peer is not None:
+            # peer-memory exchange: the whole batch in one part call, partial written straight into the symmetric buffer,
+            # one barrier, then the reduce-scatter + bias + ReLU kernel reads this rank's rows from every rank's buffer
+            buf, hdl = plan.peer.next("fwd", (B, N, N, H))
+            _, saved = _ENGINE.forward_part(Xc, Goc, Gdc, dynamic, Wc, N, plan.row_lo, K, K, prec, keep, out=buf)
+            hdl.barrier()
+            out = _ENGINE.rows_reduce_bias_act(list(hdl.buffer_ptrs), B, N, plan.row_lo, rows, H, None if b is None else _f32c(b), act, X.device)
+            ctx.meta = (dynamic, act, prec, b is not None, N, K, C, keep)
+            ctx.plan = plan
+            ctx.stash = [saved]
+            ctx.save_for_backward(out, Goc, Gdc, Wc)
+            return out
         out = torch.empty((B, rows, N, H), dtype=torch.float32, device=X.device)
         pending, stash = [], []
         for s in range(B):
@@ -238,6 +336,13 @@ class _RowShardLayerFn(torch.autograd.Function):
         if not keep:
             raise RuntimeError("mpgcn_b200.shard: backward called but forward ran without requires_grad inputs")
         B, H = d_out.shape[0], d_out.shape[-1]
+        if plan.peer is not None:
+            d_pre, hdl = plan.peer.next("bwd", (B, N, N, H))
+            db = _ENGINE.relu_backward_scatter(_f32c(d_out), out, act, list(hdl.buffer_ptrs), N, plan.row_lo, has_bias)
+            hdl.barrier()
+            dX, dW = _ENGINE.backward_part(d_pre, Goc, Gdc, dynamic, Wc, ctx.stash[0], N, plan.row_lo, plan.rows, K, K, C, prec, ctx.needs_input_grad[0])
+            ctx.stash = None
+            return dX, None, None, dW, db, None, None, None, None, None
         d_pre_slab, db = _ENGINE.relu_backward(_f32c(d_out), out, act, has_bias)       # mask + bias gradient of the rank's own rows
         d_pre = d_pre_slab.new_empty((B, N, N, H))
         pending = [all_gather_rows_begin(d_pre_slab[s], d_pre[s], plan) for s in range(B)]     # the ONE exchange step of the layer backward

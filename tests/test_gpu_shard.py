@@ -100,10 +100,11 @@ def test_bias_act_and_relu_backward_kernels(cuda_device):
     torch.testing.assert_close(db, (d * (want > 0)).reshape(-1, 32).sum(0), rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("kind", ["row", "k"])
-def test_sharded_model_nccl_world2(kind, tmp_path):
-    """The sharded model on 2 GPUs over NCCL vs the whole model on one GPU: fp32 engine <= 1e-5 forward (2e-4 gradients:
-    summation order), fp16 engine <= 1e-3 forward."""
+@pytest.mark.parametrize("kind,peer", [("row", True), ("row", False), ("k", False)])
+def test_sharded_model_nccl_world2(kind, peer, tmp_path):
+    """The sharded model on 2 GPUs vs the whole model on one GPU: fp32 engine <= 1e-5 forward (5e-4 gradients: summation
+    order + the handful of ReLU-mask flips at fp32 noise level), fp16 engine <= 1e-3 forward.  Row shard: once with the exchange
+    inside our own kernels over NVLink peer memory (symmetric memory), once with the NCCL collectives."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     with socket.socket() as s:
@@ -112,10 +113,12 @@ def test_sharded_model_nccl_world2(kind, tmp_path):
     out = tmp_path / "res.json"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(HERE, "_shard_nccl_worker.py"), kind, str(out)],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, SHARD_TEST_PEER="1" if peer else "0"))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     import json
     res = json.load(open(out))
+    if peer:
+        assert res["peer_exchange"], "symmetric-memory peer exchange could not be enabled on this box (the NCCL path is tested separately)"
     for row in res["rows"]:
         record_parity(row["what"], row["linf"], row["l2"], row["tol"])
         assert row["linf"] <= row["tol"] and row["l2"] <= row["tol"], row
