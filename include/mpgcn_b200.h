@@ -86,6 +86,10 @@ typedef struct mpgcn_bdgcn_extras {
   void* out_f16;
   const float* d_out_absmax;
   float* dX_absmax;
+  /* ABI 3, backward_part only: dPre [B,N,N,H] already masked, multiplied by d_pre_scale2[0] and cast to fp16, with its device
+   * [S, 1/S] pair -- what mpgcn_relu_backward_scatter_f16 leaves in every rank's buffer; the fp32 d_pre argument may then be NULL */
+  const void* d_pre_f16;
+  const float* d_pre_scale2;
 } mpgcn_bdgcn_extras;
 
 /* planes = (dynamic ? B : 1) * K support matrices [N,N] -> fp16 padded copy + diagonal remainders (256-byte aligned buffer) */
@@ -121,7 +125,8 @@ MPGCN_API int mpgcn_bdgcn_backward_ex(const float* d_out, const float* out, cons
  * mpgcn_relu_backward and all-gathers them / has them replicated) and returns dX for its rows ([B,rows,N,C]; K shard: the
  * partial sum over its d, to be all-reduced) and dW for its slice (row shard: partial over its rows, to be all-reduced).
  *   X [B,rows,N,C]   pre_partial [B,N,N,H]   saved: mpgcn_bdgcn_part_saved_bytes   d_pre [B,N,N,H]   dX [B,rows,N,C] or NULL
- *   d_pre_absmax (nullable): device scalar already holding max|d_pre| (skips one pass; precision 1 only). */
+ *   extras (nullable): go_prepared / gd_prepared (supports converted once by mpgcn_bdgcn_prepare_supports), d_out_absmax (= max|d_pre|
+ *   already known), d_pre_f16 + d_pre_scale2 (backward: the fp16 dPre produced by mpgcn_relu_backward_scatter_f16). */
 typedef struct mpgcn_bdgcn_part {
   int row0, rows;
   int Ko, Kd;
@@ -131,10 +136,10 @@ MPGCN_API size_t mpgcn_bdgcn_part_fwd_workspace_bytes(int B, int N, int C, int H
 MPGCN_API size_t mpgcn_bdgcn_part_bwd_workspace_bytes(int B, int N, int C, int H, int dynamic, int precision, const mpgcn_bdgcn_part* part);
 MPGCN_API int mpgcn_bdgcn_forward_part(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, float* pre_partial,
                              void* saved, void* workspace, size_t workspace_bytes, int B, int N, int C, int H, int precision,
-                             const mpgcn_bdgcn_part* part, void* stream);
+                             const mpgcn_bdgcn_part* part, const mpgcn_bdgcn_extras* extras, void* stream);
 MPGCN_API int mpgcn_bdgcn_backward_part(const float* d_pre, const float* G_o, const float* G_d, int dynamic, const float* W, const void* saved,
                               float* dX, float* dW, void* workspace, size_t workspace_bytes, int B, int N, int C, int H, int precision,
-                              const mpgcn_bdgcn_part* part, const float* d_pre_absmax, void* stream);
+                              const mpgcn_bdgcn_part* part, const mpgcn_bdgcn_extras* extras, void* stream);
 /* x[i] = act(x[i] + bias[i % H]) in place -- the `+= b`, activation of MPGCN.py:47-49, applied AFTER the exchange step */
 MPGCN_API int mpgcn_bias_act(float* x, const float* bias, int act, long long n, int H, void* stream);
 /* d_pre = d_out * [out > 0] (act 1) or d_out (act 0); db[h] = sum d_pre (nullable) -- the head of the backward, BEFORE the exchange */
@@ -151,6 +156,12 @@ MPGCN_API int mpgcn_rows_reduce_bias_act(float* out, const float* const* partial
                                int rows, int H, void* stream);
 MPGCN_API int mpgcn_relu_backward_scatter(const float* d_out, const float* out, int act, float* const* dsts, int g, float* db, int B, int N,
                                 int row0, int rows, int H, void* stream);
+/* The same for the tensor-core path with its fp16 cast folded in: absmax = device scalar holding the GLOBAL max|d_out| (every rank's
+ * mpgcn_absmax reduced with MAX), scale2 [2] receives [S, 1/S] (S = 2^k, S * absmax in [16, 32)); dsts[j] are fp16 [B,N,N,H] buffers
+ * that receive fp16(S * d_pre): half the bytes on the wire, and no rank runs a cast or absmax pass over the gathered tensor. */
+MPGCN_API int mpgcn_relu_backward_scatter_f16(const float* d_out, const float* out, int act, void* const* dsts, int g, float* db,
+                                    const float* absmax, float* scale2, int B, int N, int row0, int rows, int H, void* stream);
+MPGCN_API int mpgcn_absmax(const float* x, long long n, float* out, void* stream);
 
 /* nn.LSTM(input_size=1, hidden=C, layers=1, batch_first) over the B*NN OD cells with zero initial
  * state, returning only the last hidden state (reference MPGCN.py:69,80-87,100-104).

@@ -67,9 +67,12 @@ _SIGS = {
     "mpgcn_bdgcn_part_fwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     "mpgcn_bdgcn_part_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 6 + [ctypes.c_void_p]),
     "mpgcn_bdgcn_forward_part": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, ctypes.c_size_t] + [ctypes.c_int] * 5 +
-                                 [ctypes.c_void_p, ctypes.c_void_p]),
+                                 [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "mpgcn_bdgcn_backward_part": (ctypes.c_int, [_c_f, _c_f, _c_f, ctypes.c_int, _c_f, _c_f, _c_f, _c_f, _c_f, ctypes.c_size_t] + [ctypes.c_int] * 5 +
-                                  [ctypes.c_void_p, _c_f, ctypes.c_void_p]),
+                                  [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mpgcn_relu_backward_scatter_f16": (ctypes.c_int, [_c_f, _c_f, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _c_f, _c_f, _c_f] +
+                                        [ctypes.c_int] * 5 + [ctypes.c_void_p]),
+    "mpgcn_absmax": (ctypes.c_int, [_c_f, ctypes.c_longlong, _c_f, ctypes.c_void_p]),
     "mpgcn_rows_reduce_bias_act": (ctypes.c_int, [_c_f, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _c_f, ctypes.c_int] + [ctypes.c_int] * 5 + [ctypes.c_void_p]),
     "mpgcn_relu_backward_scatter": (ctypes.c_int, [_c_f, _c_f, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _c_f] + [ctypes.c_int] * 5 +
                                     [ctypes.c_void_p]),
@@ -85,7 +88,8 @@ EXPORTED_SYMBOLS = tuple(_SIGS)
 class BdgcnExtras(ctypes.Structure):
     """mpgcn_bdgcn_extras (include/mpgcn_b200.h): optional side inputs / outputs of the tensor-core layer."""
     _fields_ = [("go_prepared", ctypes.c_void_p), ("gd_prepared", ctypes.c_void_p), ("x_f16", ctypes.c_void_p),
-                ("out_f16", ctypes.c_void_p), ("d_out_absmax", ctypes.c_void_p), ("dX_absmax", ctypes.c_void_p)]
+                ("out_f16", ctypes.c_void_p), ("d_out_absmax", ctypes.c_void_p), ("dX_absmax", ctypes.c_void_p),
+                ("d_pre_f16", ctypes.c_void_p), ("d_pre_scale2", ctypes.c_void_p)]
 
 
 class BdgcnPart(ctypes.Structure):

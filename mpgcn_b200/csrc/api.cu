@@ -84,6 +84,7 @@ static BdgcnExtras to_extras(const mpgcn_bdgcn_extras* x) {
   if (x) {
     e.go_prepared = x->go_prepared; e.gd_prepared = x->gd_prepared; e.x_f16 = x->x_f16; e.out_f16 = x->out_f16;
     e.d_out_absmax = x->d_out_absmax; e.dx_absmax = x->dX_absmax;
+    e.d_pre_f16 = x->d_pre_f16; e.d_pre_scale2 = x->d_pre_scale2;
   }
   return e;
 }
@@ -162,7 +163,7 @@ size_t mpgcn_bdgcn_part_bwd_workspace_bytes(int B, int N, int C, int H, int dyna
 
 int mpgcn_bdgcn_forward_part(const float* X, const float* G_o, const float* G_d, int dynamic, const float* W, float* pre_partial, void* saved,
                              void* workspace, size_t workspace_bytes, int B, int N, int C, int H, int precision,
-                             const mpgcn_bdgcn_part* part, void* stream) {
+                             const mpgcn_bdgcn_part* part, const mpgcn_bdgcn_extras* extras, void* stream) {
   MPGCN_CHECK(part != nullptr, "mpgcn_bdgcn_forward_part: part descriptor is NULL");
   const BdgcnShape s = mk_part(B, N, C, H, dynamic ? 1 : 0, part);
   if (int e = check_part(s, precision)) return e;
@@ -170,22 +171,27 @@ int mpgcn_bdgcn_forward_part(const float* X, const float* G_o, const float* G_d,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfRegion region(PROF_LAYER_FWD, layer_flops(s, false) * s.R / s.N * (s.Ko + s.Kd) / (2.0 * s.K), st);
   if (precision == PREC_FP16_TC)
-    return bdgcn_forward_tc(s, X, G_o, G_d, W, nullptr, pre_partial, saved, workspace, workspace_bytes, BdgcnExtras(), st);
+  {
+    BdgcnExtras ex;                 // of the extras only the prepared supports apply to a part
+    if (extras) { ex.go_prepared = extras->go_prepared; ex.gd_prepared = extras->gd_prepared; }
+    return bdgcn_forward_tc(s, X, G_o, G_d, W, nullptr, pre_partial, saved, workspace, workspace_bytes, ex, st);
+  }
   return bdgcn_forward_simt(s, X, G_o, G_d, W, nullptr, pre_partial, saved, workspace, workspace_bytes, st);
 }
 
 int mpgcn_bdgcn_backward_part(const float* d_pre, const float* G_o, const float* G_d, int dynamic, const float* W, const void* saved, float* dX,
                               float* dW, void* workspace, size_t workspace_bytes, int B, int N, int C, int H, int precision,
-                              const mpgcn_bdgcn_part* part, const float* d_pre_absmax, void* stream) {
+                              const mpgcn_bdgcn_part* part, const mpgcn_bdgcn_extras* extras, void* stream) {
   MPGCN_CHECK(part != nullptr, "mpgcn_bdgcn_backward_part: part descriptor is NULL");
   const BdgcnShape s = mk_part(B, N, C, H, dynamic ? 1 : 0, part);
   if (int e = check_part(s, precision)) return e;
-  MPGCN_CHECK(d_pre && G_o && G_d && W && saved && dW && workspace, "mpgcn_bdgcn_backward_part: null pointer argument");
+  const bool have16 = extras && extras->d_pre_f16 && precision == PREC_FP16_TC;
+  MPGCN_CHECK((d_pre || have16) && G_o && G_d && W && saved && dW && workspace, "mpgcn_bdgcn_backward_part: null pointer argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfRegion region(PROF_LAYER_BWD, layer_flops(s, true) * s.R / s.N * (s.Ko + s.Kd) / (2.0 * s.K), st);
   if (precision == PREC_FP16_TC) {
-    BdgcnExtras ex;
-    ex.d_out_absmax = d_pre_absmax;
+    BdgcnExtras ex = to_extras(extras);
+    ex.x_f16 = nullptr; ex.out_f16 = nullptr; ex.dx_absmax = nullptr;
     return bdgcn_backward_tc(s, d_pre, nullptr, G_o, G_d, W, saved, dX, dW, nullptr, workspace, workspace_bytes, ex, st);
   }
   return bdgcn_backward_simt(s, d_pre, nullptr, G_o, G_d, W, saved, dX, dW, nullptr, workspace, workspace_bytes, st);
@@ -206,6 +212,18 @@ int mpgcn_relu_backward_scatter(const float* d_out, const float* out, int act, f
                                 int rows, int H, void* stream) {
   MPGCN_CHECK(d_out && dsts && B >= 1 && (act == 0 || (act == 1 && out)), "mpgcn_relu_backward_scatter: bad argument");
   return relu_backward_scatter(d_out, out, act, dsts, g, db, B, N, row0, rows, H, static_cast<cudaStream_t>(stream));
+}
+
+int mpgcn_relu_backward_scatter_f16(const float* d_out, const float* out, int act, void* const* dsts, int g, float* db, const float* absmax,
+                                    float* scale2, int B, int N, int row0, int rows, int H, void* stream) {
+  MPGCN_CHECK(d_out && dsts && B >= 1 && (act == 0 || (act == 1 && out)), "mpgcn_relu_backward_scatter_f16: bad argument");
+  return relu_backward_scatter_f16(d_out, out, act, reinterpret_cast<__half* const*>(dsts), g, db, absmax, scale2, B, N, row0, rows, H,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int mpgcn_absmax(const float* x, long long n, float* out, void* stream) {
+  MPGCN_CHECK(x && out && n >= 1, "mpgcn_absmax: bad argument");
+  return absmax_f32(x, (size_t)n, out, static_cast<cudaStream_t>(stream));
 }
 
 int mpgcn_relu_backward(const float* d_out, const float* out, int act, float* d_pre, float* db, long long n, int H, void* stream) {

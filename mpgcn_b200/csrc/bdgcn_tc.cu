@@ -490,19 +490,29 @@ int bdgcn_backward_tc(const BdgcnShape& s, const float* d_out, const float* out,
   MPGCN_CHECK(ws_bytes >= L.total, "bdgcn_backward: workspace too small (%zu < %zu bytes)", ws_bytes, L.total);
   MPGCN_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
   uint8_t* wb = static_cast<uint8_t*>(ws);
-  __half* dp16 = reinterpret_cast<__half*>(wb + L.dp16);
+  const __half* dp16 = reinterpret_cast<__half*>(wb + L.dp16);
   __half* v16 = reinterpret_cast<__half*>(wb + L.v16);
   __half* y16 = reinterpret_cast<__half*>(wb + L.y16);
   __half* wq16 = reinterpret_cast<__half*>(wb + L.wq16);
   float* partials = reinterpret_cast<float*>(wb + L.partials);
-  float* scale2 = reinterpret_cast<float*>(wb + L.scale);   // [S, 1/S]: power-of-two gradient scale (fp16 range)
+  const float* scale2 = reinterpret_cast<float*>(wb + L.scale);   // [S, 1/S]: power-of-two gradient scale (fp16 range)
 
-  if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 32, st));
-  if (int e = grad_scale_prepare(d_out, (size_t)s.B * NNfull * 32, scale2, ex.d_out_absmax, st)) return e;
-  if (ex.out_f16 != nullptr && act) {
-    if (int e = relu_bwd_prep_f16mask(d_out, static_cast<const __half*>(ex.out_f16), act, dp16, db, (size_t)s.B * NNfull * 32, 32, scale2, st)) return e;
+  if (ex.d_pre_f16 != nullptr) {
+    // dPre arrives masked, scaled and cast (mpgcn_relu_backward_scatter_f16 wrote it into every rank's buffer): no pass over it here
+    MPGCN_CHECK(s.partial && ex.d_pre_scale2 != nullptr, "bdgcn_backward: a prepared fp16 dPre needs a part call and its scale pair");
+    MPGCN_CHECK((reinterpret_cast<uintptr_t>(ex.d_pre_f16) & 15) == 0, "bdgcn_backward: prepared fp16 dPre must be 16-byte aligned");
+    dp16 = static_cast<const __half*>(ex.d_pre_f16);
+    scale2 = ex.d_pre_scale2;
   } else {
-    if (int e = relu_bwd_prep(d_out, out, act, dp16, nullptr, db, (size_t)s.B * NNfull * 32, 32, scale2, st)) return e;
+    __half* dp16_ws = reinterpret_cast<__half*>(wb + L.dp16);
+    float* scale2_ws = reinterpret_cast<float*>(wb + L.scale);
+    if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 32, st));
+    if (int e = grad_scale_prepare(d_out, (size_t)s.B * NNfull * 32, scale2_ws, ex.d_out_absmax, st)) return e;
+    if (ex.out_f16 != nullptr && act) {
+      if (int e = relu_bwd_prep_f16mask(d_out, static_cast<const __half*>(ex.out_f16), act, dp16_ws, db, (size_t)s.B * NNfull * 32, 32, scale2_ws, st)) return e;
+    } else {
+      if (int e = relu_bwd_prep(d_out, out, act, dp16_ws, nullptr, db, (size_t)s.B * NNfull * 32, 32, scale2_ws, st)) return e;
+    }
   }
   SideG gd{}, go{};
   const bool shared = Go == Gd && s.Ko == s.Kd;

@@ -65,6 +65,11 @@ int bias_act_inplace(float* x, const float* bias, int act, size_t n, int H, cuda
 // pointers to [B][N][N][H] buffers, the rank's own and its peers' NVLink-mapped ones)
 int rows_reduce_bias_act(float* out, const float* const* parts, int g, const float* bias, int act, int B, int N, int row0, int rows, int H,
                          cudaStream_t s);
+// the same with the fp16 cast of the tensor-core path folded in: scale2 = [S, 1/S] from the GLOBAL max|d_out| (device scalar), values
+// stored as fp16(S * d_pre) -- half the bytes on the wire and no cast / absmax pass over the gathered tensor on any rank
+int relu_backward_scatter_f16(const float* d_out, const float* out, int act, __half* const* dsts, int g, float* db, const float* absmax,
+                              float* scale2, int B, int N, int row0, int rows, int H, cudaStream_t s);
+int absmax_f32(const float* x, size_t n, float* out, cudaStream_t s);
 int relu_backward_scatter(const float* d_out, const float* out, int act, float* const* dsts, int g, float* db, int B, int N, int row0, int rows,
                           int H, cudaStream_t s);
 
@@ -134,6 +139,8 @@ struct BdgcnExtras {
   void* out_f16 = nullptr;              // forward: receives an fp16 copy of out;  backward: that copy (ReLU mask source instead of out)
   const float* d_out_absmax = nullptr;  // backward: max|d_out| already known
   float* dx_absmax = nullptr;           // backward: receives max|dX|
+  const void* d_pre_f16 = nullptr;      // backward of a PART: dPre [B,N,N,H] already masked, scaled by scale2[0] and cast to fp16
+  const float* d_pre_scale2 = nullptr;  //   ... with its device [S, 1/S] pair (mpgcn_relu_backward_scatter_f16 produces both)
 };
 size_t bdgcn_supports_prepared_bytes(long long planes, int N);
 int bdgcn_prepare_supports(const float* G, void* prepared, long long planes, int N, cudaStream_t st);

@@ -584,6 +584,69 @@ int relu_backward_scatter(const float* d_out, const float* out, int act, float* 
   return 0;
 }
 
+struct PeerPtrs16 { __half* p[8]; };
+__global__ void relu_backward_scatter_f16_kernel(const float4* __restrict__ d_out, const float4* __restrict__ out, int act, PeerPtrs16 dst, int g,
+                                                 float* __restrict__ db, const float* __restrict__ scale2, size_t slab4, size_t full4, size_t off4,
+                                                 int H4) {
+  extern __shared__ float s_db[];   // [4][blockDim.x]
+  const float S = __ldg(scale2);
+  const size_t b = blockIdx.y;
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slab4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 gq = d_out[b * slab4 + i];
+    if (act) {
+      const float4 o = out[b * slab4 + i];
+      gq.x = o.x > 0.f ? gq.x : 0.f; gq.y = o.y > 0.f ? gq.y : 0.f; gq.z = o.z > 0.f ? gq.z : 0.f; gq.w = o.w > 0.f ? gq.w : 0.f;
+    }
+    const __half2 lo = __halves2half2(f2h_sat(gq.x * S), f2h_sat(gq.y * S)), hi = __halves2half2(f2h_sat(gq.z * S), f2h_sat(gq.w * S));
+    const uint2 pk = make_uint2(*reinterpret_cast<const unsigned int*>(&lo), *reinterpret_cast<const unsigned int*>(&hi));
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < g) reinterpret_cast<uint2*>(dst.p[j])[b * full4 + off4 + i] = pk;
+    l0 += gq.x; l1 += gq.y; l2 += gq.z; l3 += gq.w;
+  }
+  if (db) {
+    const int nt = blockDim.x;
+    s_db[threadIdx.x] = l0; s_db[nt + threadIdx.x] = l1; s_db[2 * nt + threadIdx.x] = l2; s_db[3 * nt + threadIdx.x] = l3;
+    __syncthreads();
+    if ((int)threadIdx.x < 4 * H4) {
+      const int q = threadIdx.x >> 2, e = threadIdx.x & 3;
+      float sum = 0.f;
+      for (int t = q; t < nt; t += H4) sum += s_db[e * nt + t];
+      atomicAdd(&db[q * 4 + e], sum);
+    }
+  }
+}
+int relu_backward_scatter_f16(const float* d_out, const float* out, int act, __half* const* dsts, int g, float* db, const float* absmax,
+                              float* scale2, int B, int N, int row0, int rows, int H, cudaStream_t s) {
+  MPGCN_CHECK(g >= 1 && g <= 8, "relu_backward_scatter_f16: %d ranks unsupported (1..8)", g);
+  MPGCN_CHECK(H % 4 == 0 && 256 % (H / 4) == 0 && 4 * (H / 4) <= 256, "relu_backward_scatter_f16: H=%d unsupported", H);
+  MPGCN_CHECK(row0 >= 0 && rows >= 1 && row0 + rows <= N, "relu_backward_scatter_f16: bad slab rows [%d, %d) of %d", row0, row0 + rows, N);
+  MPGCN_CHECK(absmax != nullptr && scale2 != nullptr, "relu_backward_scatter_f16: absmax / scale2 are required");
+  PeerPtrs16 pp{};
+  for (int j = 0; j < g; ++j) {
+    MPGCN_CHECK(dsts[j] != nullptr && (reinterpret_cast<uintptr_t>(dsts[j]) & 7) == 0, "relu_backward_scatter_f16: destination %d null or misaligned", j);
+    pp.p[j] = dsts[j];
+  }
+  if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * H, s));
+  prof_count(PROF_ELEMENTWISE);
+  make_scale_kernel<<<1, 1, 0, s>>>(scale2, absmax);
+  const size_t slab4 = (size_t)rows * N * H / 4, full4 = (size_t)N * N * H / 4, off4 = (size_t)row0 * N * H / 4;
+  prof_count(PROF_ELEMENTWISE);
+  dim3 grid(grid_for(slab4, 256), (unsigned)B);
+  relu_backward_scatter_f16_kernel<<<grid, 256, 4 * 256 * sizeof(float), s>>>(reinterpret_cast<const float4*>(d_out), reinterpret_cast<const float4*>(out),
+                                                                             act, pp, g, db, scale2, slab4, full4, off4, H / 4);
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+int absmax_f32(const float* x, size_t n, float* out, cudaStream_t s) {
+  MPGCN_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+  prof_count(PROF_ELEMENTWISE);
+  absmax_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, n, reinterpret_cast<unsigned int*>(out));
+  MPGCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int bias_act_inplace(float* x, const float* bias, int act, size_t n, int H, cudaStream_t s) {
   MPGCN_CHECK(H >= 1, "bias_act: H=%d", H);
   prof_count(PROF_ELEMENTWISE);

@@ -66,7 +66,15 @@ class CudaEngine:
     def _part(self, row0, rows, Ko, Kd):
         return _lib.BdgcnPart(row0, rows, Ko, Kd)
 
-    def forward_part(self, X, Go, Gd, dynamic, W, N, row0, Ko, Kd, prec, keep, out=None):
+    def prepared(self, G, Gc, planes, N, prec):
+        """fp16 staging of a support stack, converted once per tensor (mpgcn_b200.ops cache) and reused by every layer, forward and
+        backward; None for the fp32 kernels"""
+        if prec != _lib.PREC_FP16_TC:
+            return None
+        with torch.cuda.device(Gc.device):
+            return ops._prepared_supports(_lib.load(), G, Gc, planes, N)
+
+    def forward_part(self, X, Go, Gd, dynamic, W, N, row0, Ko, Kd, prec, keep, out=None, preps=(None, None)):
         """X [B,rows,N,C] -> (raw partial pre-activation [B,N,N,H] (written into `out` if given), Z stash or None)"""
         lib = _lib.load()
         ops._require_cuda(X, "X")
@@ -77,25 +85,34 @@ class CudaEngine:
         pre = out if out is not None else torch.empty((B, N, N, H), dtype=torch.float32, device=X.device)
         saved = ops._scratch(lib.mpgcn_bdgcn_part_saved_bytes(B, N, C, H, prec, pp), X.device) if keep else None
         ws = ops._scratch(lib.mpgcn_bdgcn_part_fwd_workspace_bytes(B, N, C, H, int(dynamic), prec, pp), X.device)
+        ex = _lib.BdgcnExtras()
+        ex.go_prepared, ex.gd_prepared = ops._ptr(preps[0]), ops._ptr(preps[1])
         with torch.cuda.device(X.device):
             _lib.check(lib.mpgcn_bdgcn_forward_part(X.data_ptr(), Go.data_ptr(), Gd.data_ptr(), int(dynamic), W.data_ptr(), pre.data_ptr(),
-                                                    ops._ptr(saved), ws.data_ptr(), ws.numel(), B, N, C, H, prec, pp, ops._stream()),
-                       "bdgcn_forward_part")
+                                                    ops._ptr(saved), ws.data_ptr(), ws.numel(), B, N, C, H, prec, pp, ctypes.addressof(ex),
+                                                    ops._stream()), "bdgcn_forward_part")
         return pre, saved
 
-    def backward_part(self, d_pre, Go, Gd, dynamic, W, saved, N, row0, rows, Ko, Kd, C, prec, need_dx):
-        """d_pre [B,N,N,H] (every origin row, masked) -> (dX [B,rows,N,C] or None, dW [Ko*Kd*C, H])"""
+    def backward_part(self, d_pre, Go, Gd, dynamic, W, saved, N, row0, rows, Ko, Kd, C, prec, need_dx, preps=(None, None), d_pre16=None,
+                      scale2=None):
+        """d_pre [B,N,N,H] (every origin row, masked; fp32, or `d_pre16` + `scale2` from relu_backward_scatter_f16)
+        -> (dX [B,rows,N,C] or None, dW [Ko*Kd*C, H])"""
         lib = _lib.load()
+        if d_pre is None:
+            d_pre = d_pre16
         B, H = d_pre.shape[0], d_pre.shape[-1]
         part = self._part(row0, rows, Ko, Kd)
         pp = ctypes.addressof(part)
         dX = torch.empty((B, rows, N, C), dtype=torch.float32, device=d_pre.device) if need_dx else None
         dW = torch.empty((Ko * Kd * C, H), dtype=torch.float32, device=d_pre.device)
         ws = ops._scratch(lib.mpgcn_bdgcn_part_bwd_workspace_bytes(B, N, C, H, int(dynamic), prec, pp), d_pre.device)
+        ex = _lib.BdgcnExtras()
+        ex.go_prepared, ex.gd_prepared = ops._ptr(preps[0]), ops._ptr(preps[1])
+        ex.d_pre_f16, ex.d_pre_scale2 = ops._ptr(d_pre16), ops._ptr(scale2)
         with torch.cuda.device(d_pre.device):
-            _lib.check(lib.mpgcn_bdgcn_backward_part(d_pre.data_ptr(), Go.data_ptr(), Gd.data_ptr(), int(dynamic), W.data_ptr(), saved.data_ptr(),
-                                                     ops._ptr(dX), dW.data_ptr(), ws.data_ptr(), ws.numel(), B, N, C, H, prec, pp, None,
-                                                     ops._stream()), "bdgcn_backward_part")
+            _lib.check(lib.mpgcn_bdgcn_backward_part(None if d_pre16 is not None else d_pre.data_ptr(), Go.data_ptr(), Gd.data_ptr(), int(dynamic),
+                                                     W.data_ptr(), saved.data_ptr(), ops._ptr(dX), dW.data_ptr(), ws.data_ptr(), ws.numel(), B, N, C, H,
+                                                     prec, pp, ctypes.addressof(ex), ops._stream()), "bdgcn_backward_part")
         return dX, dW
 
     def bias_act(self, pre, bias, act):
@@ -135,6 +152,25 @@ class CudaEngine:
                                                        ops._stream()), "relu_backward_scatter")
         return db
 
+    def absmax(self, x):
+        lib = _lib.load()
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.mpgcn_absmax(x.data_ptr(), x.numel(), out.data_ptr(), ops._stream()), "absmax")
+        return out
+
+    def relu_backward_scatter_f16(self, d_out, out, act, ptrs, N, row0, want_db, absmax):
+        """fp16 flavour: -> (db or None, scale2 [S, 1/S]); every buffer at `ptrs` (fp16 [B,N,N,H]) receives fp16(S * masked d_out rows)"""
+        lib = _lib.load()
+        B, rows, _, H = d_out.shape
+        db = torch.empty(H, dtype=torch.float32, device=d_out.device) if want_db else None
+        scale2 = torch.empty(2, dtype=torch.float32, device=d_out.device)
+        arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        with torch.cuda.device(d_out.device):
+            _lib.check(lib.mpgcn_relu_backward_scatter_f16(d_out.data_ptr(), out.data_ptr(), int(act), arr, len(ptrs), ops._ptr(db), absmax.data_ptr(),
+                                                           scale2.data_ptr(), B, N, row0, rows, H, ops._stream()), "relu_backward_scatter_f16")
+        return db, scale2
+
     def lstm_last(self, x_seq, lstm, precision):
         return ops.lstm_last(x_seq, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0, precision=precision)
 
@@ -167,15 +203,16 @@ class PeerExchange:
         self.bufs = {}            # (direction, parity, numel) -> (tensor, handle)
         self.count = {"fwd": 0, "bwd": 0}
 
-    def next(self, direction, shape):
+    def next(self, direction, shape, dtype=torch.float32):
         """-> (tensor [shape] in this rank's symmetric buffer, handle); alternates between two buffers per direction"""
         numel = 1
         for d in shape:
             numel *= d
-        key = (direction, self.count[direction] & 1, numel)
+        self.count.setdefault(direction, 0)
+        key = (direction, self.count[direction] & 1, numel, dtype)
         self.count[direction] += 1
         if key not in self.bufs:
-            t = self.symm_mem.empty(numel, dtype=torch.float32, device=self.device)
+            t = self.symm_mem.empty(numel, dtype=dtype, device=self.device)
             hdl = self.symm_mem.rendezvous(t, self.group)            # collective: every rank allocates in the same order
             self.bufs[key] = (t, hdl)
         t, hdl = self.bufs[key]
@@ -197,9 +234,7 @@ def enable_peer_exchange(plan, device) -> bool:
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=plan.group)
     if int(flag.item()) == 1:
         try:
-            px.next("fwd", (1,))                       # smoke: one tiny rendezvous + barrier, so that a failure shows up here
-            px.bufs[("fwd", 0, 1)][1].barrier()
-            px.count["fwd"] = 0
+            px.next("probe", (4,))[1].barrier()        # smoke: one tiny rendezvous + barrier, so that a failure shows up here
             plan.peer = px
         except Exception as e:
             plan.peer = None
@@ -303,7 +338,11 @@ class _RowShardLayerFn(torch.autograd.Function):
             # peer-memory exchange: the whole batch in one part call, partial written straight into the symmetric buffer,
             # one barrier, then the reduce-scatter + bias + ReLU kernel reads this rank's rows from every rank's buffer
             buf, hdl = plan.peer.next("fwd", (B, N, N, H))
-            _, saved = _ENGINE.forward_part(Xc, Goc, Gdc, dynamic, Wc, N, plan.row_lo, K, K, prec, keep, out=buf)
+            planes = (B if dynamic else 1) * K
+            go_p = _ENGINE.prepared(G_o, Goc, planes, N, prec)
+            preps = (go_p, go_p if G_d is G_o else _ENGINE.prepared(G_d, Gdc, planes, N, prec))
+            ctx.preps = preps
+            _, saved = _ENGINE.forward_part(Xc, Goc, Gdc, dynamic, Wc, N, plan.row_lo, K, K, prec, keep, out=buf, preps=preps)
             hdl.barrier()
             out = _ENGINE.rows_reduce_bias_act(list(hdl.buffer_ptrs), B, N, plan.row_lo, rows, H, None if b is None else _f32c(b), act, X.device)
             ctx.meta = (dynamic, act, prec, b is not None, N, K, C, keep)
@@ -337,11 +376,25 @@ class _RowShardLayerFn(torch.autograd.Function):
             raise RuntimeError("mpgcn_b200.shard: backward called but forward ran without requires_grad inputs")
         B, H = d_out.shape[0], d_out.shape[-1]
         if plan.peer is not None:
-            d_pre, hdl = plan.peer.next("bwd", (B, N, N, H))
-            db = _ENGINE.relu_backward_scatter(_f32c(d_out), out, act, list(hdl.buffer_ptrs), N, plan.row_lo, has_bias)
-            hdl.barrier()
-            dX, dW = _ENGINE.backward_part(d_pre, Goc, Gdc, dynamic, Wc, ctx.stash[0], N, plan.row_lo, plan.rows, K, K, C, prec, ctx.needs_input_grad[0])
+            d_out = _f32c(d_out)
+            if prec == _lib.PREC_FP16_TC:
+                # tensor-core path: the gathered dPre travels as fp16 (what the contraction reads anyway), scaled by ONE power of two
+                # derived from the global max|dOut| -- half the bytes, and no rank casts / scans the gathered tensor
+                amax = _ENGINE.absmax(d_out)
+                dist.all_reduce(amax, op=dist.ReduceOp.MAX, group=plan.group)
+                d_pre16, hdl = plan.peer.next("bwd16", (B, N, N, H), torch.float16)
+                db, scale2 = _ENGINE.relu_backward_scatter_f16(d_out, out, act, list(hdl.buffer_ptrs), N, plan.row_lo, has_bias, amax)
+                hdl.barrier()
+                dX, dW = _ENGINE.backward_part(None, Goc, Gdc, dynamic, Wc, ctx.stash[0], N, plan.row_lo, plan.rows, K, K, C, prec,
+                                               ctx.needs_input_grad[0], preps=ctx.preps, d_pre16=d_pre16, scale2=scale2)
+            else:
+                d_pre, hdl = plan.peer.next("bwd", (B, N, N, H))
+                db = _ENGINE.relu_backward_scatter(d_out, out, act, list(hdl.buffer_ptrs), N, plan.row_lo, has_bias)
+                hdl.barrier()
+                dX, dW = _ENGINE.backward_part(d_pre, Goc, Gdc, dynamic, Wc, ctx.stash[0], N, plan.row_lo, plan.rows, K, K, C, prec,
+                                               ctx.needs_input_grad[0])
             ctx.stash = None
+            ctx.preps = None
             return dX, None, None, dW, db, None, None, None, None, None
         d_pre_slab, db = _ENGINE.relu_backward(_f32c(d_out), out, act, has_bias)       # mask + bias gradient of the rank's own rows
         d_pre = d_pre_slab.new_empty((B, N, N, H))

@@ -122,3 +122,55 @@ def test_sharded_model_nccl_world2(kind, peer, tmp_path):
     for row in res["rows"]:
         record_parity(row["what"], row["linf"], row["l2"], row["tol"])
         assert row["linf"] <= row["tol"] and row["l2"] <= row["tol"], row
+
+
+def test_peer_exchange_kernels_on_one_gpu(cuda_device):
+    """`mpgcn_rows_reduce_bias_act`, `mpgcn_relu_backward_scatter(_f16)` and the prepared-fp16-dPre entry of `backward_part`, with the g
+    "ranks'" buffers all on one GPU (the kernels only see pointers): reduce-scatter + bias + ReLU, mask + all-gather, and the fp16
+    flavour bit-identical to the fp32 route through the library's own cast."""
+    dev = cuda_device
+    torch.manual_seed(3)
+    B, N, H, g, K = 2, 136, 32, 4, 3
+    rows = N // g
+    eng = shard.CudaEngine()
+    parts = [torch.randn(B, N, N, H, device=dev) for _ in range(g)]
+    bias = torch.randn(H, device=dev)
+    for r in range(g):
+        out = eng.rows_reduce_bias_act([p.data_ptr() for p in parts], B, N, r * rows, rows, H, bias, 1, dev)
+        want = torch.relu(torch.stack([p[:, r * rows:(r + 1) * rows] for p in parts]).sum(0) + bias)
+        torch.testing.assert_close(out, want, rtol=1e-6, atol=1e-6)
+    # scatter (fp32): every destination receives the masked rows, nothing else is touched
+    r = 2
+    d_out = torch.randn(B, rows, N, H, device=dev) * 1e-5
+    out_slab = torch.relu(torch.randn(B, rows, N, H, device=dev))
+    dsts = [torch.full((B, N, N, H), 7.0, device=dev) for _ in range(g)]
+    db = eng.relu_backward_scatter(d_out, out_slab, 1, [d.data_ptr() for d in dsts], N, r * rows, True)
+    want = d_out * (out_slab > 0)
+    for d in dsts:
+        assert torch.equal(d[:, r * rows:(r + 1) * rows], want)
+        assert float((d[:, :r * rows] - 7.0).abs().max()) == 0.0 and float((d[:, (r + 1) * rows:] - 7.0).abs().max()) == 0.0
+    torch.testing.assert_close(db, want.reshape(-1, H).sum(0), rtol=1e-4, atol=1e-9)
+    # scatter (fp16): S = 2^k with S * absmax in [16, 32)
+    amax = eng.absmax(d_out)
+    assert float(amax) == float(d_out.abs().max())
+    dsts16 = [torch.zeros(B, N, N, H, device=dev, dtype=torch.float16) for _ in range(g)]
+    db16, scale2 = eng.relu_backward_scatter_f16(d_out, out_slab, 1, [d.data_ptr() for d in dsts16], N, r * rows, True, amax)
+    S = float(scale2[0])
+    assert 16.0 <= S * float(amax) < 32.0 and abs(np.log2(S) - round(np.log2(S))) < 1e-9 and float(scale2[1]) == 1.0 / S
+    for d in dsts16:
+        assert torch.equal(d[:, r * rows:(r + 1) * rows], (want * S).to(torch.float16))
+    torch.testing.assert_close(db16, db, rtol=1e-5, atol=1e-9)
+    # backward_part fed the prepared fp16 dPre == backward_part casting the fp32 dPre itself (same S, same bits)
+    X = torch.tanh(torch.randn(B, rows, N, 32, device=dev))
+    G = torch.randn(K, N, N, device=dev) / N ** 0.5
+    W = torch.randn(K * K * 32, 32, device=dev) * 0.05
+    _, saved = eng.forward_part(X, G, G, False, W, N, r * rows, K, K, 1, True)
+    d_pre = torch.randn(B, N, N, H, device=dev) * 1e-5
+    am = eng.absmax(d_pre)
+    full16 = torch.zeros(B, N, N, H, device=dev, dtype=torch.float16)
+    sc = None
+    for rr in range(g):       # fill the "gathered" fp16 tensor slab by slab, as g ranks would
+        _, sc = eng.relu_backward_scatter_f16(d_pre[:, rr * rows:(rr + 1) * rows].contiguous(), out_slab, 0, [full16.data_ptr()], N, rr * rows, False, am)
+    dX_a, dW_a = eng.backward_part(d_pre, G, G, False, W, saved, N, r * rows, rows, K, K, 32, 1, True)
+    dX_b, dW_b = eng.backward_part(None, G, G, False, W, saved, N, r * rows, rows, K, K, 32, 1, True, d_pre16=full16, scale2=sc)
+    assert torch.equal(dX_a, dX_b) and torch.equal(dW_a, dW_b)
