@@ -491,7 +491,8 @@ def run_ours(a):
     roofline_step = {"bound": "tensor", "what": "algorithmic BDGCN flops of the step (6 layers x batch x F_fwd+bwd) / step time, per GPU; the LSTM, head and "
                                                 "exchange time count, their flops do not", "achieved": sach, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": sach / peaks["tflops"], "with_lstm_flops": (step_fl + lstm_fl / a.steps) / (ms_per_step * 1e-3) / 1e12,
-                     "lstm_ms_per_step": (prof["LSTM_FWD"]["ms"] + prof["LSTM_BWD"]["ms"]) / a.steps, "head_ms_per_step": prof["HEAD"]["ms"] / a.steps}
+                     "lstm_ms_per_step": (prof["LSTM_FWD"]["ms"] + prof["LSTM_BWD"]["ms"]) / a.steps, "head_ms_per_step": prof["HEAD"]["ms"] / a.steps,
+                     "exchange_kernels_ms_per_step": prof["EXCHANGE"]["ms"] / a.steps}
     gpu_launches = sum(v["launches"] for t, v in prof.items() if t not in _lib.REGION_TAGS)
 
     cpu_baseline = None

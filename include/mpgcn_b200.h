@@ -242,6 +242,7 @@ MPGCN_API int mpgcn_head_backward(const float* const* g, const float* w, const f
  * Tags 11 (mpgcn_bdgcn_forward*), 12 (mpgcn_bdgcn_backward*) and 13 (mpgcn_head_*) are REGIONS: whole C-ABI calls -- every
  * kernel of the call and the gaps between them -- with `launches` counting calls and `flops` the layer's algorithmic work
  * (per sample F_fwd = 2KN^3(C+H) + 2K^2N^2CH, F_bwd = 2KN^3(C+H) + 4K^2N^2CH); bench.py's `roofline_layer`.
+ * Tag 14: the peer-memory exchange kernels of the row shard (mpgcn_rows_reduce_bias_act, mpgcn_relu_backward_scatter[_f16]), timed.
  * Thread-safe: counters behind a mutex, the open bracket is per calling thread. */
 MPGCN_API void mpgcn_profile_enable(int on);
 MPGCN_API void mpgcn_profile_reset(void);

@@ -134,7 +134,7 @@ def check(code: int, what: str) -> None:
 
 
 PROFILE_TAGS = ("FWD_A", "FWD_MIX", "FWD_B", "BWD_V", "BWD_DW", "BWD_MIX", "BWD_DX", "SIMT_GEMM", "ELEMENTWISE", "LSTM_FWD", "LSTM_BWD",
-                "LAYER_FWD", "LAYER_BWD", "HEAD")
+                "LAYER_FWD", "LAYER_BWD", "HEAD", "EXCHANGE")
 REGION_TAGS = ("LAYER_FWD", "LAYER_BWD", "HEAD")      # whole C-ABI calls (their `launches` count calls, not kernels)
 
 

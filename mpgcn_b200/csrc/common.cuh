@@ -252,6 +252,7 @@ enum ProfTag {
   PROF_SIMT_GEMM, PROF_ELEMENTWISE, PROF_LSTM_FWD, PROF_LSTM_BWD,
   // regions, not kernels: a whole C-ABI call (every kernel of it, the gaps between them included); they count calls, not launches
   PROF_LAYER_FWD, PROF_LAYER_BWD, PROF_HEAD,
+  PROF_EXCHANGE,      // kernels: the peer-memory exchange steps of the row shard (rows_reduce_bias_act, relu_backward_scatter[_f16])
   PROF_NUM_TAGS
 };
 constexpr int PROF_FIRST_REGION_TAG = PROF_LAYER_FWD;

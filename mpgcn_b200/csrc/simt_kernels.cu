@@ -526,9 +526,10 @@ int rows_reduce_bias_act(float* out, const float* const* parts, int g, const flo
     pp.p[j] = const_cast<float*>(parts[j]);
   }
   const size_t slab4 = (size_t)rows * N * H / 4, full4 = (size_t)N * N * H / 4, off4 = (size_t)row0 * N * H / 4;
-  prof_count(PROF_ELEMENTWISE);
   dim3 grid(grid_for(slab4, 256), (unsigned)B);
+  prof_begin(PROF_EXCHANGE, 0.0, s);
   rows_reduce_bias_act_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(out), pp, g, bias, act, slab4, full4, off4, H / 4);
+  prof_end(s);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -576,10 +577,11 @@ int relu_backward_scatter(const float* d_out, const float* out, int act, float* 
   }
   if (db) MPGCN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * H, s));
   const size_t slab4 = (size_t)rows * N * H / 4, full4 = (size_t)N * N * H / 4, off4 = (size_t)row0 * N * H / 4;
-  prof_count(PROF_ELEMENTWISE);
   dim3 grid(grid_for(slab4, 256), (unsigned)B);
+  prof_begin(PROF_EXCHANGE, 0.0, s);
   relu_backward_scatter_kernel<<<grid, 256, 4 * 256 * sizeof(float), s>>>(reinterpret_cast<const float4*>(d_out), reinterpret_cast<const float4*>(out),
                                                                          act, pp, g, db, slab4, full4, off4, H / 4);
+  prof_end(s);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -632,10 +634,11 @@ int relu_backward_scatter_f16(const float* d_out, const float* out, int act, __h
   prof_count(PROF_ELEMENTWISE);
   make_scale_kernel<<<1, 1, 0, s>>>(scale2, absmax);
   const size_t slab4 = (size_t)rows * N * H / 4, full4 = (size_t)N * N * H / 4, off4 = (size_t)row0 * N * H / 4;
-  prof_count(PROF_ELEMENTWISE);
   dim3 grid(grid_for(slab4, 256), (unsigned)B);
+  prof_begin(PROF_EXCHANGE, 0.0, s);
   relu_backward_scatter_f16_kernel<<<grid, 256, 4 * 256 * sizeof(float), s>>>(reinterpret_cast<const float4*>(d_out), reinterpret_cast<const float4*>(out),
                                                                              act, pp, g, db, scale2, slab4, full4, off4, H / 4);
+  prof_end(s);
   MPGCN_CUDA(cudaGetLastError());
   return 0;
 }

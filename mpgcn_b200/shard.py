@@ -47,6 +47,8 @@ class ShardPlan:
         self.d_lo, self.d_hi = shard_range(K, rank, world) if kind == "k" else (0, K)
         self.Kd = self.d_hi - self.d_lo
         self.peer = None          # PeerExchange once enable_peer_exchange() succeeded (row shard over NVLink peer memory)
+        self.branch = 0           # which model branch is being evaluated (selects that branch's pair of exchange buffers)
+        self.streams = None       # one CUDA stream per branch (sharded_forward): the branches are independent until the head
 
     def describe(self) -> dict:
         d = {"kind": self.kind, "world": self.world, "rows_per_rank": self.rows,
@@ -201,7 +203,7 @@ class PeerExchange:
         self.symm_mem, self.plan, self.device = symm_mem, plan, device
         self.group = plan.group if plan.group is not None else dist.group.WORLD
         self.bufs = {}            # (direction, parity, numel) -> (tensor, handle)
-        self.count = {"fwd": 0, "bwd": 0}
+        self.count = {}
 
     def next(self, direction, shape, dtype=torch.float32):
         """-> (tensor [shape] in this rank's symmetric buffer, handle); alternates between two buffers per direction"""
@@ -321,6 +323,14 @@ def _f32c(t):
     return t.detach().to(dtype=torch.float32).contiguous()
 
 
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 class _RowShardLayerFn(torch.autograd.Function):
     """Sample by sample, so that the exchange of sample b overlaps the contractions of sample b + 1 (forward: partial pre of b is
     reduce-scattered while b + 1 is computed; backward: every dPre slab is put on the wire up front and the gradient
@@ -337,7 +347,8 @@ class _RowShardLayerFn(torch.autograd.Function):
         if plan.peer is not None:
             # peer-memory exchange: the whole batch in one part call, partial written straight into the symmetric buffer,
             # one barrier, then the reduce-scatter + bias + ReLU kernel reads this rank's rows from every rank's buffer
-            buf, hdl = plan.peer.next("fwd", (B, N, N, H))
+            buf, hdl = plan.peer.next(("fwd", plan.branch), (B, N, N, H))
+            ctx.branch = plan.branch
             planes = (B if dynamic else 1) * K
             go_p = _ENGINE.prepared(G_o, Goc, planes, N, prec)
             preps = (go_p, go_p if G_d is G_o else _ENGINE.prepared(G_d, Gdc, planes, N, prec))
@@ -382,13 +393,13 @@ class _RowShardLayerFn(torch.autograd.Function):
                 # derived from the global max|dOut| -- half the bytes, and no rank casts / scans the gathered tensor
                 amax = _ENGINE.absmax(d_out)
                 dist.all_reduce(amax, op=dist.ReduceOp.MAX, group=plan.group)
-                d_pre16, hdl = plan.peer.next("bwd16", (B, N, N, H), torch.float16)
+                d_pre16, hdl = plan.peer.next(("bwd16", ctx.branch), (B, N, N, H), torch.float16)
                 db, scale2 = _ENGINE.relu_backward_scatter_f16(d_out, out, act, list(hdl.buffer_ptrs), N, plan.row_lo, has_bias, amax)
                 hdl.barrier()
                 dX, dW = _ENGINE.backward_part(None, Goc, Gdc, dynamic, Wc, ctx.stash[0], N, plan.row_lo, plan.rows, K, K, C, prec,
                                                ctx.needs_input_grad[0], preps=ctx.preps, d_pre16=d_pre16, scale2=scale2)
             else:
-                d_pre, hdl = plan.peer.next("bwd", (B, N, N, H))
+                d_pre, hdl = plan.peer.next(("bwd", ctx.branch), (B, N, N, H))
                 db = _ENGINE.relu_backward_scatter(d_out, out, act, list(hdl.buffer_ptrs), N, plan.row_lo, has_bias)
                 hdl.barrier()
                 dX, dW = _ENGINE.backward_part(d_pre, Goc, Gdc, dynamic, Wc, ctx.stash[0], N, plan.row_lo, plan.rows, K, K, C, prec,
@@ -503,18 +514,33 @@ def sharded_forward(model, plan: ShardPlan, x_slab, G_static, G_dyn):
         G_list = [(G_static, G_static[plan.d_lo:plan.d_hi]), G_dyn]       # static supports: origin side whole, destination side sliced
     else:
         G_list = [G_static, G_dyn]
+    # The branches are independent until the head: each runs on its own CUDA stream, so that the exchange steps of one branch
+    # (NVLink-bound kernels that leave the SMs mostly idle) overlap the contractions of the other.  autograd replays every
+    # backward node on the stream of its forward, so the backward overlaps the same way.
+    use_streams = x_slab.is_cuda
+    cur = torch.cuda.current_stream() if use_streams else None
+    if use_streams and plan.streams is None:
+        plan.streams = [torch.cuda.Stream(device=x_slab.device) for _ in range(model.M)]
     feats = []
     for m in range(model.M):
         branch = model.branch_models[m]
-        h = _ENGINE.lstm_last(x_slab, branch['temporal'], model.lstm_precision).reshape(B, rows, N, C)
-        g = h if plan.kind == "row" else _AllGatherRowsFn.apply(h, plan)
-        Gm = G_list[m]
-        for layer in branch['spatial']:
-            if plan.kind == "k" and isinstance(Gm, tuple) and Gm[0].dim() == 3:
-                g = _static_k_layer(layer, g, Gm, plan)
-            else:
-                g = sharded_bdgcn(layer, g, Gm, plan)
+        plan.branch = m
+        if use_streams:
+            plan.streams[m].wait_stream(cur)
+        with (torch.cuda.stream(plan.streams[m]) if use_streams else _nullcontext()):
+            h = _ENGINE.lstm_last(x_slab, branch['temporal'], model.lstm_precision).reshape(B, rows, N, C)
+            g = h if plan.kind == "row" else _AllGatherRowsFn.apply(h, plan)
+            Gm = G_list[m]
+            for layer in branch['spatial']:
+                if plan.kind == "k" and isinstance(Gm, tuple) and Gm[0].dim() == 3:
+                    g = _static_k_layer(layer, g, Gm, plan)
+                else:
+                    g = sharded_bdgcn(layer, g, Gm, plan)
         feats.append(g)
+    if use_streams:
+        for m in range(model.M):
+            cur.wait_stream(plan.streams[m])
+            feats[m].record_stream(cur)
     fcs = [model.branch_models[m]['fc'][0] for m in range(model.M)]
     w = torch.cat([fc.weight for fc in fcs], dim=0)
     b = torch.cat([fc.bias for fc in fcs], dim=0)
