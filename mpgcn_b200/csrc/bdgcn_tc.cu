@@ -314,6 +314,13 @@ static int run_fwd_b(const BdgcnShape& s, const __half* go16, const __half* u16,
   p.ep.sZ = (long long)N * N * 32; p.ep.sI = (long long)N * 32; p.ep.sR = 32;
   p.ep.m_valid = N; p.ep.r_valid = N;
   p.ep.bias = s.partial ? nullptr : bias; p.ep.relu = s.partial ? 0 : s.act;
+  if (s.partial && s.peer_g > 0) {        // push every row of the partial into its owner's staging slot for this rank (NVLink P2P stores)
+    p.ep.peer_g = s.peer_g; p.ep.peer_rows = N / s.peer_g;
+    p.ep.peer_sZ = (long long)p.ep.peer_rows * N * 32;
+    p.ep.peer_slot = (long long)s.peer_rank * s.B * p.ep.peer_sZ;
+    for (int j = 0; j < s.peer_g; ++j) p.ep.peer_out[j] = s.peer_out[j];
+    p.ep.out16 = nullptr;
+  }
   // pre[b,m,e,:] += sum_o (G_o[m,m] - fp16(G_o[m,m])) * U16[b,o,m,e,:]   (delta_o is zero outside the slab: the row n = m of U
   // exists only for row0 <= m < row0 + R; corr_src is moved so that row index m addresses slab row m - row0)
   p.ep.corr_src = u16 - (long long)s.row0 * N * 32; p.ep.corr_delta = delta_o; p.ep.corr_nseg = K;

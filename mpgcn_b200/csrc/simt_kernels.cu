@@ -516,16 +516,17 @@ __global__ void rows_reduce_bias_act_kernel(float4* __restrict__ out, PeerPtrs p
     out[b * slab4 + i] = acc;
   }
 }
-int rows_reduce_bias_act(float* out, const float* const* parts, int g, const float* bias, int act, int B, int N, int row0, int rows, int H,
-                         cudaStream_t s) {
+int rows_reduce_bias_act(float* out, const float* const* parts, int g, const float* bias, int act, int B, int N, int row0, int rows, int part_rows,
+                         int H, cudaStream_t s) {
   MPGCN_CHECK(g >= 1 && g <= 8, "rows_reduce: %d ranks unsupported (1..8)", g);
+  MPGCN_CHECK(part_rows == N || part_rows == rows, "rows_reduce: part buffers must hold N or `rows` origin rows (got %d)", part_rows);
   MPGCN_CHECK(H % 4 == 0 && row0 >= 0 && rows >= 1 && row0 + rows <= N, "rows_reduce: bad slab rows [%d, %d) of %d, H=%d", row0, row0 + rows, N, H);
   PeerPtrs pp{};
   for (int j = 0; j < g; ++j) {
     MPGCN_CHECK(parts[j] != nullptr && (reinterpret_cast<uintptr_t>(parts[j]) & 15) == 0, "rows_reduce: partial buffer %d null or misaligned", j);
     pp.p[j] = const_cast<float*>(parts[j]);
   }
-  const size_t slab4 = (size_t)rows * N * H / 4, full4 = (size_t)N * N * H / 4, off4 = (size_t)row0 * N * H / 4;
+  const size_t slab4 = (size_t)rows * N * H / 4, full4 = (size_t)part_rows * N * H / 4, off4 = part_rows == N ? (size_t)row0 * N * H / 4 : 0;
   dim3 grid(grid_for(slab4, 256), (unsigned)B);
   prof_begin(PROF_EXCHANGE, 0.0, s);
   rows_reduce_bias_act_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(out), pp, g, bias, act, slab4, full4, off4, H / 4);

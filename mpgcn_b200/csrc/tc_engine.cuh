@@ -51,6 +51,13 @@ struct Epilogue {
   const float* corr_delta;
   long long cZ, cI, cR, cSeg;
   int corr_nseg;             // <= 8
+  // optional PUSH of a partial result into peer memory (origin-row shard, FWD_B): row i belongs to owner i / peer_rows and is
+  // stored at peer_out[owner] + peer_slot + z * peer_sZ + (i % peer_rows) * sI (+ r * sR + channel) -- the owner's staging slot
+  // for THIS rank, over NVLink when the owner is another GPU.  The transfer rides in the epilogue, tile by tile, under the MMAs
+  // of the next tile; peer_g == 0: plain store to `out`.
+  float* peer_out[8];
+  int peer_g, peer_rows;
+  long long peer_slot, peer_sZ;
 };
 
 struct alignas(64) GemmParams {
@@ -146,8 +153,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__device__ __forceinline__ void store_chunk(const Epilogue& ep, float alpha, const float* sbias, long long off, uint32_t (&acc)[32],
-                                            float& amax) {
+__device__ __forceinline__ void store_chunk(const Epilogue& ep, void* out_ptr, float alpha, const float* sbias, long long off,
+                                            uint32_t (&acc)[32], float& amax) {
   float v[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
@@ -161,14 +168,14 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, float alpha, con
     for (int c = 0; c < 32; ++c) amax = fmaxf(amax, fabsf(v[c]));
   }
   if (ep.out_f16) {        // 64 bytes per row and chunk: two 32-byte stores
-    __half* dst = reinterpret_cast<__half*>(ep.out) + off;
+    __half* dst = reinterpret_cast<__half*>(out_ptr) + off;
 #pragma unroll
     for (int q = 0; q < 2; ++q)
       st_global_256(dst + 16 * q, pack_h2(v[16 * q + 0], v[16 * q + 1]), pack_h2(v[16 * q + 2], v[16 * q + 3]),
                     pack_h2(v[16 * q + 4], v[16 * q + 5]), pack_h2(v[16 * q + 6], v[16 * q + 7]), pack_h2(v[16 * q + 8], v[16 * q + 9]),
                     pack_h2(v[16 * q + 10], v[16 * q + 11]), pack_h2(v[16 * q + 12], v[16 * q + 13]), pack_h2(v[16 * q + 14], v[16 * q + 15]));
   } else {                 // 128 bytes per row and chunk: four 32-byte stores
-    float* dst = reinterpret_cast<float*>(ep.out) + off;
+    float* dst = reinterpret_cast<float*>(out_ptr) + off;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       st_global_256(dst + 8 * q, __float_as_uint(v[8 * q + 0]), __float_as_uint(v[8 * q + 1]), __float_as_uint(v[8 * q + 2]),
@@ -354,7 +361,13 @@ __global__ void __launch_bounds__(kThreads1, 1) contract_kernel(const __grid_con
       tc_fence_after();
       const int i = mt * 128 + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAccCols;
-      const long long base = (long long)z * p.ep.sZ + (long long)i * p.ep.sI;
+      long long base = (long long)z * p.ep.sZ + (long long)i * p.ep.sI;
+      void* out_ptr = p.ep.out;
+      if (p.ep.peer_g > 0 && i < p.ep.m_valid) {      // push this row of the partial result into its owner's staging slot
+        const int owner = i / p.ep.peer_rows;
+        out_ptr = p.ep.peer_out[owner];
+        base = p.ep.peer_slot + (long long)z * p.ep.peer_sZ + (long long)(i - owner * p.ep.peer_rows) * p.ep.sI;
+      }
       float dl[8];
       long long cbase = 0;
       bool any_corr = false;
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(kThreads1, 1) contract_kernel(const __grid_con
               }
             }
           }
-          store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs, amax);
+          store_chunk(p.ep, out_ptr, alpha, sbias, base + (long long)r * p.ep.sR, regs, amax);
         }
       }
       tc_fence_before();
@@ -578,7 +591,13 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
       tc_fence_after();
       const int i = mt * 256 + (int)rank * 128 + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * kAccCols;
-      const long long base = (long long)z * p.ep.sZ + (long long)i * p.ep.sI;
+      long long base = (long long)z * p.ep.sZ + (long long)i * p.ep.sI;
+      void* out_ptr = p.ep.out;
+      if (p.ep.peer_g > 0 && i < p.ep.m_valid) {      // push this row of the partial result into its owner's staging slot
+        const int owner = i / p.ep.peer_rows;
+        out_ptr = p.ep.peer_out[owner];
+        base = p.ep.peer_slot + (long long)z * p.ep.peer_sZ + (long long)(i - owner * p.ep.peer_rows) * p.ep.sI;
+      }
       float dl[8];
       long long cbase = 0;
       bool any_corr = false;
@@ -618,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) contract2_kernel(const __grid_con
               }
             }
           }
-          store_chunk(p.ep, alpha, sbias, base + (long long)r * p.ep.sR, regs, amax);
+          store_chunk(p.ep, out_ptr, alpha, sbias, base + (long long)r * p.ep.sR, regs, amax);
         }
       }
       tc_fence_before();

@@ -65,8 +65,14 @@ class ShardPlan:
 # compute back end (the C ABI); tests replace it by a CPU stand-in to exercise the exchange logic under gloo
 # ------------------------------------------------------------------------------------------------
 class CudaEngine:
-    def _part(self, row0, rows, Ko, Kd):
-        return _lib.BdgcnPart(row0, rows, Ko, Kd)
+    def _part(self, row0, rows, Ko, Kd, push=None):
+        part = _lib.BdgcnPart(row0, rows, Ko, Kd)
+        if push is not None:            # (rank, [g staging-buffer pointers]): FWD_B pushes its partial into peer memory
+            part.peer_rank, ptrs = push
+            part.peer_g = len(ptrs)
+            for j, ptr in enumerate(ptrs):
+                part.peer_out[j] = ptr
+        return part
 
     def prepared(self, G, Gc, planes, N, prec):
         """fp16 staging of a support stack, converted once per tensor (mpgcn_b200.ops cache) and reused by every layer, forward and
@@ -76,21 +82,22 @@ class CudaEngine:
         with torch.cuda.device(Gc.device):
             return ops._prepared_supports(_lib.load(), G, Gc, planes, N)
 
-    def forward_part(self, X, Go, Gd, dynamic, W, N, row0, Ko, Kd, prec, keep, out=None, preps=(None, None)):
-        """X [B,rows,N,C] -> (raw partial pre-activation [B,N,N,H] (written into `out` if given), Z stash or None)"""
+    def forward_part(self, X, Go, Gd, dynamic, W, N, row0, Ko, Kd, prec, keep, out=None, preps=(None, None), push=None):
+        """X [B,rows,N,C] -> (raw partial pre-activation [B,N,N,H] (written into `out` if given; None with `push`, which sends every
+        output row straight into its owner's staging buffer from the contraction's epilogue), Z stash or None)"""
         lib = _lib.load()
         ops._require_cuda(X, "X")
         B, rows, _, C = X.shape
         H = W.shape[1]
-        part = self._part(row0, rows, Ko, Kd)
+        part = self._part(row0, rows, Ko, Kd, push)
         pp = ctypes.addressof(part)
-        pre = out if out is not None else torch.empty((B, N, N, H), dtype=torch.float32, device=X.device)
+        pre = None if push is not None else (out if out is not None else torch.empty((B, N, N, H), dtype=torch.float32, device=X.device))
         saved = ops._scratch(lib.mpgcn_bdgcn_part_saved_bytes(B, N, C, H, prec, pp), X.device) if keep else None
         ws = ops._scratch(lib.mpgcn_bdgcn_part_fwd_workspace_bytes(B, N, C, H, int(dynamic), prec, pp), X.device)
         ex = _lib.BdgcnExtras()
         ex.go_prepared, ex.gd_prepared = ops._ptr(preps[0]), ops._ptr(preps[1])
         with torch.cuda.device(X.device):
-            _lib.check(lib.mpgcn_bdgcn_forward_part(X.data_ptr(), Go.data_ptr(), Gd.data_ptr(), int(dynamic), W.data_ptr(), pre.data_ptr(),
+            _lib.check(lib.mpgcn_bdgcn_forward_part(X.data_ptr(), Go.data_ptr(), Gd.data_ptr(), int(dynamic), W.data_ptr(), ops._ptr(pre),
                                                     ops._ptr(saved), ws.data_ptr(), ws.numel(), B, N, C, H, prec, pp, ctypes.addressof(ex),
                                                     ops._stream()), "bdgcn_forward_part")
         return pre, saved
@@ -133,14 +140,15 @@ class CudaEngine:
                                                d_out.shape[-1], ops._stream()), "relu_backward")
         return d_pre, db
 
-    def rows_reduce_bias_act(self, ptrs, B, N, row0, rows, H, bias, act, device):
-        """out [B,rows,N,H] = act(sum over the g buffers at `ptrs` (own + peers', [B,N,N,H]) of the rank's rows + bias)"""
+    def rows_reduce_bias_act(self, ptrs, B, N, row0, rows, H, bias, act, device, slots=False):
+        """out [B,rows,N,H] = act(sum over the g buffers at `ptrs` of the rank's rows + bias); the buffers are whole [B,N,N,H]
+        partials (own + peers') or, with slots=True, the local staging slots [B,rows,N,H] the peer push filled"""
         lib = _lib.load()
         out = torch.empty((B, rows, N, H), dtype=torch.float32, device=device)
         arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
         with torch.cuda.device(device):
-            _lib.check(lib.mpgcn_rows_reduce_bias_act(out.data_ptr(), arr, len(ptrs), ops._ptr(bias), int(act), B, N, row0, rows, H, ops._stream()),
-                       "rows_reduce_bias_act")
+            _lib.check(lib.mpgcn_rows_reduce_bias_act(out.data_ptr(), arr, len(ptrs), ops._ptr(bias), int(act), B, N, row0, rows,
+                                                      rows if slots else N, H, ops._stream()), "rows_reduce_bias_act")
         return out
 
     def relu_backward_scatter(self, d_out, out, act, ptrs, N, row0, want_db):
@@ -219,6 +227,12 @@ class PeerExchange:
             self.bufs[key] = (t, hdl)
         t, hdl = self.bufs[key]
         return t.view(shape), hdl
+
+
+def _push_enabled() -> bool:
+    """MPGCN_B200_SHARD_PUSH=0: pull the rows in mpgcn_rows_reduce_bias_act instead of pushing them from the FWD_B epilogue (A/B)"""
+    import os
+    return os.environ.get("MPGCN_B200_SHARD_PUSH", "0") == "1"      # default off until measured (tools/gpu_round2_multi_d.sh)
 
 
 def enable_peer_exchange(plan, device) -> bool:
@@ -353,9 +367,20 @@ class _RowShardLayerFn(torch.autograd.Function):
             go_p = _ENGINE.prepared(G_o, Goc, planes, N, prec)
             preps = (go_p, go_p if G_d is G_o else _ENGINE.prepared(G_d, Gdc, planes, N, prec))
             ctx.preps = preps
-            _, saved = _ENGINE.forward_part(Xc, Goc, Gdc, dynamic, Wc, N, plan.row_lo, K, K, prec, keep, out=buf, preps=preps)
-            hdl.barrier()
-            out = _ENGINE.rows_reduce_bias_act(list(hdl.buffer_ptrs), B, N, plan.row_lo, rows, H, None if b is None else _f32c(b), act, X.device)
+            bias = None if b is None else _f32c(b)
+            if prec == _lib.PREC_FP16_TC and _push_enabled():
+                # fused compute + exchange: the FWD_B epilogue stores every output row into its OWNER's staging slot for this rank
+                # (NVLink P2P stores, tile by tile under the MMAs); after the barrier each rank sums its g local slots
+                _, saved = _ENGINE.forward_part(Xc, Goc, Gdc, dynamic, Wc, N, plan.row_lo, K, K, prec, keep, preps=preps,
+                                                push=(plan.rank, list(hdl.buffer_ptrs)))
+                hdl.barrier()
+                slot = B * rows * N * H * 4
+                out = _ENGINE.rows_reduce_bias_act([buf.data_ptr() + j * slot for j in range(plan.world)], B, N, plan.row_lo, rows, H, bias, act,
+                                                   X.device, slots=True)
+            else:
+                _, saved = _ENGINE.forward_part(Xc, Goc, Gdc, dynamic, Wc, N, plan.row_lo, K, K, prec, keep, out=buf, preps=preps)
+                hdl.barrier()
+                out = _ENGINE.rows_reduce_bias_act(list(hdl.buffer_ptrs), B, N, plan.row_lo, rows, H, bias, act, X.device)
             ctx.meta = (dynamic, act, prec, b is not None, N, K, C, keep)
             ctx.plan = plan
             ctx.stash = [saved]
