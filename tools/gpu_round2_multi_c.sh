@@ -16,6 +16,7 @@ run batch
 run row --shard row
 run row_cfg5 --shard row --workload cfg5 --batch 8
 run k_cfg4 --shard k --workload cfg4
+run row_cfg5_b1 --shard row --workload cfg5 --batch 1
 for f in gpurun_out/r2_final_*_n$N.json; do echo $f; python -c "
 import json,sys
 try:
