@@ -21,6 +21,9 @@ never materialises the `[B*N*N, T, C]` output sequence.
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 from torch import nn
 
@@ -81,6 +84,11 @@ class MPGCN(nn.Module):
         self.lstm_num_layers = lstm_num_layers
         self.gcn_num_layers = gcn_num_layers
         self.lstm_precision = None      # None -> ops.default_precision(); or "auto" / "fp16" / "fp32"
+        # True: evaluate the M branches on M CUDA streams (they are independent until the head, reference MPGCN.py:101-110), so that
+        # the HBM-bound elementwise kernels of one branch run beside the tensor-bound contractions of the other; None -> env
+        # MPGCN_B200_BRANCH_STREAMS (default off)
+        self.branch_streams = None
+        self._streams = None
         self.branch_models = nn.ModuleList()
         for _ in range(self.M):
             branch = nn.ModuleDict()
@@ -111,13 +119,25 @@ class MPGCN(nn.Module):
         assert (len(x_seq.shape) == 5) & (self.num_nodes == x_seq.shape[2] == x_seq.shape[3])
         assert len(G_list) == self.M
         B, N = x_seq.shape[0], self.num_nodes
+        use_streams = self.branch_streams if self.branch_streams is not None else os.environ.get("MPGCN_B200_BRANCH_STREAMS", "0") == "1"
+        use_streams = bool(use_streams) and x_seq.is_cuda and self.M > 1 and not torch.cuda.is_current_stream_capturing()
+        cur = torch.cuda.current_stream() if use_streams else None
+        if use_streams and (self._streams is None or self._streams[0].device != x_seq.device):
+            self._streams = [torch.cuda.Stream(device=x_seq.device) for _ in range(self.M)]
         feats = []
         for m in range(self.M):
             branch = self.branch_models[m]
-            gcn_in = self._temporal(branch['temporal'], x_seq).reshape(B, N, N, self.lstm_hidden_dim)
-            for layer in branch['spatial']:
-                gcn_in = layer(gcn_in, G_list[m])
+            if use_streams:
+                self._streams[m].wait_stream(cur)
+            with (torch.cuda.stream(self._streams[m]) if use_streams else contextlib.nullcontext()):
+                gcn_in = self._temporal(branch['temporal'], x_seq).reshape(B, N, N, self.lstm_hidden_dim)
+                for layer in branch['spatial']:
+                    gcn_in = layer(gcn_in, G_list[m])
             feats.append(gcn_in)
+        if use_streams:
+            for m in range(self.M):
+                cur.wait_stream(self._streams[m])
+                feats[m].record_stream(cur)
         fcs = [self.branch_models[m]['fc'][0] for m in range(self.M)]
         if all(fc.out_features == 1 for fc in fcs) and feats[0].shape[-1] % 4 == 0 and self.M <= 8:
             # Linear(C -> 1) + ReLU per branch and the mean over branches in one fused pass (reference MPGCN.py:107,110)
