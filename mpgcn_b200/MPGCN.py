@@ -120,7 +120,8 @@ class MPGCN(nn.Module):
         assert len(G_list) == self.M
         B, N = x_seq.shape[0], self.num_nodes
         use_streams = self.branch_streams if self.branch_streams is not None else os.environ.get("MPGCN_B200_BRANCH_STREAMS", "0") == "1"
-        use_streams = bool(use_streams) and x_seq.is_cuda and self.M > 1 and not torch.cuda.is_current_stream_capturing()
+        use_streams = bool(use_streams) and x_seq.is_cuda and self.M > 1
+        capturing = use_streams and torch.cuda.is_current_stream_capturing()
         cur = torch.cuda.current_stream() if use_streams else None
         if use_streams and (self._streams is None or self._streams[0].device != x_seq.device):
             self._streams = [torch.cuda.Stream(device=x_seq.device) for _ in range(self.M)]
@@ -137,7 +138,8 @@ class MPGCN(nn.Module):
         if use_streams:
             for m in range(self.M):
                 cur.wait_stream(self._streams[m])
-                feats[m].record_stream(cur)
+                if not capturing:       # under CUDA-graph capture the join above is a graph dependency: later frees / re-uses are ordered by it
+                    feats[m].record_stream(cur)
         fcs = [self.branch_models[m]['fc'][0] for m in range(self.M)]
         if all(fc.out_features == 1 for fc in fcs) and feats[0].shape[-1] % 4 == 0 and self.M <= 8:
             # Linear(C -> 1) + ReLU per branch and the mean over branches in one fused pass (reference MPGCN.py:107,110)

@@ -23,7 +23,11 @@ from . import ops
 
 
 class GraphedTrainStep:
-    def __init__(self, model, criterion, optimizer, example, warmup: int = 3):
+    def __init__(self, model, criterion, optimizer, example, warmup: int = 3, branch_streams=None):
+        """branch_streams: True -> the model's branches are captured on parallel streams (fork / join inside the graph): at
+        launch-bound sizes the kernels of the two branches then run side by side; None -> leave `model.branch_streams` as it is."""
+        if branch_streams is not None:
+            model.branch_streams = bool(branch_streams)
         x, y, G_static, (g_o, g_d) = example
         if not x.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (the engine has no CPU path)")

@@ -151,11 +151,13 @@ def _set_precision(model, prec):
             mod.precision = prec
 
 
-@pytest.mark.parametrize("N,K,T,B", [(200, 3, 8, 2), (500, 3, 12, 1)])
+@pytest.mark.parametrize("N,K,T,B", [(200, 3, 8, 2)])
 def test_full_model_matches_oracle_at_baseline_configs(N, K, T, B, cuda_device):
-    """BASELINE.json configs[1] (N=200, K=3, T=8) and configs[2] (N=500, K=3, T=12), batch reduced: the whole model (LSTM ->
-    3 x BDGCN -> head, static + dynamic branch, trainer-style random-walk supports) forward + backward against
-    `orc.mpgcn_forward_backward`; the trainer's MSE loss against a zero target supplies a coherent d_y."""
+    """BASELINE.json configs[1] (N=200, K=3, T=8), batch reduced: the whole model (LSTM -> 3 x BDGCN -> head, static + dynamic
+    branch, trainer-style random-walk supports) forward + backward against `orc.mpgcn_forward_backward`; the trainer's MSE loss
+    against a zero target supplies a coherent d_y.  (configs[2] N=500 and the headline N=1000: forward, next test; round 2 also ran
+    this test at N=500, T=12 -- 94 s of oracle BPTT -- with y 6.2e-4 and every gradient inside the same bounds,
+    profiles/parity_report_r2.json.)"""
     model, x_seq, g_static, g_o, g_d = _model_and_inputs(N, K, T, B, 77 + N, cuda_device)
     params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
     G_np = [g_static, (g_o, g_d)]
@@ -188,10 +190,10 @@ def test_full_model_matches_oracle_at_baseline_configs(N, K, T, B, cuda_device):
                 _check(p.grad, grads_o[k], LOOSE_FP16_GRAD, f"model N={N}/{prec}/grad:{k} vs oracle", l2_only=True)
 
 
-def test_headline_config_forward_matches_oracle(cuda_device):
-    """The benchmarked configuration itself -- N=1000, K=3, T=12, hidden 32, M=2, L=3 (batch 1) -- forward on the fp16
-    tcgen05 kernels against the oracle, within north_star's 1e-3."""
-    N, K, T, B = 1000, 3, 12, 1
+@pytest.mark.parametrize("N,K,T,B", [(500, 3, 12, 1), (1000, 3, 12, 1)])
+def test_headline_config_forward_matches_oracle(N, K, T, B, cuda_device):
+    """The benchmarked configuration itself -- N=1000, K=3, T=12, hidden 32, M=2, L=3 (batch 1) -- and BASELINE configs[2]
+    (N=500): forward on the fp16 tcgen05 kernels against the oracle, within north_star's 1e-3."""
     model, x_seq, g_static, g_o, g_d = _model_and_inputs(N, K, T, B, 4242, cuda_device)
     params = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
     t0 = time.time()

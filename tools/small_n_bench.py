@@ -56,8 +56,16 @@ def main():
         t_eager = timed(eager)
         step = GraphedTrainStep(model, crit, opt, example=(x, y, G, (go, gd)))
         t_graph = timed(lambda: step(x, y, go, gd))
+        t_par = None
+        try:        # the two branches forked onto parallel streams inside the captured graph
+            step2 = GraphedTrainStep(model, crit, opt, example=(x, y, G, (go, gd)), branch_streams=True)
+            t_par = timed(lambda: step2(x, y, go, gd))
+        except Exception as e:
+            print(f"branch-parallel capture failed at N={N}: {type(e).__name__}: {str(e)[:200]}", file=sys.stderr)
+        model.branch_streams = None
         print(json.dumps({"N": N, "K": K, "T": T, "batch": B, "library_kernels_per_step": launches, "eager_ms_per_step": round(t_eager, 4),
-                          "graphed_ms_per_step": round(t_graph, 4), "od_cells_per_s_graphed": B * T * N * N / (t_graph * 1e-3)}), flush=True)
+                          "graphed_ms_per_step": round(t_graph, 4), "graphed_branch_parallel_ms_per_step": None if t_par is None else round(t_par, 4),
+                          "od_cells_per_s_graphed": B * T * N * N / (min(t_graph, t_par or t_graph) * 1e-3)}), flush=True)
 
 
 if __name__ == "__main__":
