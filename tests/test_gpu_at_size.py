@@ -290,8 +290,8 @@ def test_two_devices_in_one_process(cuda_device):
     assert torch.equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize("N", [47, 200])
-def test_graphed_training_step_equals_eager_training(N, cuda_device):
+@pytest.mark.parametrize("N,par", [(47, False), (47, True), (200, True)])
+def test_graphed_training_step_equals_eager_training(N, par, cuda_device):
     """mpgcn_b200.graph_step: 6 Adam steps through the captured graph (new batch copied in every step) == the same 6 steps
     eagerly, bit for bit (same kernels, same buffers' contents), at the reference's N = 47 and at N = 200."""
     from mpgcn_b200.graph_step import GraphedTrainStep
@@ -311,7 +311,8 @@ def test_graphed_training_step_equals_eager_training(N, cuda_device):
         out = []
         if mode == "graph":
             state = {k: v.clone() for k, v in model.state_dict().items()}
-            step = GraphedTrainStep(model, crit, opt, example=(batches[0][0], batches[0][1], G, (batches[0][2], batches[0][3])), warmup=2)
+            step = GraphedTrainStep(model, crit, opt, example=(batches[0][0], batches[0][1], G, (batches[0][2], batches[0][3])), warmup=2,
+                                    branch_streams=par)       # par: the two branches forked onto parallel streams inside the graph
             with torch.no_grad():                           # undo the warm-up / capture updates IN PLACE (the graph holds these buffers)
                 for k, v in model.state_dict().items():
                     v.copy_(state[k])
