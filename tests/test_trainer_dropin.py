@@ -80,7 +80,7 @@ def test_unchanged_trainer_trains_and_tests_on_the_engine(tmp_path):
     data.mkdir()
     write_synthetic_data(str(data))
     common = ["-GPU", "cuda:0", "-in", str(data), "-out", str(out), "-batch", "4", "-lr", "1e-3"]
-    stdout = run_main([], common + ["-mode", "train", "-epoch", "2"])
+    stdout = run_main(["--seed", "0"], common + ["-mode", "train", "-epoch", "2"])      # the reference seeds nothing: fix the init for a stable assertion
     losses = val_losses(stdout)
     assert len(losses) >= 1 and all(np.isfinite(losses)), stdout[-2000:]
     assert len(losses) == 2 and losses[1] < losses[0], f"validation loss did not decrease over two epochs: {losses}"

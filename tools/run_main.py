@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--reference-dir", default=os.path.join(ROOT, "baseline", "_ref"))
     ap.add_argument("--graph-rollout", action="store_true")
     ap.add_argument("--gpu-dyn-graphs", action="store_true")
+    ap.add_argument("--seed", type=int, default=None, help="torch.manual_seed / numpy seed before Main.py runs (the reference sets none)")
     ap.add_argument("--stock", action="store_true", help="do NOT shadow MPGCN / GCN: run the reference as it is (CPU plumbing check)")
     ap.add_argument("main_args", nargs=argparse.REMAINDER)
     a = ap.parse_args()
@@ -53,6 +54,11 @@ def main():
             from mpgcn_b200 import rollout
             get_model = Model_Trainer.ModelTrainer.get_model
             Model_Trainer.ModelTrainer.get_model = lambda self: rollout.install(get_model(self))
+    if a.seed is not None:
+        import numpy as np
+        import torch
+        torch.manual_seed(a.seed)
+        np.random.seed(a.seed)
     sys.argv = [main_py] + margs
     os.chdir(ref)           # Main.py's defaults are relative paths (../data, ./output)
     runpy.run_path(main_py, run_name="__main__")
