@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--hidden", type=int, default=32)
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "auto"])
     ap.add_argument("--shard", default="batch", choices=["batch", "row", "k"])
+    ap.add_argument("--row-ranks", type=int, default=0,
+                    help="row shard: ranks per row group (default: all).  R < N GPUs = hybrid: N/R groups of R consecutive ranks, every group "
+                         "takes batch/(N/R) of the samples and splits THEIR origin rows R ways -- the exchange stays inside a group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -81,7 +84,9 @@ def workload_config(a, world):
     if a.shard == "batch":
         gb, par = a.batch * world, f"batch-shard x{world}"
     else:
-        gb, par = a.batch, f"{'origin-row' if a.shard == 'row' else 'K (destination-support)'}-shard x{world}"
+        R = a.row_ranks if (a.shard == "row" and 0 < a.row_ranks < world) else world
+        gb = a.batch
+        par = (f"{'origin-row' if a.shard == 'row' else 'K (destination-support)'}-shard x{R}" + (f" x batch-shard x{world // R}" if R < world else ""))
     return {
         "workload": f"MPGCN hot path N={a.nodes} K={a.supports} T={a.obs} hidden={a.hidden} M=2 L=3, "
                     + (f"batch {a.batch}/GPU" if a.shard == "batch" else f"batch {a.batch} in total"),
@@ -341,9 +346,19 @@ def run_ours(a):
     gd_host = (torch.randn(B, K, N, N, generator=g) / N ** 0.5).pin_memory()
     params = [p for p in model.parameters()]
     plan = None
+    n_groups = 1
     if sharded:
         from mpgcn_b200 import shard as mshard
-        plan = mshard.ShardPlan(a.shard, rank, world, N, K)
+        R = a.row_ranks if (a.shard == "row" and 0 < a.row_ranks < world) else world
+        assert world % R == 0 and B % (world // R) == 0, "--row-ranks must divide the number of GPUs, and the batch the number of groups"
+        n_groups = world // R
+        group = None
+        if n_groups > 1:          # hybrid: batch over the groups, origin rows inside a group (every rank creates every group)
+            groups = [dist.new_group(list(range(gi * R, (gi + 1) * R))) for gi in range(n_groups)]
+            group = groups[rank // R]
+            Bg, g0 = B // n_groups, (rank // R) * (B // n_groups)
+            x_host, y_host, go_host, gd_host = (t[g0:g0 + Bg] for t in (x_host, y_host, go_host, gd_host))
+        plan = mshard.ShardPlan(a.shard, rank % R, R, N, K, group=group)
         mshard.enable_peer_exchange(plan, dev)          # row shard: exchange inside our own kernels over NVLink peer memory, if available
         hosts = mshard.shard_host_inputs(plan, x_host, y_host, go_host, gd_host)       # this rank's slices (pinned)
         fwd = lambda x, go, gd: mshard.sharded_forward(model, plan, x, G_static, (go, gd))
@@ -357,7 +372,8 @@ def run_ours(a):
         if sharded:
             loss = mshard.sharded_mse_loss(plan, fwd(x, go, gd), y)
             loss.backward()
-            mshard.allreduce_sum_gradients(params, plan, model)      # every rank holds partial parameter gradients of the SAME samples
+            # every rank holds partial parameter gradients of its group's samples: sum inside a group, mean over the groups
+            mshard.allreduce_sum_gradients(params, plan, model, over_world=n_groups > 1, scale=1.0 / n_groups)
         else:
             loss = crit(fwd(x, go, gd), y)
             loss.backward()

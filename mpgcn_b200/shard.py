@@ -590,14 +590,16 @@ def sharded_mse_loss(plan: ShardPlan, y_pred, y_true):
     return torch.nn.functional.mse_loss(y_pred, y_true)
 
 
-def allreduce_sum_gradients(params, plan: ShardPlan = None, model=None) -> int:
+def allreduce_sum_gradients(params, plan: ShardPlan = None, model=None, over_world: bool = False, scale: float = 1.0) -> int:
     """ONE all-reduce (sum) of every parameter gradient on a flat buffer.  Row shard: all gradients are partial sums over the
     rank's cells.  K shard: dW slices are disjoint (zeros elsewhere), db was pre-divided, the LSTM is row-sharded; only the
-    replicated head's gradients must be divided by the number of ranks first (pass `model`)."""
+    replicated head's gradients must be divided by the number of ranks first (pass `model`).
+    Hybrid (row groups x batch shard): over_world=True reduces over ALL ranks and `scale` = 1 / number of groups turns the sum of
+    the groups' mean-loss gradients into the gradient of the global mean."""
     params = list(params)
     if not (dist.is_available() and dist.is_initialized()) or not params:
         return 0
-    group = plan.group if plan is not None else None
+    group = None if over_world else (plan.group if plan is not None else None)
     world = dist.get_world_size(group)
     if world == 1:
         return 0
@@ -605,9 +607,11 @@ def allreduce_sum_gradients(params, plan: ShardPlan = None, model=None) -> int:
         for m in range(model.M):
             for p in model.branch_models[m]['fc'].parameters():
                 if p.grad is not None:
-                    p.grad.div_(world)
+                    p.grad.div_(plan.world)
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
     dist.all_reduce(flat, group=group)
+    if scale != 1.0:
+        flat.mul_(scale)
     off = 0
     for p in params:
         n = p.numel()

@@ -32,17 +32,28 @@ def main(kind, out_path):
     G = torch.from_numpy((rng.random((K, N, N)) / N).astype(np.float32))
     go = torch.from_numpy((rng.random((B, K, N, N)) / N).astype(np.float32))
     gd = torch.from_numpy((rng.random((B, K, N, N)) / N).astype(np.float32))
-    plan = shard.ShardPlan(kind, rank, world, N, K)
+    n_groups, sample0 = 1, 0
+    if kind == "rowhyb":          # hybrid: world = 4 = 2 batch groups x 2 row ranks (bench.py --shard row --row-ranks 2)
+        R = 2
+        n_groups = world // R
+        groups = [dist.new_group(list(range(gi * R, (gi + 1) * R))) for gi in range(n_groups)]
+        Bg = B // n_groups
+        sample0 = (rank // R) * Bg
+        x, y, go, gd = (t[sample0:sample0 + Bg] for t in (x, y, go, gd))
+        plan = shard.ShardPlan("row", rank % R, R, N, K, group=groups[rank // R])
+    else:
+        plan = shard.ShardPlan(kind, rank, world, N, K)
     xs, ys, gos, gds = shard.shard_host_inputs(plan, x, y, go, gd)
     pred = shard.sharded_forward(model, plan, xs, G, (gos, gds))
     loss = shard.sharded_mse_loss(plan, pred, ys)
     loss.backward()
     params = list(model.parameters())
-    shard.allreduce_sum_gradients(params, plan, model)
+    shard.allreduce_sum_gradients(params, plan, model, over_world=n_groups > 1, scale=1.0 / n_groups)
     loss_all = loss.detach().clone()
-    if kind == "row":
+    if kind in ("row", "rowhyb"):
         dist.all_reduce(loss_all)
-    torch.save({"rank": rank, "pred": pred.detach(), "rows": (plan.row_lo, plan.row_hi), "loss": float(loss_all),
+        loss_all /= n_groups
+    torch.save({"rank": rank, "pred": pred.detach(), "rows": (plan.row_lo, plan.row_hi), "sample0": sample0, "loss": float(loss_all),
                 "grads": {k: p.grad.clone() for k, p in model.named_parameters()}}, out_path)
     dist.destroy_process_group()
 

@@ -28,19 +28,22 @@ def test_shard_plan_partitions():
         shard.ShardPlan("row", 0, 3, 1000, 3)
 
 
-@pytest.mark.parametrize("kind", ["row", "k"])
+@pytest.mark.parametrize("kind", ["row", "k", "rowhyb"])
 def test_sharded_model_world2_matches_whole_model_oracle(kind, tmp_path):
+    """row / k: world 2.  rowhyb: world 4 = 2 batch groups x 2 row ranks (the exchange stays inside a group; gradients are summed
+    over all ranks and averaged over the groups)."""
+    nproc = 4 if kind == "rowhyb" else 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     worker = os.path.join(HERE, "_shard_worker.py")
     procs = []
-    for r in range(2):
-        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(r), WORLD_SIZE="2")
+    for r in range(nproc):
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(r), WORLD_SIZE=str(nproc))
         procs.append(subprocess.Popen([sys.executable, worker, kind, str(tmp_path / f"r{r}.pt")], env=env))
     for p in procs:
         assert p.wait(timeout=300) == 0
-    res = [torch.load(tmp_path / f"r{r}.pt") for r in range(2)]
+    res = [torch.load(tmp_path / f"r{r}.pt") for r in range(nproc)]
     # the same model / inputs as the worker builds, evaluated whole by the oracle
     sys.path.insert(0, os.path.dirname(HERE))
     import MPGCN as shim
@@ -66,6 +69,9 @@ def test_sharded_model_world2_matches_whole_model_oracle(kind, tmp_path):
     loss_o = float(((y_o - y) ** 2).mean())
     if kind == "row":
         pred = np.concatenate([r["pred"].numpy() for r in sorted(res, key=lambda r: r["rank"])], axis=2)
+    elif kind == "rowhyb":     # ranks (0,1) hold sample 0's row slabs, ranks (2,3) sample 1's
+        by = sorted(res, key=lambda r: r["rank"])
+        pred = np.concatenate([np.concatenate([by[2 * gi]["pred"].numpy(), by[2 * gi + 1]["pred"].numpy()], axis=2) for gi in range(2)], axis=0)
     else:
         pred = res[0]["pred"].numpy()
         assert np.array_equal(pred, res[1]["pred"].numpy()), "K shard: the prediction is replicated"
