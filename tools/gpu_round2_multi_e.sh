@@ -8,9 +8,9 @@ run() {  # name, extra args
       > gpurun_out/r2_hyb_${name}_n$N.json 2> gpurun_out/r2_hyb_${name}_n$N.err
 }
 run row2 --shard row --row-ranks 2
-run row4 --shard row --row-ranks 4
+[ "$N" -ge 8 ] && run row4 --shard row --row-ranks 4
 run row2_cfg5 --shard row --row-ranks 2 --workload cfg5 --batch 8
-run row4_cfg5 --shard row --row-ranks 4 --workload cfg5 --batch 8
+[ "$N" -ge 8 ] && run row4_cfg5 --shard row --row-ranks 4 --workload cfg5 --batch 8
 for f in gpurun_out/r2_hyb_*_n$N.json; do echo $f; python -c "
 import json,sys
 try:
