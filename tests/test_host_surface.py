@@ -162,3 +162,44 @@ def test_gradient_hint_routing_is_graph_based():
     assert ops._take_hint(node, g) is None
     ops._put_hint(None, g, scalar)                                                       # no producer: nothing happens
 
+
+
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    """Argument validation happens before any CUDA call: empty / malformed shapes, unknown precisions, bad layer parts and bad
+    peer layouts come back as error codes with a message (`mpgcn_last_error`), never as a crash -- also on a box without a GPU."""
+    import ctypes
+    from mpgcn_b200 import _lib
+    lib = _lib.load()
+    one = ctypes.c_void_p(256)          # any non-null, 256-byte "aligned" pointer: never dereferenced on these paths
+
+    def err():
+        return lib.mpgcn_last_error().decode()
+    # empty batch / zero nodes (the reference would return empty tensors; the engine refuses them loudly)
+    assert lib.mpgcn_bdgcn_forward(one, one, one, 0, one, None, 1, one, None, one, 1 << 20, 0, 8, 3, 32, 32, 0, None) != 0 and "bad BDGCN shape" in err()
+    assert lib.mpgcn_bdgcn_forward(one, one, one, 0, one, None, 1, one, None, one, 1 << 20, 2, 0, 3, 32, 32, 0, None) != 0
+    assert lib.mpgcn_bdgcn_forward(one, one, one, 0, one, None, 1, one, None, one, 1 << 20, 2, 8, 3, 32, 32, 7, None) != 0 and "unknown precision" in err()
+    assert lib.mpgcn_bdgcn_forward(one, one, one, 0, one, None, 2, one, None, one, 1 << 20, 2, 8, 3, 32, 32, 0, None) != 0 and "activation" in err()
+    assert lib.mpgcn_bdgcn_forward(one, one, one, 0, one, None, 1, one, None, one, 1 << 20, 2, 8, 3, 16, 32, 1, None) != 0 and "C == H == 32" in err()
+    # layer parts
+    part = _lib.BdgcnPart(4, 8, 3, 3)                      # rows [4, 12) of N = 8
+    assert lib.mpgcn_bdgcn_forward_part(one, one, one, 0, one, one, None, one, 1 << 20, 2, 8, 32, 32, 0, ctypes.addressof(part), None, None) != 0
+    assert "bad layer part" in err()
+    assert lib.mpgcn_bdgcn_forward_part(one, one, one, 0, one, one, None, one, 1 << 20, 2, 8, 32, 32, 0, None, None, None) != 0 and "part descriptor" in err()
+    part = _lib.BdgcnPart(0, 4, 3, 3)
+    part.peer_g, part.peer_rank = 3, 0                     # N = 8 is not a multiple of 3 ranks; and the push needs precision 1
+    assert lib.mpgcn_bdgcn_forward_part(one, one, one, 0, one, None, None, one, 1 << 20, 2, 8, 32, 32, 1, ctypes.addressof(part), None, None) != 0
+    assert "peer layout" in err()
+    assert lib.mpgcn_bdgcn_forward_part(one, one, one, 0, one, None, None, one, 1 << 20, 2, 8, 32, 32, 0, ctypes.addressof(part), None, None) != 0
+    assert "tensor-core epilogue only" in err()
+    # exchange kernels
+    arr = (ctypes.c_void_p * 9)(*[256] * 9)
+    assert lib.mpgcn_rows_reduce_bias_act(one, arr, 9, None, 1, 1, 8, 0, 4, 8, 32, None) != 0 and "ranks unsupported" in err()
+    assert lib.mpgcn_rows_reduce_bias_act(one, arr, 2, None, 1, 1, 8, 6, 4, 8, 32, None) != 0 and "bad slab" in err()
+    assert lib.mpgcn_rows_reduce_bias_act(one, arr, 2, None, 1, 1, 8, 0, 4, 5, 32, None) != 0 and "part buffers" in err()
+    assert lib.mpgcn_relu_backward_scatter(one, one, 1, arr, 2, None, 1, 8, 6, 4, 32, None) != 0 and "bad slab" in err()
+    # LSTM
+    assert lib.mpgcn_lstm_last_forward(one, one, one, one, one, one, 0, 4, 16, 32, 0, None) != 0 and "empty input" in err()
+    assert lib.mpgcn_lstm_last_forward(one, one, one, one, one, one, 1, 4, 16, 48, 1, None) != 0 and "does not support" in err()
+    # sizing queries are pure host functions
+    assert lib.mpgcn_bdgcn_part_saved_bytes(2, 8, 32, 32, 1, ctypes.addressof(_lib.BdgcnPart(0, 4, 3, 2))) == 2 * 2 * 4 * 8 * 32 * 2
+    assert lib.mpgcn_bdgcn_part_saved_bytes(2, 8, 32, 32, 0, ctypes.addressof(_lib.BdgcnPart(0, 4, 3, 2))) == 2 * 2 * 4 * 8 * 32 * 4
