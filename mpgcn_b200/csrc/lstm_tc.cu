@@ -51,6 +51,26 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 1.f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two IEEE operations).  The activation math of two
+// neighbouring hidden units is identical, so everything on the FMA pipe is done on pairs; the SFU operations (ex2, rcp) and the
+// clamps stay scalar.  ~21 FMA-pipe instructions per unit and step become ~10.5: the kernels are co-limited by issue slots
+// (51 % / 61 % used) and the SFU queue (profiles/ncu_lstm_r2.txt).
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 f2_mk(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_un(f2 x, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+// 1 + 2^min(a, 40) on a pair (two clamps, two SFU ops, one packed add)
+__device__ __forceinline__ f2 f2_one_plus_ex2(float a0, float a1, f2 one) {
+  return f2_add(f2_mk(ex2_(fminf(a0, 40.f)), ex2_(fminf(a1, 40.f))), one);
+}
+__device__ __forceinline__ f2 f2_rcp(f2 x) {
+  float a, b;
+  f2_un(x, a, b);
+  return f2_mk(rcp_(a), rcp_(b));
+}
+
 // POLY = how many of the five exponentials per unit and step take the polynomial (0: none; 1: tanh(c); 2: tanh(c) and the o gate)
 template <int POLY, int WHICH> __device__ __forceinline__ float ex2_sel(float x) { return (WHICH < POLY) ? ex2_poly(x) : ex2_(x); }
 
@@ -161,7 +181,7 @@ __device__ void load_weights_ext(uint8_t* sWx, const float* w_ih, const float* w
 
 constexpr int FWD_THREADS = 256;
 
-template <bool SAVE, int POLY>
+template <bool SAVE, int POLY, bool PACK>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                    const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ hT, __half* __restrict__ saved,
@@ -237,10 +257,43 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
         // (g); arguments are clamped from above at 40 (ex2(-big) = 0 is fine), so a triple product stays below 1.4e36; the
         // clamp moves sigmoid / tanh by < 1e-12.
         uint32_t ra[UN], rb[UN];
-        float p[UN];                      // a_i * a_g, later o's (1 + 2^arg) term
         tmem_ld_32x16(t_col + 0 * C, ra);
         tmem_ld_32x16(t_col + 2 * C, rb);
         tmem_ld_wait();
+        if constexpr (PACK) {             // the same arithmetic on pairs of units (FFMA2 / FMUL2 / FADD2)
+          const f2 one = f2_mk(1.f, 1.f), m1 = f2_mk(-1.f, -1.f), k2 = f2_mk(-2.8853900817779268f, -2.8853900817779268f);
+          f2 AI[UN / 2], AG[UN / 2], P[UN / 2];
+#pragma unroll
+          for (int k = 0; k < UN / 2; ++k) {
+            AI[k] = f2_one_plus_ex2(__uint_as_float(ra[2 * k]), __uint_as_float(ra[2 * k + 1]), one);
+            AG[k] = f2_one_plus_ex2(__uint_as_float(rb[2 * k]), __uint_as_float(rb[2 * k + 1]), one);
+          }
+          tmem_ld_32x16(t_col + 1 * C, ra);
+          tmem_ld_32x16(t_col + 3 * C, rb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < UN / 2; ++k) {
+            const f2 AF = f2_one_plus_ex2(__uint_as_float(ra[2 * k]), __uint_as_float(ra[2 * k + 1]), one);
+            const f2 PIG = f2_mul(AI[k], AG[k]);
+            const f2 R = f2_rcp(f2_mul(PIG, AF));
+            const f2 GI = f2_mul(R, f2_mul(AG[k], AF));                         // sigmoid(i)
+            const f2 GG = f2_fma(f2_add(R, R), f2_mul(AI[k], AF), m1);          // tanh(g)
+            const f2 GF = f2_mul(R, PIG);                                       // sigmoid(f)
+            f2 Cc = f2_mk(c[2 * k], c[2 * k + 1]);
+            Cc = f2_fma(GF, Cc, f2_mul(GI, GG));
+            f2_un(Cc, c[2 * k], c[2 * k + 1]);
+            P[k] = f2_one_plus_ex2(__uint_as_float(rb[2 * k]), __uint_as_float(rb[2 * k + 1]), one);
+          }
+#pragma unroll
+          for (int k = 0; k < UN / 2; ++k) {
+            float x0, x1;
+            f2_un(f2_mul(f2_mk(c[2 * k], c[2 * k + 1]), k2), x0, x1);
+            const f2 AC = f2_one_plus_ex2(x0, x1, one);
+            const f2 R = f2_rcp(f2_mul(P[k], AC));
+            f2_un(f2_mul(f2_mul(R, AC), f2_fma(f2_add(R, R), P[k], m1)), h[2 * k], h[2 * k + 1]);      // sigmoid(o) * tanh(c)
+          }
+        } else {
+        float p[UN];                      // a_i * a_g, later o's (1 + 2^arg) term
         float ai[UN], ag[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
@@ -266,6 +319,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           const float ac = 1.f + ex2_sel<POLY, 0>(fminf(-2.8853900817779268f * c[u], 40.f));
           const float r = rcp_(p[u] * ac);
           h[u] = (r * ac) * fmaf(r + r, p[u], -1.f);            // sigmoid(o) * tanh(c)
+        }
         }
       }
       if (SAVE) {                     // training: c_t and h_t (fp16) for the backward kernel, see save_at()
@@ -613,6 +667,16 @@ static int lstm_poly_knob() {
   return v;
 }
 
+// MPGCN_B200_LSTM_PACK = 0 | 1: FMA-pipe arithmetic of the LSTM kernels on packed fp32 pairs (FFMA2 / FMUL2 / FADD2)
+static int lstm_pack_knob() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MPGCN_B200_LSTM_PACK");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v;
+}
+
 static int lstm_grid(long long cells) {
   const long long tiles = (cells + lstm_tc::CELLS - 1) / lstm_tc::CELLS;
   static int per_sm = 0;
@@ -650,13 +714,16 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
   }
   const int poly = lstm_poly_knob();
   using Kern = void (*)(const float*, const float*, const float*, const float*, const float*, float*, __half*, long long, int, long long);
-  static const Kern kerns[2][3] = {{lstm_fwd_tc_kernel<false, 0>, lstm_fwd_tc_kernel<false, 1>, lstm_fwd_tc_kernel<false, 2>},
-                                   {lstm_fwd_tc_kernel<true, 0>, lstm_fwd_tc_kernel<true, 1>, lstm_fwd_tc_kernel<true, 2>}};
-  static DynSmemAttr attrs[2][3] = {};
+  static const Kern kerns[2][4] = {{lstm_fwd_tc_kernel<false, 0, false>, lstm_fwd_tc_kernel<false, 1, false>, lstm_fwd_tc_kernel<false, 2, false>,
+                                    lstm_fwd_tc_kernel<false, 0, true>},
+                                   {lstm_fwd_tc_kernel<true, 0, false>, lstm_fwd_tc_kernel<true, 1, false>, lstm_fwd_tc_kernel<true, 2, false>,
+                                    lstm_fwd_tc_kernel<true, 0, true>}};
+  static DynSmemAttr attrs[2][4] = {};
   const int sv = saved ? 1 : 0;
-  if (int e = ensure_dyn_smem(kerns[sv][poly], fwd_smem, attrs[sv][poly])) return e;
+  const int var = lstm_pack_knob() ? 3 : poly;          // variant 3 = packed f32x2 arithmetic (no polynomial)
+  if (int e = ensure_dyn_smem(kerns[sv][var], fwd_smem, attrs[sv][var])) return e;
   prof_begin(PROF_LSTM_FWD, 8.0 * C * (C + 1) * (double)cells * T, st);
-  kerns[sv][poly]<<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, static_cast<__half*>(saved), cells, T, NN);
+  kerns[sv][var]<<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, static_cast<__half*>(saved), cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
   return 0;

@@ -50,7 +50,7 @@ def child():
     h16s = ops.lstm_last(xs, *ws, precision="fp16")
     h16s.backward(ds)
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
-    print(json.dumps({"poly": int(os.environ.get("MPGCN_B200_LSTM_POLY", "0")), "batch": B,
+    print(json.dumps({"poly": int(os.environ.get("MPGCN_B200_LSTM_POLY", "0")), "pack": int(os.environ.get("MPGCN_B200_LSTM_PACK", "0")), "batch": B,
                       "fwd_ms": prof["LSTM_FWD"]["ms"] / prof["LSTM_FWD"]["launches"], "bwd_ms": prof["LSTM_BWD"]["ms"] / prof["LSTM_BWD"]["launches"],
                       "hT_rel_linf_vs_fp32": rel(h16s.detach(), h32.detach()),
                       "grad_rel_linf_vs_fp32": [rel(w.grad, g) for w, g in zip(ws, g32)]}), flush=True)
@@ -60,5 +60,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for poly in (0, 1, 2):
-            subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, MPGCN_B200_LSTM_POLY=str(poly)))
+        variants = [(0, 0), (0, 1)] if os.environ.get("PROBE_PACK_ONLY") else [(0, 0), (1, 0), (2, 0), (0, 1)]
+        for poly, pack in variants:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "child"],
+                           env=dict(os.environ, MPGCN_B200_LSTM_POLY=str(poly), MPGCN_B200_LSTM_PACK=str(pack)))
