@@ -65,6 +65,29 @@ __device__ __forceinline__ f2 f2_add(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %
 __device__ __forceinline__ f2 f2_one_plus_ex2(float a0, float a1, f2 one) {
   return f2_add(f2_mk(ex2_(fminf(a0, 40.f)), ex2_(fminf(a1, 40.f))), one);
 }
+// 2^x for a pair on the FMA pipe (see ex2_poly): inputs already clamped to <= 40
+__device__ __forceinline__ f2 f2_ex2_poly(float x0, float x1) {
+  const f2 x = f2_mk(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const f2 magic = f2_mk(12582912.f, 12582912.f), nmagic = f2_mk(-12582912.f, -12582912.f), m1 = f2_mk(-1.f, -1.f);
+  const f2 t = f2_add(x, magic);
+  const f2 f = f2_fma(f2_add(t, nmagic), m1, x);                 // x - round(x)  in [-0.5, 0.5]
+  f2 p = f2_mk(1.535336188319500e-4f, 1.535336188319500e-4f);
+  p = f2_fma(p, f, f2_mk(1.339887440266574e-3f, 1.339887440266574e-3f));
+  p = f2_fma(p, f, f2_mk(9.618437357674640e-3f, 9.618437357674640e-3f));
+  p = f2_fma(p, f, f2_mk(5.550332471162809e-2f, 5.550332471162809e-2f));
+  p = f2_fma(p, f, f2_mk(2.402264791363012e-1f, 2.402264791363012e-1f));
+  p = f2_fma(p, f, f2_mk(6.931472028550421e-1f, 6.931472028550421e-1f));
+  p = f2_fma(p, f, f2_mk(1.f, 1.f));
+  float p0, p1, t0, t1;
+  f2_un(p, p0, p1);
+  f2_un(t, t0, t1);
+  return f2_mk(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)), __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+}
+template <bool USE_POLY>
+__device__ __forceinline__ f2 f2_one_plus_ex2_sel(float a0, float a1, f2 one) {
+  if (USE_POLY) return f2_add(f2_ex2_poly(fminf(a0, 40.f), fminf(a1, 40.f)), one);
+  return f2_one_plus_ex2(a0, a1, one);
+}
 __device__ __forceinline__ f2 f2_rcp(f2 x) {
   float a, b;
   f2_un(x, a, b);
@@ -288,7 +311,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           for (int k = 0; k < UN / 2; ++k) {
             float x0, x1;
             f2_un(f2_mul(f2_mk(c[2 * k], c[2 * k + 1]), k2), x0, x1);
-            const f2 AC = f2_one_plus_ex2(x0, x1, one);
+            const f2 AC = f2_one_plus_ex2_sel<(POLY > 0)>(x0, x1, one);
             const f2 R = f2_rcp(f2_mul(P[k], AC));
             f2_un(f2_mul(f2_mul(R, AC), f2_fma(f2_add(R, R), P[k], m1)), h[2 * k], h[2 * k + 1]);      // sigmoid(o) * tanh(c)
           }
@@ -377,7 +400,7 @@ template <> __device__ __forceinline__ void tmem_st_w<4>(uint32_t taddr, const u
 // No dedicated MMA warp: with 9 warps per CTA the register file only holds ONE CTA per SM at > 102 registers per thread
 // (18 warps -> 5 on one scheduler partition).  Every step ends in one CTA-wide barrier, after which lane 0 of warp 0 issues
 // the step's three MMA groups while everybody moves on.
-template <int TPC, int POLY>
+template <int TPC, int POLY, bool PACK>
 __global__ void __launch_bounds__(128 * TPC, 2)
 lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                          const float* __restrict__ b_ih, const float* __restrict__ b_hh, const float* __restrict__ d_hT,
@@ -544,6 +567,41 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
           fcp[0] = b0.x; fcp[1] = b0.y; fcp[2] = b1.x; fcp[3] = b1.y;
         }
         float di[PW], df[PW], dg[PW], d_o[PW];
+        if constexpr (PACK) {            // the same arithmetic on pairs of units (FFMA2 / FMUL2 / FADD2); d_x is accumulated below
+          const f2 one = f2_mk(1.f, 1.f), m1 = f2_mk(-1.f, -1.f), k2 = f2_mk(-2.8853900817779268f, -2.8853900817779268f);
+#pragma unroll
+          for (int e = 0; e < PW; e += 2) {
+            const f2 AI = f2_one_plus_ex2(__uint_as_float(ri[e]), __uint_as_float(ri[e + 1]), one);
+            const f2 AG = f2_one_plus_ex2(__uint_as_float(rg[e]), __uint_as_float(rg[e + 1]), one);
+            const f2 AF = f2_one_plus_ex2(__uint_as_float(rf[e]), __uint_as_float(rf[e + 1]), one);
+            const f2 AO = f2_one_plus_ex2(__uint_as_float(ro[e]), __uint_as_float(ro[e + 1]), one);
+            float x0, x1;
+            f2_un(f2_mul(f2_mk(fc[e], fc[e + 1]), k2), x0, x1);
+            const f2 AC = f2_one_plus_ex2_sel<(POLY > 0)>(x0, x1, one);
+            const f2 PIG = f2_mul(AI, AG);
+            const f2 R1 = f2_rcp(f2_mul(PIG, AF)), R2 = f2_rcp(f2_mul(AO, AC));
+            const f2 GI = f2_mul(R1, f2_mul(AG, AF)), GG = f2_fma(f2_add(R1, R1), f2_mul(AI, AF), m1), GF = f2_mul(R1, PIG);
+            const f2 GO = f2_mul(R2, AC), TC = f2_fma(f2_add(R2, R2), AO, m1);
+            const f2 DH = f2_mk(__uint_as_float(rdh[e]), __uint_as_float(rdh[e + 1]));
+            const f2 nTC = f2_mul(TC, m1), nGO = f2_mul(GO, m1), nGI = f2_mul(GI, m1), nGF = f2_mul(GF, m1), nGG = f2_mul(GG, m1);
+            const f2 DC = f2_fma(f2_mul(DH, GO), f2_fma(nTC, TC, one), f2_mk(__uint_as_float(rdc[e]), __uint_as_float(rdc[e + 1])));
+            f2_un(f2_mul(f2_mul(DH, TC), f2_fma(nGO, GO, GO)), d_o[e], d_o[e + 1]);
+            f2_un(f2_mul(f2_mul(DC, GG), f2_fma(nGI, GI, GI)), di[e], di[e + 1]);
+            f2_un(f2_mul(f2_mul(DC, f2_mk(fcp[e], fcp[e + 1])), f2_fma(nGF, GF, GF)), df[e], df[e + 1]);
+            f2_un(f2_mul(f2_mul(DC, GI), f2_fma(nGG, GG, one)), dg[e], dg[e + 1]);
+            float c0, c1;
+            f2_un(f2_mul(DC, GF), c0, c1);
+            rdc[e] = __float_as_uint(c0);
+            rdc[e + 1] = __float_as_uint(c1);
+          }
+          if (d_x != nullptr) {
+#pragma unroll
+            for (int e = 0; e < PW; ++e) {
+              const int u = u0 + PW * q + e;
+              dx_acc += di[e] * s_wih[u] + df[e] * s_wih[C + u] + dg[e] * s_wih[2 * C + u] + d_o[e] * s_wih[3 * C + u];
+            }
+          }
+        } else {
 #pragma unroll
         for (int e = 0; e < PW; ++e) {
           // accumulators are -log2e * pre (i, f, o) and -2 log2e * pre (g); clamp from above only (ex2(-big) = 0 is fine),
@@ -568,6 +626,7 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
             const int u = u0 + PW * q + e;
             dx_acc += di[e] * s_wih[u] + df[e] * s_wih[C + u] + dg[e] * s_wih[2 * C + u] + d_o[e] * s_wih[3 * C + u];
           }
+        }
         }
         if (q == 0 && mma2_pending) {    // MMA2 of step t+1 must have retired before sDA is overwritten; by now it has
           mbar_wait(mma_free, ph_free);
@@ -714,13 +773,13 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
   }
   const int poly = lstm_poly_knob();
   using Kern = void (*)(const float*, const float*, const float*, const float*, const float*, float*, __half*, long long, int, long long);
-  static const Kern kerns[2][4] = {{lstm_fwd_tc_kernel<false, 0, false>, lstm_fwd_tc_kernel<false, 1, false>, lstm_fwd_tc_kernel<false, 2, false>,
-                                    lstm_fwd_tc_kernel<false, 0, true>},
+  static const Kern kerns[2][5] = {{lstm_fwd_tc_kernel<false, 0, false>, lstm_fwd_tc_kernel<false, 1, false>, lstm_fwd_tc_kernel<false, 2, false>,
+                                    lstm_fwd_tc_kernel<false, 0, true>, lstm_fwd_tc_kernel<false, 1, true>},
                                    {lstm_fwd_tc_kernel<true, 0, false>, lstm_fwd_tc_kernel<true, 1, false>, lstm_fwd_tc_kernel<true, 2, false>,
-                                    lstm_fwd_tc_kernel<true, 0, true>}};
-  static DynSmemAttr attrs[2][4] = {};
+                                    lstm_fwd_tc_kernel<true, 0, true>, lstm_fwd_tc_kernel<true, 1, true>}};
+  static DynSmemAttr attrs[2][5] = {};
   const int sv = saved ? 1 : 0;
-  const int var = lstm_pack_knob() ? 3 : poly;          // variant 3 = packed f32x2 arithmetic (no polynomial)
+  const int var = lstm_pack_knob() ? (poly > 0 ? 4 : 3) : poly;     // variants 3 / 4: packed f32x2 arithmetic (without / with one polynomial ex2)
   if (int e = ensure_dyn_smem(kerns[sv][var], fwd_smem, attrs[sv][var])) return e;
   prof_begin(PROF_LSTM_FWD, 8.0 * C * (C + 1) * (double)cells * T, st);
   kerns[sv][var]<<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, static_cast<__half*>(saved), cells, T, NN);
@@ -752,12 +811,14 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   const int poly = lstm_poly_knob();
   using KernB = void (*)(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                          const __half*, const float*, long long, int, long long);
-  static const KernB kernb[3] = {lstm_bwd_saved_tc_kernel<2, 0>, lstm_bwd_saved_tc_kernel<2, 1>, lstm_bwd_saved_tc_kernel<2, 2>};
-  static DynSmemAttr attr_b[3] = {};
-  if (int e = ensure_dyn_smem(kernb[poly], kLstmSavedSmem, attr_b[poly])) return e;
+  static const KernB kernb[5] = {lstm_bwd_saved_tc_kernel<2, 0, false>, lstm_bwd_saved_tc_kernel<2, 1, false>, lstm_bwd_saved_tc_kernel<2, 2, false>,
+                                 lstm_bwd_saved_tc_kernel<2, 0, true>, lstm_bwd_saved_tc_kernel<2, 1, true>};
+  static DynSmemAttr attr_b[5] = {};
+  const int varb = lstm_pack_knob() ? (poly > 0 ? 4 : 3) : poly;        // variants 3 / 4: packed f32x2 arithmetic (without / with one polynomial ex2)
+  if (int e = ensure_dyn_smem(kernb[varb], kLstmSavedSmem, attr_b[varb])) return e;
   static_assert(1024 + DA_BYTES + 3 * HX_BYTES + WX_BYTES + 8192 + 2 * G4 * sizeof(float) + 256 <= (size_t)kLstmSavedSmem, "smem");
   prof_begin(PROF_LSTM_BWD, 12.0 * C * (C + 1) * (double)cells * T, st);
-  kernb[poly]<<<lstm_grid(cells), 256, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
+  kernb[varb]<<<lstm_grid(cells), 256, kLstmSavedSmem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, d_hT, d_w_ih, d_w_hh, d_b_ih, d_x,
                                                             static_cast<const __half*>(saved), scale2, cells, T, NN);
   prof_end(st);
   MPGCN_CUDA(cudaGetLastError());
