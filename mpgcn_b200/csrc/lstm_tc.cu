@@ -296,7 +296,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < UN / 2; ++k) {
-            const f2 AF = f2_one_plus_ex2(__uint_as_float(ra[2 * k]), __uint_as_float(ra[2 * k + 1]), one);
+            const f2 AF = f2_one_plus_ex2_sel<(POLY > 2)>(__uint_as_float(ra[2 * k]), __uint_as_float(ra[2 * k + 1]), one);
             const f2 PIG = f2_mul(AI[k], AG[k]);
             const f2 R = f2_rcp(f2_mul(PIG, AF));
             const f2 GI = f2_mul(R, f2_mul(AG[k], AF));                         // sigmoid(i)
@@ -305,7 +305,7 @@ lstm_fwd_tc_kernel(const float* __restrict__ x_seq, const float* __restrict__ w_
             f2 Cc = f2_mk(c[2 * k], c[2 * k + 1]);
             Cc = f2_fma(GF, Cc, f2_mul(GI, GG));
             f2_un(Cc, c[2 * k], c[2 * k + 1]);
-            P[k] = f2_one_plus_ex2(__uint_as_float(rb[2 * k]), __uint_as_float(rb[2 * k + 1]), one);
+            P[k] = f2_one_plus_ex2_sel<(POLY > 1)>(__uint_as_float(rb[2 * k]), __uint_as_float(rb[2 * k + 1]), one);
           }
 #pragma unroll
           for (int k = 0; k < UN / 2; ++k) {
@@ -573,8 +573,8 @@ lstm_bwd_saved_tc_kernel(const float* __restrict__ x_seq, const float* __restric
           for (int e = 0; e < PW; e += 2) {
             const f2 AI = f2_one_plus_ex2(__uint_as_float(ri[e]), __uint_as_float(ri[e + 1]), one);
             const f2 AG = f2_one_plus_ex2(__uint_as_float(rg[e]), __uint_as_float(rg[e + 1]), one);
-            const f2 AF = f2_one_plus_ex2(__uint_as_float(rf[e]), __uint_as_float(rf[e + 1]), one);
-            const f2 AO = f2_one_plus_ex2(__uint_as_float(ro[e]), __uint_as_float(ro[e + 1]), one);
+            const f2 AF = f2_one_plus_ex2_sel<(POLY > 2)>(__uint_as_float(rf[e]), __uint_as_float(rf[e + 1]), one);
+            const f2 AO = f2_one_plus_ex2_sel<(POLY > 1)>(__uint_as_float(ro[e]), __uint_as_float(ro[e + 1]), one);
             float x0, x1;
             f2_un(f2_mul(f2_mk(fc[e], fc[e + 1]), k2), x0, x1);
             const f2 AC = f2_one_plus_ex2_sel<(POLY > 0)>(x0, x1, one);
@@ -721,7 +721,7 @@ static int lstm_poly_knob() {
   if (v < 0) {
     const char* e = getenv("MPGCN_B200_LSTM_POLY");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 2) v = 0;
+    if (v < 0 || v > 3) v = 0;
   }
   return v;
 }
@@ -773,13 +773,16 @@ int lstm_last_forward_tc(const float* x_seq, const float* w_ih, const float* w_h
   }
   const int poly = lstm_poly_knob();
   using Kern = void (*)(const float*, const float*, const float*, const float*, const float*, float*, __half*, long long, int, long long);
-  static const Kern kerns[2][5] = {{lstm_fwd_tc_kernel<false, 0, false>, lstm_fwd_tc_kernel<false, 1, false>, lstm_fwd_tc_kernel<false, 2, false>,
-                                    lstm_fwd_tc_kernel<false, 0, true>, lstm_fwd_tc_kernel<false, 1, true>},
+  // variants 0..2: scalar arithmetic with POLY polynomial exponentials; 3..6: packed f32x2 arithmetic with POLY = 0..3
+  static const Kern kerns[2][7] = {{lstm_fwd_tc_kernel<false, 0, false>, lstm_fwd_tc_kernel<false, 1, false>, lstm_fwd_tc_kernel<false, 2, false>,
+                                    lstm_fwd_tc_kernel<false, 0, true>, lstm_fwd_tc_kernel<false, 1, true>, lstm_fwd_tc_kernel<false, 2, true>,
+                                    lstm_fwd_tc_kernel<false, 3, true>},
                                    {lstm_fwd_tc_kernel<true, 0, false>, lstm_fwd_tc_kernel<true, 1, false>, lstm_fwd_tc_kernel<true, 2, false>,
-                                    lstm_fwd_tc_kernel<true, 0, true>, lstm_fwd_tc_kernel<true, 1, true>}};
-  static DynSmemAttr attrs[2][5] = {};
+                                    lstm_fwd_tc_kernel<true, 0, true>, lstm_fwd_tc_kernel<true, 1, true>, lstm_fwd_tc_kernel<true, 2, true>,
+                                    lstm_fwd_tc_kernel<true, 3, true>}};
+  static DynSmemAttr attrs[2][7] = {};
   const int sv = saved ? 1 : 0;
-  const int var = lstm_pack_knob() ? (poly > 0 ? 4 : 3) : poly;     // variants 3 / 4: packed f32x2 arithmetic (without / with one polynomial ex2)
+  const int var = lstm_pack_knob() ? 3 + poly : (poly > 2 ? 2 : poly);
   if (int e = ensure_dyn_smem(kerns[sv][var], fwd_smem, attrs[sv][var])) return e;
   prof_begin(PROF_LSTM_FWD, 8.0 * C * (C + 1) * (double)cells * T, st);
   kerns[sv][var]<<<lstm_grid(cells), FWD_THREADS, fwd_smem, st>>>(x_seq, w_ih, w_hh, b_ih, b_hh, hT, static_cast<__half*>(saved), cells, T, NN);
@@ -811,10 +814,11 @@ int lstm_last_backward_tc(const float* x_seq, const float* w_ih, const float* w_
   const int poly = lstm_poly_knob();
   using KernB = void (*)(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                          const __half*, const float*, long long, int, long long);
-  static const KernB kernb[5] = {lstm_bwd_saved_tc_kernel<2, 0, false>, lstm_bwd_saved_tc_kernel<2, 1, false>, lstm_bwd_saved_tc_kernel<2, 2, false>,
-                                 lstm_bwd_saved_tc_kernel<2, 0, true>, lstm_bwd_saved_tc_kernel<2, 1, true>};
-  static DynSmemAttr attr_b[5] = {};
-  const int varb = lstm_pack_knob() ? (poly > 0 ? 4 : 3) : poly;        // variants 3 / 4: packed f32x2 arithmetic (without / with one polynomial ex2)
+  static const KernB kernb[7] = {lstm_bwd_saved_tc_kernel<2, 0, false>, lstm_bwd_saved_tc_kernel<2, 1, false>, lstm_bwd_saved_tc_kernel<2, 2, false>,
+                                 lstm_bwd_saved_tc_kernel<2, 0, true>, lstm_bwd_saved_tc_kernel<2, 1, true>, lstm_bwd_saved_tc_kernel<2, 2, true>,
+                                 lstm_bwd_saved_tc_kernel<2, 3, true>};
+  static DynSmemAttr attr_b[7] = {};
+  const int varb = lstm_pack_knob() ? 3 + poly : (poly > 2 ? 2 : poly);        // as in the forward
   if (int e = ensure_dyn_smem(kernb[varb], kLstmSavedSmem, attr_b[varb])) return e;
   static_assert(1024 + DA_BYTES + 3 * HX_BYTES + WX_BYTES + 8192 + 2 * G4 * sizeof(float) + 256 <= (size_t)kLstmSavedSmem, "smem");
   prof_begin(PROF_LSTM_BWD, 12.0 * C * (C + 1) * (double)cells * T, st);

@@ -60,7 +60,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        variants = [(0, 0), (0, 1), (1, 1)] if os.environ.get("PROBE_PACK_ONLY") else [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1)]
+        variants = [(0, 0), (1, 1), (2, 1), (3, 1)] if os.environ.get("PROBE_PACK_ONLY") else [(0, 0), (1, 0), (2, 0), (0, 1), (1, 1)]
         for poly, pack in variants:
             subprocess.run([sys.executable, os.path.abspath(__file__), "child"],
                            env=dict(os.environ, MPGCN_B200_LSTM_POLY=str(poly), MPGCN_B200_LSTM_PACK=str(pack)))
