@@ -715,13 +715,16 @@ __global__ void copy_vec_kernel(const float* src, float* dst, int n) {
 // ---------------------------------------------------------------------------------------
 bool lstm_tc_supported(int T, int C) { return C == 32 && T >= 1 && T <= 256; }
 
-// MPGCN_B200_LSTM_POLY = 0 | 1 | 2: exponentials per unit and step evaluated by ex2_poly (FMA pipe) instead of the SFU
+// MPGCN_B200_LSTM_POLY = 0 | 1 | 2 | 3: exponentials per unit and step evaluated by ex2_poly (FMA pipe) instead of the SFU.
+// Measured (B200, batch 8, N = 1000, T = 12; forward / backward ms per launch): scalar arithmetic 6.88 / 10.03 with POLY = 0 and
+// slower with POLY = 1, 2 (7.26 / 10.22, 7.69 / 11.08: the polynomial costs more issue slots than the SFU slots it frees);
+// packed f32x2 arithmetic 6.69 / 9.98 (POLY 0), **6.21 / 9.67 (POLY 1, the default)**, 7.06 / 10.01 (POLY 2), 6.82 / 10.70 (POLY 3).
 static int lstm_poly_knob() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MPGCN_B200_LSTM_POLY");
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v > 3) v = 0;
+    v = e ? atoi(e) : 1;          // measured best with packed arithmetic: tanh(c)'s exponential on the FMA pipe (profiles/lstm_poly_r2.jsonl)
+    if (v < 0 || v > 3) v = 1;
   }
   return v;
 }
@@ -731,7 +734,7 @@ static int lstm_pack_knob() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MPGCN_B200_LSTM_PACK");
-    v = e ? (atoi(e) != 0) : 0;
+    v = e ? (atoi(e) != 0) : 1;   // default on
   }
   return v;
 }
