@@ -30,9 +30,18 @@ def main(kind, out_path):
     G = torch.from_numpy((rng.standard_normal((K, N, N)) / N ** 0.5).astype(np.float32)).to(dev)
     go = torch.from_numpy((rng.standard_normal((B, K, N, N)) / N ** 0.5).astype(np.float32))
     gd = torch.from_numpy((rng.standard_normal((B, K, N, N)) / N ** 0.5).astype(np.float32))
-    plan = shard.ShardPlan(kind, rank, world, N, K)
+    n_groups, s0, s1 = 1, 0, B
+    if kind == "rowhyb":          # world 4 = 2 batch groups x 2 row ranks (bench.py --shard row --row-ranks 2)
+        R = 2
+        n_groups = world // R
+        groups = [dist.new_group(list(range(gi * R, (gi + 1) * R))) for gi in range(n_groups)]
+        Bg = B // n_groups
+        s0, s1 = (rank // R) * Bg, (rank // R + 1) * Bg
+        plan = shard.ShardPlan("row", rank % R, R, N, K, group=groups[rank // R])
+    else:
+        plan = shard.ShardPlan(kind, rank, world, N, K)
     peer = shard.enable_peer_exchange(plan, dev) if os.environ.get("SHARD_TEST_PEER", "1") == "1" else False
-    xs, ys, gos, gds = (t.to(dev) for t in shard.shard_host_inputs(plan, x, y, go, gd))
+    xs, ys, gos, gds = (t.to(dev) for t in shard.shard_host_inputs(plan, x[s0:s1], y[s0:s1], go[s0:s1], gd[s0:s1]))
     rows = []
     for prec, tol_f, tol_g in (("fp32", 1e-5, 2e-3), ("fp16", 1e-3, 8e-2)):
         model.lstm_precision = prec
@@ -56,9 +65,9 @@ def main(kind, out_path):
         pred = shard.sharded_forward(model, plan, xs, G, (gos, gds))
         loss = shard.sharded_mse_loss(plan, pred, ys)
         loss.backward()
-        shard.allreduce_sum_gradients(list(model.parameters()), plan, model)
+        shard.allreduce_sum_gradients(list(model.parameters()), plan, model, over_world=n_groups > 1, scale=1.0 / n_groups)
         torch.cuda.synchronize()
-        ref_pred = pred_w[:, :, plan.row_lo:plan.row_hi] if kind == "row" else pred_w
+        ref_pred = pred_w[s0:s1, :, plan.row_lo:plan.row_hi] if kind in ("row", "rowhyb") else pred_w
         linf, l2 = orc.rel_errors(pred.detach().cpu().numpy(), ref_pred.detach().cpu().numpy())
         rows.append(dict(what=f"nccl world-{world} {kind} shard {prec}: y (rank {rank})", linf=linf, l2=l2, tol=tol_f))
         for k, p in model.named_parameters():

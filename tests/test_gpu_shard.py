@@ -208,3 +208,23 @@ def test_fused_push_epilogue_on_one_gpu(N, g, dyn, cuda_device):
             assert torch.equal(staging[owner][r], local[r][:, owner * rows:(owner + 1) * rows]), f"slot {r} of owner {owner}"
         out = eng.rows_reduce_bias_act([staging[owner].data_ptr() + j * slot for j in range(g)], B, N, owner * rows, rows, C, bias, 1, dev, slots=True)
         _check(out, whole[:, owner * rows:(owner + 1) * rows], 1e-3, f"push N={N} g={g} owner {owner}: summed slots == whole layer rows")
+
+
+def test_hybrid_row_x_batch_shard_nccl_world4(tmp_path):
+    """world 4 = 2 batch groups x 2 row ranks (bench.py --shard row --row-ranks 2) on 4 GPUs: the row exchange (peer memory) stays
+    inside a group, the gradients are summed over all ranks and averaged over the groups; vs the whole model on one GPU."""
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs four GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "res.json"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(HERE, "_shard_nccl_worker.py"), "rowhyb", str(out)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import json
+    res = json.load(open(out))
+    for row in res["rows"]:
+        record_parity(row["what"], row["linf"], row["l2"], row["tol"])
+        assert row["linf"] <= row["tol"] and row["l2"] <= row["tol"], row
