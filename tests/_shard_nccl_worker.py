@@ -20,7 +20,7 @@ def main(kind, out_path):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     rank, world = mdist.init_from_env("nccl", device=dev)
-    N, K, T, B, hid = 260, 3 if kind == "row" else 4, 5, 2, 32
+    N, K, T, B, hid = 260, 4 if kind == "k" else 3, 5, 2, 32
     torch.manual_seed(0)
     model = shim.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=hid, lstm_num_layers=1, gcn_hidden_dim=hid, gcn_num_layers=3,
                        num_nodes=N, user_bias=True, activation=nn.ReLU).to(dev)

@@ -212,7 +212,10 @@ def test_fused_push_epilogue_on_one_gpu(N, g, dyn, cuda_device):
 
 def test_hybrid_row_x_batch_shard_nccl_world4(tmp_path):
     """world 4 = 2 batch groups x 2 row ranks (bench.py --shard row --row-ranks 2) on 4 GPUs: the row exchange (peer memory) stays
-    inside a group, the gradients are summed over all ranks and averaged over the groups; vs the whole model on one GPU."""
+    inside a group, the gradients are summed over all ranks and averaged over the groups; vs the whole model on one GPU.
+    (Round 2, 4 GPUs, K = 4 dense supports: fp32 engine y 1.3e-6, every gradient inside its bound; fp16 engine y rel_L2 8.4e-4 with
+    rel_Linf 8.9e-4 .. 1.02e-3 on a slab -- the fp16 engine's own error at K = 4 dense supports, the K shard measures the same on the
+    whole output -- hence K = 3 here, like the world-2 row test.)"""
     if torch.cuda.device_count() < 4:
         pytest.skip("needs four GPUs")
     with socket.socket() as s:
