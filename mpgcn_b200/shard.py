@@ -201,8 +201,9 @@ class PeerExchange:
     instead of a separate NCCL collective whose kernels compete with the persistent contraction kernels for SMs:
         forward   every rank writes its partial pre-activation into ITS buffer, barrier, `mpgcn_rows_reduce_bias_act` reads the
                   rank's rows out of all g buffers (reduce-scatter + bias + ReLU in one pass);
-        backward  `mpgcn_relu_backward_scatter` masks the rank's dOut rows and stores them into ALL g buffers (all-gather fused
-                  with the mask), barrier, `mpgcn_bdgcn_backward_part` reads the local copy.
+        backward  `mpgcn_relu_backward_scatter[_f16]` masks the rank's dOut rows and stores them into ALL g buffers (all-gather
+                  fused with the mask; tensor-core path: already scaled and cast to fp16, half the bytes), barrier,
+                  `mpgcn_bdgcn_backward_part` reads the local copy.
     Two buffers per direction alternate from layer to layer; with ONE barrier per exchange that is enough: a rank re-uses
     buffer X two layers later, after a barrier that every rank enters only when it is done with the previous use of X."""
 
@@ -230,9 +231,11 @@ class PeerExchange:
 
 
 def _push_enabled() -> bool:
-    """MPGCN_B200_SHARD_PUSH=0: pull the rows in mpgcn_rows_reduce_bias_act instead of pushing them from the FWD_B epilogue (A/B)"""
+    """MPGCN_B200_SHARD_PUSH=1: push every output row of the partial from the FWD_B epilogue into its owner's staging slot (the
+    fused compute + exchange kernel) instead of pulling the rows in mpgcn_rows_reduce_bias_act.  Default off: bit-identical, but
+    measured slower on 2 GPUs (51.9 vs 50.5 ms per step: the epilogue's 32-byte stores land 128 KB apart)."""
     import os
-    return os.environ.get("MPGCN_B200_SHARD_PUSH", "0") == "1"      # default off until measured (tools/gpu_round2_multi_d.sh)
+    return os.environ.get("MPGCN_B200_SHARD_PUSH", "0") == "1"
 
 
 def enable_peer_exchange(plan, device) -> bool:
