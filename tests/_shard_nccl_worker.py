@@ -24,6 +24,9 @@ def main(kind, out_path):
     torch.manual_seed(0)
     model = shim.MPGCN(M=2, K=K, input_dim=1, lstm_hidden_dim=hid, lstm_num_layers=1, gcn_hidden_dim=hid, gcn_num_layers=3,
                        num_nodes=N, user_bias=True, activation=nn.ReLU).to(dev)
+    with torch.no_grad():          # keep both heads alive whatever the init draws (an all-zero prediction would make the comparison vacuous)
+        for m in range(2):
+            model.branch_models[m]['fc'][0].bias.add_(0.5)
     rng = np.random.default_rng(1)
     x = torch.from_numpy((rng.random((B, T, N, N, 1)) * 6).astype(np.float32))
     y = torch.from_numpy((rng.random((B, 1, N, N, 1)) * 2).astype(np.float32))
@@ -58,6 +61,7 @@ def main(kind, out_path):
                 mod.precision = "fp32"
         model.zero_grad(set_to_none=True)
         pred_w = model(x_seq=x.to(dev), G_list=[G, (go.to(dev), gd.to(dev))])
+        assert float((pred_w > 0).float().mean()) > 0.5, "degenerate test case: the whole model's prediction is (almost) all zero"
         nn.functional.mse_loss(pred_w, y.to(dev)).backward()
         want = {k: p.grad.clone() for k, p in model.named_parameters()}
         model.lstm_precision = prec
